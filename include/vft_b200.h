@@ -1,0 +1,123 @@
+/* vft_b200.h -- C ABI of the B200-native QLoRA hot path (NF4 base Linear + LoRA,
+ * forward / backward, and NF4 quantize/pack).
+ *
+ * This is the boundary a maintainer of p1atdev/vision-ft binds instead of
+ * bitsandbytes for this path (see INTEGRATION.md for the ctypes stub).  The
+ * reference has no FFI of its own: the path sits behind Python classes, so each
+ * entry point cites the reference call site (or the bitsandbytes function that
+ * call site reaches) it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch types: raw DEVICE pointers + sizes + an explicit
+ *     cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - nothing is allocated, nothing is freed, no global state; every buffer
+ *     (outputs, saved LoRA activations, workspace) belongs to the caller and is
+ *     borrowed for the duration of the call on the given stream;
+ *   - re-entrant and callable from any host thread (autograd worker threads call
+ *     the backward entry points); the current CUDA device is the caller's;
+ *   - every function returns 0 on success or a negative vft_status; the message
+ *     is in vft_last_error() (thread-local);
+ *   - there is NO CPU fallback: without a CUDA device the compute entry points
+ *     return VFT_ERR_CUDA.
+ *
+ * Shapes: T tokens (batch*seq, flattened), K in_features, N out_features,
+ * r LoRA rank, blocksize 64.  W is [N, K] row-major, quantized over the FLATTENED
+ * tensor: packed[(N*K+1)/2] (element 2j in the HIGH nibble of byte j),
+ * absmax[ceil(N*K/blocksize)] fp32.
+ */
+#ifndef VFT_B200_H_
+#define VFT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFT_ABI_VERSION 1
+#define VFT_LORA_LD 64 /* leading dimension (elements) of the saved LoRA activations t_save / dt_save */
+
+enum vft_dtype { VFT_F32 = 0, VFT_F16 = 1, VFT_BF16 = 2 };
+
+enum vft_status {
+  VFT_OK = 0,
+  VFT_ERR_INVALID = -1,     /* bad argument (null pointer, size, alignment, dtype) */
+  VFT_ERR_UNSUPPORTED = -2, /* valid request this build does not implement */
+  VFT_ERR_CUDA = -3,        /* CUDA runtime / driver error (no device, launch failure) */
+  VFT_ERR_WORKSPACE = -4    /* workspace too small: see vft_workspace_bytes */
+};
+
+/* Which kernel family served the last compute call on this thread. */
+enum vft_path {
+  VFT_PATH_NONE = 0,
+  VFT_PATH_TCGEN05 = 1, /* fused dequant -> tcgen05.mma (TMEM accumulators), sm_100a */
+  VFT_PATH_SIMT = 2     /* generic CUDA-core kernels: shapes the tensor path does not take */
+};
+
+enum vft_op { VFT_OP_FWD = 0, VFT_OP_BWD_DX = 1, VFT_OP_BWD_DAB = 2 };
+
+int vft_abi_version(void);
+const char* vft_last_error(void);
+int vft_last_path(void);
+/* Force a kernel family for subsequent calls on this thread (tests/bench): 0 = auto. */
+void vft_force_path(int path);
+
+/* NF4 quantize/pack.  Replaces bitsandbytes.functional.quantize_4bit(quant_type="nf4")
+ * as called at /root/reference/src/modules/quant/functional.py:362-365 and, lazily, by
+ * Params4bit.cuda() from /root/reference/tools/quantize_model.py:53.
+ *   w       [n] device, dtype in {F32,F16,BF16}
+ *   packed  [(n+1)/2] device uint8 out;  absmax [ceil(n/blocksize)] device fp32 out
+ * Bit-exact contract: absmax = max|float(w)| per block; code = number of NF4
+ * thresholds strictly below float(w) * (1.0f/absmax) (IEEE fp32). */
+int vft_nf4_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t* packed, float* absmax, void* stream);
+
+/* NF4 dequantize (debug / checker entry; the fused kernels never materialise W).
+ * Replaces bitsandbytes.functional.dequantize_4bit.  out[n] in `dtype`. */
+int vft_nf4_dequantize(const uint8_t* packed, const float* absmax, int64_t n, int blocksize, void* out, int dtype,
+                       void* stream);
+
+/* Same two operations with HOST buffers: copies in, kernel, copies out, synchronises.
+ * This is the "reference-facing call with host buffers" used for the e2e numbers and
+ * what quantize_state_dict() (functional.py:342-371: .cuda() ... .cpu()) amounts to. */
+int vft_nf4_quantize_host(const void* w_host, int dtype, int64_t n, int blocksize, uint8_t* packed_host,
+                          float* absmax_host);
+
+/* Scratch the caller must provide for an op (bytes; 0 is possible). */
+int64_t vft_workspace_bytes(int op, int64_t T, int64_t N, int64_t K, int r);
+
+/* Fused forward.  Replaces Linear4bit.forward -> matmul_4bit -> MatMul4Bit.forward
+ * (dequant to a bf16 copy + cuBLAS) reached from
+ * /root/reference/src/modules/peft/lora.py:93, plus the adapter arithmetic of
+ * lora.py:100-104:
+ *     y[T,N] = x[T,K] . W~^T (+ bias) + scale * (x . A^T) . B^T
+ *   act_dtype  dtype of x, y, bias, A, B, t_save: VFT_BF16 or VFT_F16
+ *   qdtype     quant_state.dtype: W~ is rounded to it first, then to act_dtype
+ *   lora_a [r,K] (lora_down.weight), lora_b [N,r] (lora_up.weight); both NULL and
+ *   r = 0 for an NF4-only layer.  scale = alpha / rank.
+ *   t_save [T, VFT_LORA_LD] out: x . A^T rounded to act_dtype, zero padded; required
+ *   when r > 0 (the backward reads it). */
+int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
+                  int blocksize, int act_dtype, int qdtype, const void* bias, const void* lora_a, const void* lora_b,
+                  int r, float scale, void* y, void* t_save, void* ws, int64_t ws_bytes, void* stream);
+
+/* Fused backward w.r.t. the input.  Replaces MatMul4Bit.backward (second dequant +
+ * cuBLAS) and the dX half of the adapter's autograd:
+ *     dt_save[T, VFT_LORA_LD] = scale * dy . B        (rounded to act_dtype)
+ *     dx[T,K] = dy[T,N] . W~ + dt . A
+ * dx may be NULL when only dt_save is wanted (input does not require grad). */
+int vft_qlora_bwd_dx(const void* dy, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
+                     int blocksize, int act_dtype, int qdtype, const void* lora_a, const void* lora_b, int r,
+                     float scale, void* dx, void* dt_save, void* ws, int64_t ws_bytes, void* stream);
+
+/* Adapter weight gradients (autograd of lora.py:100-104):
+ *     dA[r,K] = dt^T . x        dB[N,r] = scale * dy^T . t
+ * with t_save / dt_save as produced by the two calls above.  dA, dB in act_dtype. */
+int vft_lora_bwd_dab(const void* dy, const void* x, const void* t_save, const void* dt_save, int64_t T, int64_t N,
+                     int64_t K, int r, int act_dtype, float scale, void* dA, void* dB, void* ws, int64_t ws_bytes,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFT_B200_H_ */

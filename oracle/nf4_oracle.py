@@ -1,0 +1,167 @@
+"""CPU oracle for the NF4 quantize/pack + dequantize half of the QLoRA hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` may be imported by the
+product path (``vision-ft_b200/``); only ``tests/``, ``__graft_entry__.smoke()``
+and ``bench.py``'s CPU-baseline / ``--impl reference`` legs use it, as the
+checker or as the timed CPU baseline.
+
+PARITY UNPINNED for this file: the arithmetic lives in the third-party
+dependency ``bitsandbytes==0.48.2`` (/root/reference/uv.lock:307-308), which is
+not vendored under /root/reference and is not installable here (no network).
+The reference only *calls* it:
+
+  * /root/reference/src/modules/quant/functional.py:12,362-368
+        ``quantize_4bit(t.cuda(), quant_type="nf4")`` + ``state.as_dict(packed=True)``
+  * /root/reference/src/modules/quant/bnb.py:56-64,94-99,122-129
+        ``bnb.nn.Params4bit`` / ``Params4bit.from_prequantized``
+  * /root/reference/src/modules/peft/lora.py:93  ``self.linear(x)`` -> ``bnb.matmul_4bit``
+
+and its tests hold no golden vectors for codes / absmax / dequantized values
+(/root/reference/tests/test_modules_quant.py:154-193 is a round-trip
+self-consistency check).  What follows restates the *published* bitsandbytes
+blockwise-NF4 algorithm ("[bnb-recall]"):
+
+  absmax_b = max_i |float32(w_i)|            over each 64-element block of the
+                                             FLATTENED weight
+  s_b      = 1.0f / absmax_b                 (IEEE round-to-nearest fp32)
+  x_i      = float32(w_i) * s_b              (one fp32 multiply)
+  code_i   = #{ t in THRESHOLDS : t < x_i }  (== bnb's dQuantizeNF4 '>' tree)
+  byte_j   = code_{2j} << 4 | code_{2j+1}    (odd tail: low nibble 0)
+  dequant  = float32(CODEBOOK[code_i]) * absmax_b  -> rounded to the weight dtype
+
+Edge case adopted (unverified against bnb): an all-zero block has absmax 0,
+s = +inf, x = NaN, every '>' is false -> code 0; it decodes to -1.0 * 0 = -0.0.
+"""
+from __future__ import annotations
+
+import json
+
+import numpy as np
+
+BLOCKSIZE = 64
+
+# fp32-exact NF4 code book (also the ``quant_map`` bitsandbytes stores).
+NF4_CODEBOOK = np.array(
+    [
+        -1.0,
+        -0.6961928009986877,
+        -0.5250730514526367,
+        -0.39491748809814453,
+        -0.28444138169288635,
+        -0.18477343022823334,
+        -0.09105003625154495,
+        0.0,
+        0.07958029955625534,
+        0.16093020141124725,
+        0.24611230194568634,
+        0.33791524171829224,
+        0.44070982933044434,
+        0.5626170039176941,
+        0.7229568362236023,
+        1.0,
+    ],
+    dtype=np.float32,
+)
+
+# The 15 decision thresholds of bitsandbytes' dQuantizeNF4 (float literals).
+NF4_THRESHOLDS = np.array(
+    [
+        -0.8480964004993439,
+        -0.6106329262256622,
+        -0.4599952697753906,
+        -0.33967943489551544,
+        -0.23460740596055984,
+        -0.13791173323988914,
+        -0.045525018125772476,
+        0.03979014977812767,
+        0.1202552504837513,
+        0.2035212516784668,
+        0.2920137718319893,
+        0.3893125355243683,
+        0.5016634166240692,
+        0.6427869200706482,
+        0.8614784181118011,
+    ],
+    dtype=np.float32,
+)
+
+
+def _as_f32(w) -> np.ndarray:
+    """Flatten any array-like (numpy or torch, any float dtype) to float32."""
+    if hasattr(w, "detach"):  # torch tensor; bf16 has no numpy dtype
+        w = w.detach().to("cpu").float().numpy()
+    return np.ascontiguousarray(np.asarray(w, dtype=np.float32).reshape(-1))
+
+
+def nf4_quantize(w, blocksize: int = BLOCKSIZE):
+    """Blockwise NF4 encode + pack.
+
+    Returns ``(packed uint8[(n+1)//2, 1], absmax float32[ceil(n/blocksize)])``
+    exactly as ``bitsandbytes.functional.quantize_4bit`` lays them out
+    (call site: /root/reference/src/modules/quant/functional.py:362-366).
+    """
+    x = _as_f32(w)
+    n = x.size
+    nblocks = (n + blocksize - 1) // blocksize
+    pad = nblocks * blocksize - n
+    xp = np.concatenate([x, np.zeros(pad, np.float32)]) if pad else x
+    blocks = xp.reshape(nblocks, blocksize)
+    absmax = np.abs(blocks).max(axis=1).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        scale = (np.float32(1.0) / absmax).astype(np.float32)
+        scaled = (blocks * scale[:, None]).astype(np.float32)
+    # number of thresholds strictly below x  (NaN -> 0, matching the '>' tree)
+    flat = scaled.reshape(-1)
+    codes = np.searchsorted(NF4_THRESHOLDS, flat, side="left").astype(np.uint8)
+    codes[np.isnan(flat)] = 0
+    codes = codes[:n]
+    if n % 2:
+        codes = np.concatenate([codes, np.zeros(1, np.uint8)])
+    packed = ((codes[0::2] << 4) | codes[1::2]).astype(np.uint8).reshape(-1, 1)
+    return packed, absmax
+
+
+def nf4_unpack(packed, n: int) -> np.ndarray:
+    p = np.asarray(packed, dtype=np.uint8).reshape(-1)
+    codes = np.empty(p.size * 2, np.uint8)
+    codes[0::2] = p >> 4
+    codes[1::2] = p & 0xF
+    return codes[:n]
+
+
+def nf4_dequantize_f32(packed, absmax, n: int, blocksize: int = BLOCKSIZE) -> np.ndarray:
+    """fp32 product ``CODEBOOK[code] * absmax[i // blocksize]`` (before the
+    rounding to ``quant_state.dtype`` that bitsandbytes applies)."""
+    codes = nf4_unpack(packed, n)
+    am = np.asarray(absmax, dtype=np.float32).reshape(-1)
+    idx = np.arange(n) // blocksize
+    return (NF4_CODEBOOK[codes] * am[idx]).astype(np.float32)
+
+
+def nf4_dequantize(packed, absmax, shape, dtype: str = "bfloat16", blocksize: int = BLOCKSIZE):
+    """Dequantize to a torch tensor of ``dtype`` (the stored ``quant_state.dtype``)
+    -- one rounding fp32 -> dtype, as bitsandbytes' kDequantizeBlockwise does."""
+    import torch
+
+    n = int(np.prod(shape))
+    f = nf4_dequantize_f32(packed, absmax, n, blocksize)
+    tdt = {"bfloat16": torch.bfloat16, "float16": torch.float16, "float32": torch.float32}[dtype]
+    return torch.from_numpy(f).to(tdt).reshape(tuple(shape))
+
+
+# ---------------------------------------------------------------------------
+# quant_state (de)serialisation: bitsandbytes ``QuantState.as_dict(packed=True)``
+# key names pinned by /root/reference/tests/test_modules_quant.py:54,183 and
+# corroborated by transformers/quantizers/quantizer_bnb_4bit.py.
+# ---------------------------------------------------------------------------
+def pack_quant_state_blob(shape, dtype: str, blocksize: int = BLOCKSIZE, nested: dict | None = None) -> np.ndarray:
+    meta = {"quant_type": "nf4", "blocksize": int(blocksize), "dtype": dtype, "shape": [int(s) for s in shape]}
+    if nested:
+        meta.update(nested)
+    return np.frombuffer(json.dumps(meta).encode("utf-8"), dtype=np.uint8).copy()
+
+
+def unpack_quant_state_blob(blob) -> dict:
+    if hasattr(blob, "detach"):
+        blob = blob.detach().cpu().numpy()
+    return json.loads(bytes(np.asarray(blob, dtype=np.uint8)).decode("utf-8"))

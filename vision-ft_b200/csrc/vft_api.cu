@@ -1,0 +1,185 @@
+// extern "C" entry points of libvft_b200.so (declared in include/vft_b200.h) and the
+// dispatcher between the tcgen05 family (qlora_tc.cu) and the generic family (qlora_simt.cu).
+#include <stdarg.h>
+
+#include "vft_common.cuh"
+
+namespace vft {
+
+static thread_local char g_error[512] = "";
+static thread_local int g_path = VFT_PATH_NONE;
+static thread_local int g_forced = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+void set_path(int path) { g_path = path; }
+int forced_path() { return g_forced; }
+
+static int check_layer(const LayerArgs& a, const void* act, const void* out, bool out_optional = false) {
+  VFT_REQUIRE(a.T >= 0 && a.N > 0 && a.K > 0, "bad shape T=%lld N=%lld K=%lld", (long long)a.T, (long long)a.N,
+              (long long)a.K);
+  VFT_REQUIRE(a.blocksize >= 2 && a.blocksize % 2 == 0, "bad blocksize %d", a.blocksize);
+  VFT_REQUIRE(a.act_dtype == VFT_BF16 || a.act_dtype == VFT_F16 || a.act_dtype == VFT_F32, "bad act_dtype %d",
+              a.act_dtype);
+  VFT_REQUIRE(a.qdtype == VFT_BF16 || a.qdtype == VFT_F16 || a.qdtype == VFT_F32, "bad qdtype %d", a.qdtype);
+  VFT_REQUIRE(a.packed && a.absmax, "packed/absmax must not be null");
+  VFT_REQUIRE(a.T == 0 || (act && (out || out_optional)), "activation/output pointers must not be null");
+  VFT_REQUIRE(a.r >= 0 && a.r <= VFT_LORA_LD, "LoRA rank %d outside [0, %d]", a.r, VFT_LORA_LD);
+  VFT_REQUIRE((a.r == 0) == (a.lora_a == nullptr) && (a.r == 0) == (a.lora_b == nullptr),
+              "lora_a/lora_b must be given exactly when r > 0");
+  return VFT_OK;
+}
+
+static bool use_tc(const LayerArgs& a, bool backward, int* status) {
+  *status = VFT_OK;
+  const int forced = forced_path();
+  const bool ok = tc_supported(a, backward);
+  if (forced == VFT_PATH_TCGEN05 && !ok) {
+    set_error("tcgen05 path forced but shape/dtype not supported (T=%lld N=%lld K=%lld blocksize=%d dtype=%d)",
+              (long long)a.T, (long long)a.N, (long long)a.K, a.blocksize, a.act_dtype);
+    *status = VFT_ERR_UNSUPPORTED;
+    return false;
+  }
+  if (forced == VFT_PATH_SIMT) return false;
+  return ok;
+}
+
+}  // namespace vft
+
+using namespace vft;
+
+extern "C" {
+
+int vft_abi_version(void) { return VFT_ABI_VERSION; }
+const char* vft_last_error(void) { return g_error; }
+int vft_last_path(void) { return g_path; }
+void vft_force_path(int path) { g_forced = path; }
+
+int vft_nf4_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t* packed, float* absmax,
+                     void* stream) {
+  VFT_REQUIRE(n >= 0, "n must be >= 0");
+  VFT_REQUIRE(n == 0 || (w && packed && absmax), "null pointer");
+  return launch_quantize(w, dtype, n, blocksize, packed, absmax, static_cast<cudaStream_t>(stream));
+}
+
+int vft_nf4_dequantize(const uint8_t* packed, const float* absmax, int64_t n, int blocksize, void* out, int dtype,
+                       void* stream) {
+  VFT_REQUIRE(n >= 0, "n must be >= 0");
+  VFT_REQUIRE(n == 0 || (packed && absmax && out), "null pointer");
+  return launch_dequantize(packed, absmax, n, blocksize, out, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int vft_nf4_quantize_host(const void* w_host, int dtype, int64_t n, int blocksize, uint8_t* packed_host,
+                          float* absmax_host) {
+  VFT_REQUIRE(n >= 0 && blocksize >= 2, "bad n/blocksize");
+  if (n == 0) return VFT_OK;
+  VFT_REQUIRE(w_host && packed_host && absmax_host, "null pointer");
+  const size_t esz = dtype == VFT_F32 ? 4 : 2;
+  const size_t nb_packed = (size_t)(n + 1) / 2, nb_absmax = sizeof(float) * (size_t)((n + blocksize - 1) / blocksize);
+  void *d_w = nullptr, *d_p = nullptr, *d_a = nullptr;
+  cudaStream_t st = nullptr;
+  int rc = VFT_OK;
+  auto cleanup = [&]() {
+    if (d_w) cudaFree(d_w);
+    if (d_p) cudaFree(d_p);
+    if (d_a) cudaFree(d_a);
+    if (st) cudaStreamDestroy(st);
+  };
+#define VFT_HOST_OK(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                       \
+      cleanup();                                                                       \
+      return VFT_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+  VFT_HOST_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  VFT_HOST_OK(cudaMalloc(&d_w, esz * (size_t)n));
+  VFT_HOST_OK(cudaMalloc(&d_p, nb_packed));
+  VFT_HOST_OK(cudaMalloc(&d_a, nb_absmax));
+  VFT_HOST_OK(cudaMemcpyAsync(d_w, w_host, esz * (size_t)n, cudaMemcpyHostToDevice, st));
+  rc = launch_quantize(d_w, dtype, n, blocksize, static_cast<uint8_t*>(d_p), static_cast<float*>(d_a), st);
+  if (rc != VFT_OK) {
+    cleanup();
+    return rc;
+  }
+  VFT_HOST_OK(cudaMemcpyAsync(packed_host, d_p, nb_packed, cudaMemcpyDeviceToHost, st));
+  VFT_HOST_OK(cudaMemcpyAsync(absmax_host, d_a, nb_absmax, cudaMemcpyDeviceToHost, st));
+  VFT_HOST_OK(cudaStreamSynchronize(st));
+#undef VFT_HOST_OK
+  cleanup();
+  return VFT_OK;
+}
+
+int64_t vft_workspace_bytes(int op, int64_t T, int64_t N, int64_t K, int r) {
+  (void)T;
+  if (op == VFT_OP_BWD_DAB) return (int64_t)sizeof(float) * (N + K) * (r > 0 ? r : 0);
+  return 0;
+}
+
+int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
+                  int blocksize, int act_dtype, int qdtype, const void* bias, const void* lora_a, const void* lora_b,
+                  int r, float scale, void* y, void* t_save, void* ws, int64_t ws_bytes, void* stream) {
+  (void)ws;
+  (void)ws_bytes;
+  LayerArgs a{T, N, K, blocksize, act_dtype, qdtype, r, scale, packed, absmax, bias, lora_a, lora_b};
+  int rc = check_layer(a, x, y);
+  if (rc != VFT_OK) return rc;
+  VFT_REQUIRE(r == 0 || t_save != nullptr, "t_save is required when r > 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (r > 0) {
+    rc = simt_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st);
+    if (rc != VFT_OK) return rc;
+  }
+  const bool tc = use_tc(a, false, &rc);
+  if (rc != VFT_OK) return rc;
+  set_path(tc ? VFT_PATH_TCGEN05 : VFT_PATH_SIMT);
+  return tc ? tc_fwd(a, x, y, t_save, st) : simt_fwd(a, x, y, t_save, st);
+}
+
+int vft_qlora_bwd_dx(const void* dy, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
+                     int blocksize, int act_dtype, int qdtype, const void* lora_a, const void* lora_b, int r,
+                     float scale, void* dx, void* dt_save, void* ws, int64_t ws_bytes, void* stream) {
+  (void)ws;
+  (void)ws_bytes;
+  LayerArgs a{T, N, K, blocksize, act_dtype, qdtype, r, scale, packed, absmax, nullptr, lora_a, lora_b};
+  int rc = check_layer(a, dy, dx, /*out_optional=*/true);  // dx == NULL: only dt_save is wanted
+  if (rc != VFT_OK) return rc;
+  VFT_REQUIRE(r == 0 || dt_save != nullptr, "dt_save is required when r > 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (r > 0) {
+    rc = simt_lora_dt(dy, lora_b, T, N, r, scale, act_dtype, dt_save, st);
+    if (rc != VFT_OK) return rc;
+  }
+  if (dx == nullptr) {
+    set_path(VFT_PATH_SIMT);
+    return VFT_OK;
+  }
+  const bool tc = use_tc(a, true, &rc);
+  if (rc != VFT_OK) return rc;
+  set_path(tc ? VFT_PATH_TCGEN05 : VFT_PATH_SIMT);
+  return tc ? tc_bwd_dx(a, dy, dx, dt_save, st) : simt_bwd_dx(a, dy, dx, dt_save, st);
+}
+
+int vft_lora_bwd_dab(const void* dy, const void* x, const void* t_save, const void* dt_save, int64_t T, int64_t N,
+                     int64_t K, int r, int act_dtype, float scale, void* dA, void* dB, void* ws, int64_t ws_bytes,
+                     void* stream) {
+  VFT_REQUIRE(r > 0 && r <= VFT_LORA_LD, "LoRA rank %d outside [1, %d]", r, VFT_LORA_LD);
+  VFT_REQUIRE(T >= 0 && N > 0 && K > 0, "bad shape");
+  VFT_REQUIRE(dA && dB && (T == 0 || (dy && x && t_save && dt_save)), "null pointer");
+  const int64_t need = vft_workspace_bytes(VFT_OP_BWD_DAB, T, N, K, r);
+  if (ws == nullptr || ws_bytes < need) {
+    set_error("workspace too small: need %lld bytes, got %lld", (long long)need, (long long)ws_bytes);
+    return VFT_ERR_WORKSPACE;
+  }
+  set_path(VFT_PATH_SIMT);
+  return simt_dab(dy, x, t_save, dt_save, T, N, K, r, act_dtype, scale, dA, dB, static_cast<float*>(ws),
+                  static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+// Shared helpers for the vft_b200 CUDA sources (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vft_b200.h"
+
+namespace vft {
+
+// ---------------------------------------------------------------------------
+// error plumbing (thread-local message, read through vft_last_error()).
+// ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void set_path(int path);
+int forced_path();
+
+#define VFT_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::vft::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return VFT_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define VFT_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::vft::set_error(__VA_ARGS__);    \
+      return VFT_ERR_INVALID;           \
+    }                                   \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// NF4 constants.  Code book = bitsandbytes' NF4 `quant_map`; thresholds = the 15
+// literals of its dQuantizeNF4 decision tree.
+// ---------------------------------------------------------------------------
+#define VFT_NF4_CODEBOOK                                                                       \
+  {-1.0f, -0.6961928009986877f, -0.5250730514526367f, -0.39491748809814453f,                  \
+   -0.28444138169288635f, -0.18477343022823334f, -0.09105003625154495f, 0.0f,                 \
+   0.07958029955625534f, 0.16093020141124725f, 0.24611230194568634f, 0.33791524171829224f,    \
+   0.44070982933044434f, 0.5626170039176941f, 0.7229568362236023f, 1.0f}
+
+#define VFT_NF4_THRESHOLDS                                                                     \
+  {-0.8480964004993439f, -0.6106329262256622f, -0.4599952697753906f, -0.33967943489551544f,   \
+   -0.23460740596055984f, -0.13791173323988914f, -0.045525018125772476f, 0.03979014977812767f, \
+   0.1202552504837513f, 0.2035212516784668f, 0.2920137718319893f, 0.3893125355243683f,        \
+   0.5016634166240692f, 0.6427869200706482f, 0.8614784181118011f}
+
+__device__ __forceinline__ float nf4_code_value(unsigned c) {
+  // Compile-time table folded into a select chain / constant bank by nvcc.
+  constexpr float kCode[16] = VFT_NF4_CODEBOOK;
+  return kCode[c & 15u];
+}
+
+// ---------------------------------------------------------------------------
+// dtype helpers
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Rounding W~ the way bitsandbytes does: fp32 product -> quant_state.dtype -> activation dtype.
+template <typename ActT>
+__device__ __forceinline__ float round_through(float v, int qdtype) {
+  if (qdtype == VFT_F16) v = __half2float(__float2half_rn(v));
+  else if (qdtype == VFT_BF16) v = __bfloat162float(__float2bfloat16_rn(v));
+  return to_f32<ActT>(from_f32<ActT>(v));
+}
+
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------
+// launchers implemented across the .cu files (all return vft_status)
+// ---------------------------------------------------------------------------
+int launch_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t* packed, float* absmax,
+                    cudaStream_t st);
+int launch_dequantize(const uint8_t* packed, const float* absmax, int64_t n, int blocksize, void* out, int dtype,
+                      cudaStream_t st);
+
+struct LayerArgs {
+  int64_t T, N, K;
+  int blocksize, act_dtype, qdtype, r;
+  float scale;
+  const uint8_t* packed;
+  const float* absmax;
+  const void* bias;
+  const void* lora_a;
+  const void* lora_b;
+};
+
+// generic CUDA-core family
+int simt_lora_down(const void* x, const void* a, int64_t T, int64_t K, int r, int act_dtype, void* t_save,
+                   cudaStream_t st);
+int simt_lora_dt(const void* dy, const void* b, int64_t T, int64_t N, int r, float scale, int act_dtype, void* dt_save,
+                 cudaStream_t st);
+int simt_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st);
+int simt_bwd_dx(const LayerArgs& a, const void* dy, void* dx, const void* dt_save, cudaStream_t st);
+int simt_dab(const void* dy, const void* x, const void* t_save, const void* dt_save, int64_t T, int64_t N, int64_t K,
+             int r, int act_dtype, float scale, void* dA, void* dB, float* ws, cudaStream_t st);
+
+// tcgen05 family
+bool tc_supported(const LayerArgs& a, bool backward);
+int tc_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st);
+int tc_bwd_dx(const LayerArgs& a, const void* dy, void* dx, const void* dt_save, cudaStream_t st);
+
+}  // namespace vft

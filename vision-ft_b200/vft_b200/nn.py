@@ -1,0 +1,282 @@
+"""Module-level containers of the NF4 base layer: ``QuantState``, ``Params4bit``, ``Linear4bit``.
+
+These stand where ``bitsandbytes.functional.QuantState``, ``bitsandbytes.nn.Params4bit``
+and ``bitsandbytes.nn.Linear4bit`` stand under the reference
+(/root/reference/src/modules/quant/bnb.py:6,37,56-64,94-99,122-129): same attribute
+names, same checkpoint key format (``weight.absmax``, ``weight.quant_map``,
+``weight.quant_state.bitsandbytes__nf4`` [+ ``nested_*``]), same "quantize when the
+fp weight first moves to a CUDA device" behaviour -- but backed by libvft_b200.so.
+Only NF4 is implemented (BASELINE.json north_star); fp4 raises.
+"""
+from __future__ import annotations
+
+import json
+from typing import Any
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+NF4_QUANT_MAP = (
+    -1.0, -0.6961928009986877, -0.5250730514526367, -0.39491748809814453,
+    -0.28444138169288635, -0.18477343022823334, -0.09105003625154495, 0.0,
+    0.07958029955625534, 0.16093020141124725, 0.24611230194568634, 0.33791524171829224,
+    0.44070982933044434, 0.5626170039176941, 0.7229568362236023, 1.0,
+)
+_DTYPE_BY_NAME = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}
+_PACKED_KEY = "quant_state.bitsandbytes__"
+
+
+def _dtype_name(dt: torch.dtype) -> str:
+    return str(dt).replace("torch.", "")
+
+
+class QuantState:
+    """Everything needed to decode a packed 4-bit weight (mirror of bitsandbytes' QuantState)."""
+
+    def __init__(self, absmax, shape, dtype, blocksize=64, quant_type="nf4", code=None, offset=None, state2=None):
+        self.absmax = absmax  # fp32 [nblocks] (or uint8 when nested, with state2/offset)
+        self.shape = torch.Size(shape)
+        self.dtype = dtype  # dtype of the ORIGINAL weight; dequantisation rounds to it first
+        self.blocksize = int(blocksize)
+        self.quant_type = quant_type
+        self.code = code if code is not None else torch.tensor(NF4_QUANT_MAP, dtype=torch.float32, device=absmax.device)
+        self.offset = offset
+        self.state2 = state2
+        self.nested = state2 is not None
+
+    # ---- nested ("double quant") statistics: decode only; see DESIGN.md for the encode status
+    def denest(self) -> None:
+        """absmax(uint8) -> fp32: nested_quant_map[absmax] * nested_absmax[i // bs2] + offset (bitsandbytes
+        dequantize_blockwise + offset; formula corroborated by vllm's bitsandbytes loader)."""
+        if not self.nested:
+            return
+        s2 = self.state2
+        idx = self.absmax.to(torch.long).reshape(-1)
+        vals = s2.code.to(idx.device)[idx]
+        scale = s2.absmax.to(idx.device).float().repeat_interleave(s2.blocksize)[: idx.numel()]
+        off = self.offset if torch.is_tensor(self.offset) else torch.tensor(float(self.offset))
+        self.absmax = (vals * scale + off.to(idx.device).float()).float()
+        self.state2, self.offset, self.nested = None, None, False
+
+    def to(self, device) -> "QuantState":
+        self.absmax = self.absmax.to(device)
+        self.code = self.code.to(device)
+        if self.nested:
+            self.offset = self.offset.to(device) if torch.is_tensor(self.offset) else self.offset
+            self.state2.absmax = self.state2.absmax.to(device)
+            self.state2.code = self.state2.code.to(device)
+        return self
+
+    def as_dict(self, packed: bool = False) -> dict[str, Any]:
+        d: dict[str, Any] = {
+            "quant_type": self.quant_type,
+            "absmax": self.absmax,
+            "blocksize": self.blocksize,
+            "quant_map": self.code,
+            "dtype": _dtype_name(self.dtype),
+            "shape": tuple(self.shape),
+        }
+        if self.nested:
+            d.update(
+                {
+                    "nested_absmax": self.state2.absmax,
+                    "nested_blocksize": self.state2.blocksize,
+                    "nested_quant_map": self.state2.code.clone(),
+                    "nested_dtype": _dtype_name(self.state2.dtype),
+                    "nested_offset": float(self.offset),
+                }
+            )
+        if not packed:
+            return d
+        tensors = {k: v for k, v in d.items() if torch.is_tensor(v)}
+        meta = {k: (list(v) if isinstance(v, tuple) else v) for k, v in d.items() if not torch.is_tensor(v)}
+        blob = torch.tensor(list(json.dumps(meta).encode("utf-8")), dtype=torch.uint8)
+        tensors[_PACKED_KEY + self.quant_type] = blob
+        return tensors
+
+    @classmethod
+    def from_dict(cls, qs_dict: dict[str, Any], device) -> "QuantState":
+        qs = dict(qs_dict)
+        blob_keys = [k for k in qs if _PACKED_KEY in k and torch.is_tensor(qs[k])]
+        if len(blob_keys) > 1 or (not blob_keys and "quant_type" not in qs):
+            raise ValueError("expected exactly one packed 'quant_state.bitsandbytes__*' entry or an unpacked dict")
+        if blob_keys:
+            blob = qs.pop(blob_keys[0])
+            qs.update(json.loads(bytes(blob.detach().cpu().to(torch.uint8).tolist()).decode("utf-8")))
+        qs = {k.split(".")[-1]: v for k, v in qs.items()}
+        if qs["quant_type"] != "nf4":
+            raise NotImplementedError(f"vft_b200 implements nf4 only, checkpoint has quant_type={qs['quant_type']!r}")
+        state2 = offset = None
+        if "nested_absmax" in qs:
+            offset = torch.tensor(float(qs["nested_offset"]), device=device)
+            state2 = QuantState(
+                absmax=qs["nested_absmax"].to(device),
+                shape=qs["absmax"].shape,
+                dtype=_DTYPE_BY_NAME[qs["nested_dtype"]],
+                blocksize=qs["nested_blocksize"],
+                quant_type="dynamic8",
+                code=qs["nested_quant_map"].to(device),
+            )
+        return cls(
+            absmax=qs["absmax"].to(device),
+            shape=qs["shape"],
+            dtype=_DTYPE_BY_NAME[qs["dtype"]],
+            blocksize=qs["blocksize"],
+            quant_type=qs["quant_type"],
+            code=qs["quant_map"].to(device),
+            offset=offset,
+            state2=state2,
+        )
+
+
+def quantize_4bit(w: torch.Tensor, blocksize: int = 64, compress_statistics: bool = False, quant_type: str = "nf4",
+                  quant_storage: torch.dtype = torch.uint8) -> tuple[torch.Tensor, QuantState]:
+    """CUDA NF4 quantize/pack (stands where bitsandbytes.functional.quantize_4bit stands,
+    /root/reference/src/modules/quant/functional.py:12,362-365)."""
+    if quant_type != "nf4":
+        raise NotImplementedError(f"vft_b200 implements nf4 only, got quant_type={quant_type!r}")
+    if quant_storage != torch.uint8:
+        raise NotImplementedError("only uint8 quant_storage is implemented")
+    if w.dtype not in _DTYPE_BY_NAME.values():
+        raise ValueError(f"cannot quantize dtype {w.dtype}")
+    packed, absmax = ops.nf4_quantize(w, blocksize)
+    # compress_statistics (nested absmax) is accepted; statistics stay fp32 in this round ("next").
+    return packed, QuantState(absmax=absmax, shape=w.shape, dtype=w.dtype, blocksize=blocksize, quant_type="nf4")
+
+
+def dequantize_4bit(packed: torch.Tensor, quant_state: QuantState) -> torch.Tensor:
+    quant_state.denest()
+    return ops.nf4_dequantize(packed, quant_state.absmax, quant_state.shape, quant_state.dtype, quant_state.blocksize)
+
+
+class Params4bit(torch.nn.Parameter):
+    """Packed 4-bit weight.  Holds fp data until it first reaches a CUDA device, where it is
+    quantized in place (``bnb_quantized`` flips to True and ``quant_state`` appears)."""
+
+    def __new__(cls, data=None, requires_grad=False, quant_state=None, blocksize=64, compress_statistics=True,
+                quant_type="fp4", quant_storage=torch.uint8, module=None, bnb_quantized=False):
+        if data is None:
+            data = torch.empty(0)
+        self = torch.Tensor._make_subclass(cls, data, requires_grad)
+        self.blocksize = blocksize
+        self.compress_statistics = compress_statistics
+        self.quant_type = quant_type
+        self.quant_state = quant_state
+        self.quant_storage = quant_storage
+        self.bnb_quantized = bnb_quantized
+        self.module = module
+        return self
+
+    def __deepcopy__(self, memo):
+        new = type(self).__new__(
+            type(self), self.data.clone(), self.requires_grad, self.quant_state, self.blocksize,
+            self.compress_statistics, self.quant_type, self.quant_storage, self.module, self.bnb_quantized,
+        )
+        return new
+
+    @classmethod
+    def from_prequantized(cls, data, quantized_stats, requires_grad=False, device="cuda", module=None, **kwargs):
+        if str(device).startswith("cuda") and not torch.cuda.is_available():
+            device = data.device  # nothing to run on; keep the packed bytes where they are
+        self = torch.Tensor._make_subclass(cls, data.to(device), requires_grad)
+        self.quant_state = QuantState.from_dict(quantized_stats, device=device)
+        self.quant_state.denest()
+        self.blocksize = self.quant_state.blocksize
+        self.compress_statistics = False
+        self.quant_type = self.quant_state.quant_type
+        self.quant_storage = data.dtype
+        self.bnb_quantized = True
+        self.module = module
+        if module is not None:
+            module.quant_state = self.quant_state
+        return self
+
+    def _quantize(self, device):
+        w = self.data.contiguous().to(device)
+        packed, state = quantize_4bit(w, blocksize=self.blocksize, compress_statistics=self.compress_statistics,
+                                      quant_type=self.quant_type, quant_storage=self.quant_storage)
+        self.data = packed
+        self.quant_state = state
+        if self.module is not None:
+            self.module.quant_state = state
+        self.bnb_quantized = True
+        return self
+
+    def cuda(self, device=None, non_blocking=False):
+        return self.to(device="cuda" if device is None else device, non_blocking=non_blocking)
+
+    def cpu(self):
+        return self.to(device="cpu")
+
+    def to(self, *args, **kwargs):
+        device, dtype, non_blocking, _ = torch._C._nn._parse_to(*args, **kwargs)
+        if device is not None and device.type == "cuda" and not self.bnb_quantized and self.data.device.type != "meta":
+            return self._quantize(device)
+        if self.bnb_quantized:
+            dtype = None  # packed bytes never change dtype
+        new = Params4bit(
+            super().to(device=device, dtype=dtype, non_blocking=non_blocking), requires_grad=self.requires_grad,
+            quant_state=self.quant_state, blocksize=self.blocksize, compress_statistics=self.compress_statistics,
+            quant_type=self.quant_type, quant_storage=self.quant_storage, module=self.module,
+            bnb_quantized=self.bnb_quantized,
+        )
+        if self.quant_state is not None and device is not None:
+            self.quant_state.to(device)
+        return new
+
+
+class Linear4bit(nn.Linear):
+    """NF4 base layer; forward = fused dequant GEMM (stands where bnb.nn.Linear4bit stands)."""
+
+    def __init__(self, input_features, output_features, bias=True, compute_dtype=None, compress_statistics=True,
+                 quant_type="fp4", quant_storage=torch.uint8, device=None):
+        super().__init__(input_features, output_features, bias, device)
+        self.weight = Params4bit(self.weight.data, requires_grad=False, compress_statistics=compress_statistics,
+                                 quant_type=quant_type, quant_storage=quant_storage, module=self)
+        self.compute_dtype = compute_dtype
+        self.quant_state = None
+        self.quant_storage = quant_storage
+
+    def _packed(self):
+        w = self.weight
+        qs = getattr(w, "quant_state", None) or self.quant_state
+        if qs is None or not getattr(w, "bnb_quantized", False):
+            raise RuntimeError(
+                "Linear4bit weight is not quantized yet: move the module to a CUDA device first "
+                "(the NF4 path has no CPU implementation)"
+            )
+        qs.denest()
+        return w.data, qs
+
+    def _cast_input(self, x: torch.Tensor) -> torch.Tensor:
+        if torch.is_autocast_enabled("cuda") and x.is_cuda:
+            return x.to(torch.get_autocast_dtype("cuda"))
+        if self.compute_dtype is not None:
+            return x.to(self.compute_dtype)
+        return x
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        packed, qs = self._packed()
+        inp_dtype = x.dtype
+        x = self._cast_input(x)
+        out = ops.qlora_linear(x, packed, qs.absmax, self.bias, None, None, 0.0, self.out_features, self.in_features,
+                               qs.blocksize, qs.dtype)
+        return out.to(inp_dtype)
+
+    def forward_with_lora(self, x: torch.Tensor, lora_a: torch.Tensor, lora_b: torch.Tensor, scale: float) -> torch.Tensor:
+        """One fused kernel sequence for base + adapter (used by LoRALinear)."""
+        packed, qs = self._packed()
+        inp_dtype = x.dtype
+        x = self._cast_input(x)
+        out = ops.qlora_linear(x, packed, qs.absmax, self.bias, lora_a, lora_b, scale, self.out_features,
+                               self.in_features, qs.blocksize, qs.dtype)
+        return out.to(inp_dtype)
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        qs = getattr(self.weight, "quant_state", None)
+        if qs is not None:
+            for k, v in qs.as_dict(packed=True).items():
+                destination[prefix + "weight." + k] = v if keep_vars else v.detach()

@@ -1,0 +1,182 @@
+"""torch-facing wrappers over the C ABI (libvft_b200.so).
+
+torch is used for device memory, streams and autograd bookkeeping only; every
+arithmetic step of the hot path runs in the hand-written CUDA kernels.  There is
+no CPU path: tensors that are not on a CUDA device raise.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi
+from ._cabi import lib, check
+
+LORA_LD = _cabi.LORA_LD
+_DT = {torch.float32: _cabi.F32, torch.float16: _cabi.F16, torch.bfloat16: _cabi.BF16}
+_DT_NAME = {"float32": _cabi.F32, "float16": _cabi.F16, "bfloat16": _cabi.BF16}
+_TORCH_DT = {v: k for k, v in _DT.items()}
+
+
+def dtype_code(dt) -> int:
+    if isinstance(dt, str):
+        return _DT_NAME[dt.replace("torch.", "")]
+    try:
+        return _DT[dt]
+    except KeyError:
+        raise TypeError(f"vft_b200 supports float32/float16/bfloat16, got {dt}") from None
+
+
+def _require_cuda(*tensors: torch.Tensor | None) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "vft_b200: the NF4/LoRA hot path runs on CUDA (sm_100a) only and has no CPU fallback; "
+                f"got a tensor on {t.device}"
+            )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"vft_b200: tensors on different devices ({dev} vs {t.device})")
+    assert dev is not None
+    return dev
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def last_path() -> int:
+    return lib.vft_last_path()
+
+
+def force_path(path: int) -> None:
+    lib.vft_force_path(path)
+
+
+# ----------------------------------------------------------------------------- NF4 quantize / dequantize
+def nf4_quantize(w: torch.Tensor, blocksize: int = 64) -> tuple[torch.Tensor, torch.Tensor]:
+    """Blockwise NF4 encode + pack of a CUDA tensor -> (packed uint8 [(n+1)//2, 1], absmax fp32 [ceil(n/bs)])."""
+    dev = _require_cuda(w)
+    w = w.contiguous()
+    n = w.numel()
+    packed = torch.empty(((n + 1) // 2, 1), dtype=torch.uint8, device=dev)
+    absmax = torch.empty(((n + blocksize - 1) // blocksize,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.vft_nf4_quantize(w.data_ptr(), dtype_code(w.dtype), n, blocksize, packed.data_ptr(), absmax.data_ptr(), _stream()))
+    return packed, absmax
+
+
+def nf4_dequantize(packed: torch.Tensor, absmax: torch.Tensor, shape, dtype: torch.dtype, blocksize: int = 64) -> torch.Tensor:
+    dev = _require_cuda(packed, absmax)
+    n = 1
+    for s in shape:
+        n *= int(s)
+    out = torch.empty(tuple(shape), dtype=dtype, device=dev)
+    packed = packed.contiguous()
+    absmax = absmax.contiguous().float()
+    with torch.cuda.device(dev):
+        check(lib.vft_nf4_dequantize(packed.data_ptr(), absmax.data_ptr(), n, blocksize, out.data_ptr(), dtype_code(dtype), _stream()))
+    return out
+
+
+def nf4_quantize_host(w: torch.Tensor, blocksize: int = 64) -> tuple[torch.Tensor, torch.Tensor]:
+    """Host-buffer entry (H2D + kernel + D2H inside the C call): what quantize_state_dict amounts to per tensor."""
+    if w.is_cuda:
+        raise RuntimeError("nf4_quantize_host expects a host tensor")
+    w = w.contiguous()
+    n = w.numel()
+    packed = torch.empty(((n + 1) // 2, 1), dtype=torch.uint8)
+    absmax = torch.empty(((n + blocksize - 1) // blocksize,), dtype=torch.float32)
+    check(lib.vft_nf4_quantize_host(w.data_ptr(), dtype_code(w.dtype), n, blocksize, packed.data_ptr(), absmax.data_ptr()))
+    return packed, absmax
+
+
+# ----------------------------------------------------------------------------- fused layer
+class QLoRALinearFunction(torch.autograd.Function):
+    """y = x . W~^T (+bias) + scale * (x . A^T) . B^T with W~ decoded from NF4 inside the GEMM.
+
+    Replaces bitsandbytes.matmul_4bit (MatMul4Bit) under LoRALinear.forward
+    (/root/reference/src/modules/peft/lora.py:92-104).  The base weight is frozen
+    (/root/reference/src/modules/quant/functional.py:115), so only dX, dA, dB exist.
+    """
+
+    @staticmethod
+    def forward(ctx, x, packed, absmax, bias, lora_a, lora_b, scale, out_features, in_features, blocksize, qdtype):
+        dev = _require_cuda(x, packed, absmax, bias, lora_a, lora_b)
+        N, K = int(out_features), int(in_features)
+        if x.shape[-1] != K:
+            raise RuntimeError(f"input feature size {x.shape[-1]} does not match in_features {K}")
+        act = dtype_code(x.dtype)
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        T = x2.shape[0]
+        r = 0 if lora_a is None else int(lora_a.shape[0])
+        if r:
+            if lora_a.dtype != x.dtype or lora_b.dtype != x.dtype:
+                raise RuntimeError("fused LoRA needs adapter weights in the activation dtype")
+            lora_a = lora_a.contiguous()
+            lora_b = lora_b.contiguous()
+        if bias is not None:
+            bias = bias.to(x.dtype).contiguous()
+        y = torch.empty((T, N), dtype=x.dtype, device=dev)
+        t_save = torch.empty((T, LORA_LD), dtype=x.dtype, device=dev) if r else None
+        with torch.cuda.device(dev):
+            check(
+                lib.vft_qlora_fwd(
+                    x2.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, blocksize, act, dtype_code(qdtype),
+                    _ptr(bias), _ptr(lora_a), _ptr(lora_b), r, float(scale), y.data_ptr(), _ptr(t_save), None, 0, _stream(),
+                )
+            )
+        ctx.meta = (N, K, blocksize, act, dtype_code(qdtype), r, float(scale), x.shape)
+        ctx.save_for_backward(x2 if r else None, packed, absmax, lora_a, lora_b, t_save)
+        return y.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, K, blocksize, act, qd, r, scale, x_shape = ctx.meta
+        x2, packed, absmax, lora_a, lora_b, t_save = ctx.saved_tensors
+        dev = dy.device
+        dy2 = dy.reshape(-1, N)
+        if dy2.dtype != _TORCH_DT[act]:
+            dy2 = dy2.to(_TORCH_DT[act])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        T = dy2.shape[0]
+        need_dx = ctx.needs_input_grad[0]
+        need_ab = r > 0 and (ctx.needs_input_grad[4] or ctx.needs_input_grad[5])
+        dx = torch.empty((T, K), dtype=dy2.dtype, device=dev) if need_dx else None
+        dt_save = torch.empty((T, LORA_LD), dtype=dy2.dtype, device=dev) if r else None
+        da = db = None
+        with torch.cuda.device(dev):
+            if need_dx or need_ab:
+                check(
+                    lib.vft_qlora_bwd_dx(
+                        dy2.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, blocksize, act, qd,
+                        _ptr(lora_a), _ptr(lora_b), r, scale, _ptr(dx), _ptr(dt_save), None, 0, _stream(),
+                    )
+                )
+            if need_ab:
+                da = torch.empty_like(lora_a)
+                db = torch.empty_like(lora_b)
+                ws_bytes = lib.vft_workspace_bytes(_cabi.OP_BWD_DAB, T, N, K, r)
+                ws = torch.empty((max(ws_bytes, 4),), dtype=torch.uint8, device=dev)
+                check(
+                    lib.vft_lora_bwd_dab(
+                        dy2.data_ptr(), x2.data_ptr(), t_save.data_ptr(), dt_save.data_ptr(), T, N, K, r, act, scale,
+                        da.data_ptr(), db.data_ptr(), ws.data_ptr(), ws_bytes, _stream(),
+                    )
+                )
+        dxo = dx.reshape(x_shape) if need_dx else None
+        return dxo, None, None, None, da, db, None, None, None, None, None
+
+
+def qlora_linear(x, packed, absmax, bias, lora_a, lora_b, scale, out_features, in_features, blocksize=64, qdtype=torch.bfloat16):
+    return QLoRALinearFunction.apply(x, packed, absmax, bias, lora_a, lora_b, scale, out_features, in_features, blocksize, qdtype)
