@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""Benchmark of the QLoRA hot path on B200 (contract: one JSON line on stdout from rank 0).
+
+Workload (BASELINE.json configs[0], the configuration the metric is quoted on): a single NF4 Linear
+3072x3072 + LoRA r=16, forward + backward (dX, dA, dB) on 4096 tokens per GPU, bf16.  One "step" is one
+forward+backward pass of that layer over one batch of synthetic activations.
+
+  value     whole-job TFLOP/s with inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       same metric through the module API with HOST (pinned) inputs: H2D of x, dy every step, D2H of dA, dB
+  roofline  the dominant kernel (fused NF4-decode tcgen05 GEMM, forward + backward launches) timed alone
+  cpu_baseline  the oracle port (oracle/qlora_oracle.py) on the host cores, bounded sample, rank 0 at N=1 only
+
+`--impl reference` times the reference's CPU path for the same layer (the oracle port: bitsandbytes itself is
+not installable here) on the host cores.  Multi-GPU: weak scaling, each rank steps its own 4096 tokens and the
+LoRA gradients are all-reduced over NCCL on a side stream, overlapped with the next step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "vision-ft_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+N_FEAT = K_FEAT = 3072
+RANK = 16
+TOKENS = 4096
+METRIC = "nf4_lora_linear_fwd_bwd_tflops"
+UNIT = "TFLOP/s"
+
+
+def layer_flops(T, N=N_FEAT, K=K_FEAT, r=RANK):
+    """4*T*N*K + 6*T*r*(N+K)."""
+    return 4 * T * N * K + 6 * T * r * (N + K)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def make_cpu_case(T):
+    import torch
+    from oracle import nf4_oracle, qlora_oracle
+
+    w = (torch.randn(N_FEAT, K_FEAT, generator=torch.Generator().manual_seed(0)) * 0.02).to(torch.bfloat16)
+    p, a = nf4_oracle.nf4_quantize(w)
+    w_deq = qlora_oracle.dequant_weight(p, a, (N_FEAT, K_FEAT), "bfloat16")
+    x = torch.randn(T, K_FEAT, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
+    dy = torch.randn(T, N_FEAT, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16)
+    la = ((torch.rand(RANK, K_FEAT, generator=torch.Generator().manual_seed(3)) * 2 - 1) * (6.0 / K_FEAT) ** 0.5).to(torch.bfloat16)
+    lb = (torch.randn(N_FEAT, RANK, generator=torch.Generator().manual_seed(4)) * 0.02).to(torch.bfloat16)
+    return p, a, w_deq, x, dy, la, lb
+
+
+def cpu_step(case, T):
+    """What the reference does per call on its CPU path: dequantize W to bf16 (forward), F.linear + LoRA,
+    autograd backward (MatMul4Bit.backward dequantizes again)."""
+    from oracle import nf4_oracle, qlora_oracle
+
+    p, a, _, x, dy, la, lb = case
+    w_deq = nf4_oracle.nf4_dequantize(p, a, (N_FEAT, K_FEAT), "bfloat16")  # forward dequant
+    out = qlora_oracle.qlora_linear_ref(x, w_deq, None, la, lb, 1.0, dy)
+    nf4_oracle.nf4_dequantize(p, a, (N_FEAT, K_FEAT), "bfloat16")  # backward dequant
+    return out
+
+
+def time_cpu(T, steps, warmup):
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    case = make_cpu_case(T)
+    for _ in range(warmup):
+        cpu_step(case, T)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_step(case, T)
+        times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    return {"value": layer_flops(T) / mean / 1e12, "ms": mean * 1e3, "cores": torch.get_num_threads()}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    T = 256  # bounded sample of the 4096-token batch (same layer, same seeds)
+    res = time_cpu(T, max(args.steps, 1), max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "single NF4 Linear 3072x3072 + LoRA r=16 fwd+bwd, bf16 (BASELINE configs[0])",
+                   "tokens_per_step": T, "note": "CPU path: dequantize W -> bf16, F.linear + LoRA, autograd backward"},
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+                         "sample": f"{T} of {TOKENS} tokens per step; oracle port of the bitsandbytes+LoRA CPU path "
+                                   "(bitsandbytes 0.48.2 is not installable offline)"},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+        0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def build_layer(device):
+    import torch
+    import torch.nn as nn
+    from src.modules.peft import LoRAConfig, PeftTargetConfig
+    from src.modules.quant import quantize_inplace
+
+    class Model(nn.Module):  # tests/test_modules_quant.py-style (SURVEY.md 8d cfg 1)
+        def __init__(self):
+            super().__init__()
+            self.linear = nn.Linear(K_FEAT, N_FEAT, bias=False, dtype=torch.bfloat16)
+
+    model = Model()
+    with torch.no_grad():
+        model.linear.weight.copy_((torch.randn(N_FEAT, K_FEAT, generator=torch.Generator().manual_seed(0)) * 0.02))
+    quantize_inplace(model, "bnb_nf4", include_keys=["linear"])
+    model.to(device)
+    PeftTargetConfig(config=LoRAConfig(rank=RANK, alpha=1.0, dtype="bfloat16"), include_keys=["linear"]).replace_to_peft_layer(
+        model, freeze_base=True
+    )
+    with torch.no_grad():
+        model.linear.lora_up.weight.copy_(
+            (torch.randn(N_FEAT, RANK, generator=torch.Generator().manual_seed(4)) * 0.02).to(device))
+    return model
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from vft_b200 import _cabi, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the QLoRA hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = measured_peaks()
+    model = build_layer(dev)
+    layer = model.linear
+    params = [layer.lora_down.weight, layer.lora_up.weight]
+    T = TOKENS
+
+    # input sets: rotate so the footprint between two uses of a set exceeds L2 (126 MB)
+    n_sets = 4
+    gens = [torch.Generator(device=dev).manual_seed(1000 * rank + i) for i in range(n_sets)]
+    xs = [torch.randn(2, T // 2, K_FEAT, generator=g, device=dev, dtype=torch.bfloat16).requires_grad_(True) for g in gens]
+    dys = [torch.randn(2, T // 2, N_FEAT, generator=g, device=dev, dtype=torch.bfloat16) for g in gens]
+
+    def step(i):
+        x = xs[i % n_sets]
+        x.grad = None
+        for p in params:
+            p.grad = None
+        y = layer(x)
+        y.backward(dys[i % n_sets])
+
+    # eager warm-up (also compiles nothing: kernels are prebuilt)
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    assert ops.last_path() in (_cabi.PATH_TCGEN05, _cabi.PATH_SIMT)
+
+    # CUDA graphs: one per input set, so launch overhead is off the device timeline
+    graphs, launch_mode = [], "cuda_graph"
+    grad_bufs = []
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(n_sets):
+                step(i)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for i in range(n_sets):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step(i)
+                flat = torch.cat([p.grad.reshape(-1) for p in params])
+            graphs.append(g)
+            grad_bufs.append(flat)
+        torch.cuda.synchronize()
+    except Exception as e:  # pragma: no cover - reported, not hidden
+        print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+        graphs, launch_mode = [], "eager"
+        torch.cuda.synchronize()
+
+    comm = torch.cuda.Stream() if world > 1 else None
+    comm_events = [None] * n_sets
+
+    def run_step(i):
+        s = i % n_sets
+        if comm is not None and comm_events[s] is not None:
+            torch.cuda.current_stream().wait_event(comm_events[s])  # the set's gradients are about to be overwritten
+        if graphs:
+            graphs[s].replay()
+            flat = grad_bufs[s]
+        else:
+            step(i)
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+        if comm is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev)
+                dist.all_reduce(flat)  # LoRA-gradient exchange, overlapped with the next step's kernels
+                done = torch.cuda.Event()
+                done.record()
+            comm_events[s] = done
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        run_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run_step(i)
+    if comm is not None:
+        torch.cuda.current_stream().wait_stream(comm)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # keep the GPU under the same load a little longer if the region was too short to sample clocks
+    t_end = time.time() + 0.25
+    while len(sampler.samples) < 8 and time.time() < t_end:
+        run_step(0)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * layer_flops(T) / (ms_per_step * 1e-3) / 1e12
+
+    # ---- e2e: host (pinned) inputs, H2D every step, D2H of the adapter gradients every step
+    hx = [torch.randn(2, T // 2, K_FEAT, dtype=torch.bfloat16).pin_memory() for _ in range(2)]
+    hdy = [torch.randn(2, T // 2, N_FEAT, dtype=torch.bfloat16).pin_memory() for _ in range(2)]
+    hga = torch.empty(RANK, K_FEAT, dtype=torch.bfloat16).pin_memory()
+    hgb = torch.empty(N_FEAT, RANK, dtype=torch.bfloat16).pin_memory()
+
+    def e2e_step(i):
+        x = hx[i % 2].to(dev, non_blocking=True).requires_grad_(True)
+        dy = hdy[i % 2].to(dev, non_blocking=True)
+        for p in params:
+            p.grad = None
+        layer(x).backward(dy)
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+        hga.copy_(params[0].grad, non_blocking=True)
+        hgb.copy_(params[1].grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the result on the host
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e2e_steps = max(5, min(args.steps, 50))
+    t0 = time.perf_counter()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    c1.record()
+    barrier()
+    e2e_ms = max(c0.elapsed_time(c1), (time.perf_counter() - t0) * 1e3) / e2e_steps  # host-visible time per step
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_val = world * layer_flops(T) / (e2e_ms * 1e-3) / 1e12
+    h2d = hx[0].numel() * 2 + hdy[0].numel() * 2
+    d2h = hga.numel() * 2 + hgb.numel() * 2
+
+    # ---- roofline: the fused tcgen05 GEMM alone (NF4-only call = exactly one launch), forward and backward
+    roof = None
+    if rank == 0:
+        w = layer.linear.weight
+        qs = w.quant_state
+        xk = [torch.randn(T, K_FEAT, device=dev, dtype=torch.bfloat16) for _ in range(n_sets)]
+        gk = [torch.randn(T, N_FEAT, device=dev, dtype=torch.bfloat16) for _ in range(n_sets)]
+        yk = torch.empty(T, N_FEAT, device=dev, dtype=torch.bfloat16)
+        dxk = torch.empty(T, K_FEAT, device=dev, dtype=torch.bfloat16)
+        st = torch.cuda.current_stream().cuda_stream
+
+        def k_fwd(i):
+            _cabi.check(_cabi.lib.vft_qlora_fwd(xk[i % n_sets].data_ptr(), T, w.data_ptr(), qs.absmax.data_ptr(), N_FEAT, K_FEAT, 64,
+                                                _cabi.BF16, _cabi.BF16, None, None, None, 0, 0.0, yk.data_ptr(), None, None, 0, st))
+
+        def k_bwd(i):
+            _cabi.check(_cabi.lib.vft_qlora_bwd_dx(gk[i % n_sets].data_ptr(), T, w.data_ptr(), qs.absmax.data_ptr(), N_FEAT, K_FEAT, 64,
+                                                   _cabi.BF16, _cabi.BF16, None, None, 0, 0.0, dxk.data_ptr(), None, None, 0, st))
+
+        def time_kernel(fn, iters=50):
+            for i in range(5):
+                fn(i)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(iters):
+                fn(i)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / iters
+
+        t_f, t_b = time_kernel(k_fwd), time_kernel(k_bwd)
+        assert ops.last_path() == _cabi.PATH_TCGEN05, "roofline kernel is not the tcgen05 path"
+        flops_launch = 2 * T * N_FEAT * K_FEAT
+        achieved = 2 * flops_launch / ((t_f + t_b) * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": UNIT,
+                "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"] + ", burst",
+                "kernel": "qlora_tc_kernel (fwd + bwd launches)", "fwd_us": t_f * 1e3, "bwd_us": t_b * 1e3,
+                "flops_per_launch": flops_launch}
+
+    # ---- secondary figures of merit (same run, rank 0): quantize/pack GB/s, small-T weight-stream GB/s
+    extra = {}
+    if rank == 0:
+        wq = (torch.randn(8192, 3072, device=dev) * 0.02).to(torch.bfloat16)
+        wq2 = [(torch.randn(8192, 3072, device=dev) * 0.02).to(torch.bfloat16) for _ in range(3)]
+        for t in wq2:
+            ops.nf4_quantize(t)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        iters = 30
+        for i in range(iters):
+            ops.nf4_quantize(wq2[i % 3])
+        b.record()
+        torch.cuda.synchronize()
+        n = wq.numel()
+        q_ms = a.elapsed_time(b) / iters
+        gbs = (2 * n + n / 2 + n / 16) / (q_ms * 1e-3) / 1e9
+        extra["nf4_quantize_pack"] = {"GB/s": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"], "elements": n,
+                                      "bytes_per_element": 2.5625, "note": "includes torch.empty of outputs per call"}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            r = time_cpu(256, 3, 1)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                   "sample": f"256 of {TOKENS} tokens, 1 warm-up + 3 runs of the oracle port (dequant + F.linear + LoRA, autograd)"}
+        kernels_per_step = 7  # lora_down, tc_fwd | lora_dt, tc_bwd, colsum x2, finalize
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "single NF4 Linear 3072x3072 + LoRA r=16 fwd+bwd on 4096 tokens per GPU, bf16 (BASELINE configs[0])",
+                       "N": N_FEAT, "K": K_FEAT, "r": RANK, "tokens_per_gpu": T, "parallelism": f"dp{world}",
+                       "launch": launch_mode,
+                       "l2": f"inputs rotate over {n_sets} sets (x,dy,y,dx = {4 * T * 3072 * 2 * n_sets / 1e6:.0f} MB > 126 MB L2)",
+                       "flops_per_step_per_gpu": layer_flops(T),
+                       "frac_of_measured_bf16_peak": value / world / peaks["bf16_tflops"]},
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+            "gpu_launches": kernels_per_step * args.steps, "clocks": clocks, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

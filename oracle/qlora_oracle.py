@@ -69,7 +69,8 @@ def qlora_linear_ref(
 
 def qlora_linear_truth(x, w_deq, bias, lora_a, lora_b, alpha, dy=None):
     """float64, no intermediate rounding.  Same return layout as qlora_linear_ref."""
-    xd = x.double()
+    lead = x.shape[:-1]
+    xd = x.double().reshape(-1, x.shape[-1])
     wd = w_deq.double()
     y = xd @ wd.t()
     if bias is not None:
@@ -80,16 +81,16 @@ def qlora_linear_truth(x, w_deq, bias, lora_a, lora_b, alpha, dy=None):
         s = float(alpha) / ad.shape[0]
         t = xd @ ad.t()
         y = y + s * (t @ bd.t())
-    out = {"y": y, "dx": None, "da": None, "db": None}
+    out = {"y": y.reshape(*lead, -1), "dx": None, "da": None, "db": None}
     if dy is not None:
-        g = dy.double()
+        g = dy.double().reshape(-1, dy.shape[-1])
         dx = g @ wd
         if lora_a is not None:
             dt = s * (g @ bd)  # [T, r]
             dx = dx + dt @ ad
-            out["da"] = dt.t() @ xd.reshape(-1, xd.shape[-1])
-            out["db"] = s * (g.reshape(-1, g.shape[-1]).t() @ t.reshape(-1, t.shape[-1]))
-        out["dx"] = dx
+            out["da"] = dt.t() @ xd
+            out["db"] = s * (g.t() @ t)
+        out["dx"] = dx.reshape(*lead, -1)
     return out
 
 

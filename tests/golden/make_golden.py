@@ -41,7 +41,7 @@ def nf4_vectors() -> dict:
     for v in list(nf4_oracle.NF4_CODEBOOK) + list(nf4_oracle.NF4_THRESHOLDS):
         v = np.float32(v)
         vals += [np.nextafter(v, np.float32(-2)), v, np.nextafter(v, np.float32(2))]
-    vals = np.array(vals, np.float32)
+    vals = np.clip(np.array(vals, np.float32), -1.0, 1.0)  # keep |x| <= 1 so every block's absmax is the 1.0 anchor
     blocks = []
     for i in range(0, len(vals), 63):  # 63 probes + a 1.0 anchor so absmax == 1
         chunk = vals[i : i + 63]

@@ -1,0 +1,296 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star):
+  * NF4 codes + absmax: BIT-EXACT against oracle/nf4_oracle.py and the committed golden vectors;
+  * dequantized weights: bit-exact;
+  * fused forward / backward: bf16 tolerance, stated here --
+        rel-L2(cuda, oracle_with_reference_roundings) <= 6e-3   (outputs, dX)   2e-2 (dA, dB)
+        rel-L2(cuda, float64 truth)                   <= 4e-3   (outputs, dX)   6e-3 (dA, dB)
+        max-abs(cuda, oracle)                         <= 4 bf16 ulps of the largest reference magnitude
+    (the reference rounds base output, lora_down, lora_up, the scale product and the sum to bf16
+    separately; the fused kernel rounds once, so it sits closer to the truth than the reference does);
+  * size-independent properties at BASELINE.json's full sizes: an identity activation must reproduce the
+    dequantized weight bit for bit through the whole TMA -> decode -> tcgen05 -> TMEM -> epilogue path.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+from safetensors.torch import load_file
+
+pytestmark = pytest.mark.gpu
+
+from oracle import nf4_oracle, qlora_oracle  # noqa: E402  (checker only)
+
+TC, SIMT = 1, 2
+BF16_ULP = 2.0 ** -8
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vft_b200 import ops as _ops
+
+    yield _ops
+    _ops.force_path(0)
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ----------------------------------------------------------------------------- quantize / dequantize
+@pytest.mark.parametrize("name", ["probe", "tail1", "tail63", "tail64", "tail65", "tail127", "odd_rows", "k16", "zero_block"])
+def test_quantize_golden(ops, golden_dir, name):
+    v = load_file(os.path.join(golden_dir, "nf4_vectors.safetensors"))
+    w = v["probe_f32"] if name == "probe" else v[f"{name}_w"]
+    packed, absmax = ops.nf4_quantize(w.cuda())
+    assert packed.dtype == torch.uint8 and packed.shape == ((w.numel() + 1) // 2, 1)
+    assert torch.equal(packed.cpu(), v[f"{name}_packed"])
+    assert torch.equal(absmax.cpu(), v[f"{name}_absmax"])
+
+
+@pytest.mark.parametrize("dt_name,dt", [("bfloat16", torch.bfloat16), ("float16", torch.float16)])
+def test_quantize_seeded_3072_hash(ops, golden_dir, dt_name, dt):
+    ref = json.load(open(os.path.join(golden_dir, "nf4_hashes.json")))[dt_name]
+    g = torch.Generator().manual_seed(ref["seed"])
+    w = (torch.randn(*ref["shape"], generator=g) * ref["std"]).to(dt)
+    packed, absmax = ops.nf4_quantize(w.cuda())
+    assert _sha(packed.cpu().numpy()) == ref["packed_sha256"]
+    assert _sha(absmax.cpu().numpy()) == ref["absmax_sha256"]
+    # host-buffer entry point gives the same bytes
+    p2, a2 = ops.nf4_quantize_host(w)
+    assert torch.equal(p2, packed.cpu()) and torch.equal(a2, absmax.cpu())
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n", [1, 2, 1023, 1024, 1025, 4096 + 64 + 3, 3 * 1024 * 37 + 5])
+def test_quantize_random_sizes(ops, dt, n):
+    g = torch.Generator().manual_seed(n)
+    w = (torch.randn(n, generator=g) * 0.05).to(dt)
+    w[::97] = 0
+    packed, absmax = ops.nf4_quantize(w.cuda())
+    p, a = nf4_oracle.nf4_quantize(w)
+    assert np.array_equal(packed.cpu().numpy(), p) and np.array_equal(absmax.cpu().numpy(), a)
+    # misaligned base pointer takes the generic kernel
+    if n > 8:
+        buf = torch.empty(n + 1, dtype=dt, device="cuda")
+        buf[1:] = w.cuda()
+        p3, a3 = ops.nf4_quantize(buf[1:])
+        assert np.array_equal(p3.cpu().numpy(), p) and np.array_equal(a3.cpu().numpy(), a)
+
+
+@pytest.mark.parametrize("blocksize", [128, 256, 4096])
+def test_quantize_other_blocksizes(ops, blocksize):
+    g = torch.Generator().manual_seed(blocksize)
+    w = (torch.randn(5 * 4096 + 77, generator=g) * 0.02).to(torch.bfloat16)
+    packed, absmax = ops.nf4_quantize(w.cuda(), blocksize)
+    p, a = nf4_oracle.nf4_quantize(w, blocksize)
+    assert np.array_equal(packed.cpu().numpy(), p) and np.array_equal(absmax.cpu().numpy(), a)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(1,), (63,), (48, 16), (257, 129), (3072, 3072)])
+def test_dequantize_bit_exact(ops, dt, shape):
+    g = torch.Generator().manual_seed(len(shape) + shape[0])
+    w = (torch.randn(*shape, generator=g) * 0.02).to(dt)
+    p, a = nf4_oracle.nf4_quantize(w)
+    want = nf4_oracle.nf4_dequantize(p, a, shape, str(dt).replace("torch.", ""))
+    got = ops.nf4_dequantize(torch.from_numpy(p).cuda(), torch.from_numpy(a).cuda(), shape, dt)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_quantize_idempotent_full_size(ops):
+    g = torch.Generator(device="cuda").manual_seed(7)
+    w = (torch.randn(8192, 3072, generator=g, device="cuda") * 0.02).to(torch.bfloat16)
+    p, a = ops.nf4_quantize(w)
+    d = ops.nf4_dequantize(p, a, w.shape, torch.bfloat16)
+    p2, a2 = ops.nf4_quantize(d)
+    assert torch.equal(p, p2)
+    assert torch.equal(a2, d.float().abs().reshape(-1, 64).amax(dim=1))
+
+
+# ----------------------------------------------------------------------------- fused layer
+def _make_case(T, K, N, r, seed, dt=torch.bfloat16, bias=False, qdt=None, lead=None):
+    g = torch.Generator().manual_seed(seed)
+    qdt = qdt or dt
+    w = (torch.randn(N, K, generator=g) * 0.02).to(qdt)
+    x = torch.randn(T, K, generator=g).to(dt)
+    dy = torch.randn(T, N, generator=g).to(dt)
+    a = ((torch.rand(r, K, generator=g) * 2 - 1) * (6.0 / K) ** 0.5).to(dt) if r else None
+    b = (torch.randn(N, r, generator=g) * 0.02).to(dt) if r else None
+    bv = (torch.randn(N, generator=g) * 0.1).to(dt) if bias else None
+    if lead:
+        x, dy = x.reshape(*lead, K), dy.reshape(*lead, N)
+    return w, x, dy, a, b, bv
+
+
+def _run_cuda(ops, packed, absmax, x, dy, a, b, bias, alpha, N, K, qdt, path):
+    ops.force_path(path)
+    xc = x.cuda().requires_grad_(True)
+    ac = a.cuda().requires_grad_(True) if a is not None else None
+    bc = b.cuda().requires_grad_(True) if b is not None else None
+    scale = alpha / a.shape[0] if a is not None else 0.0
+    y = ops.qlora_linear(xc, packed, absmax, None if bias is None else bias.cuda(), ac, bc, scale, N, K, 64, qdt)
+    used_fwd = ops.last_path()
+    y.backward(dy.cuda())
+    torch.cuda.synchronize()
+    ops.force_path(0)
+    out = {"y": y.detach().cpu(), "dx": xc.grad.cpu(), "da": None, "db": None}
+    if a is not None:
+        out["da"], out["db"] = ac.grad.cpu(), bc.grad.cpu()
+    return out, used_fwd
+
+
+def _check(out, ref, truth, keys, what):
+    for k in keys:
+        lim_ref, lim_truth = (6e-3, 4e-3) if k in ("y", "dx") else (2e-2, 6e-3)
+        e_ref = qlora_oracle.rel_l2(out[k], ref[k])
+        e_truth = qlora_oracle.rel_l2(out[k], truth[k])
+        assert e_ref <= lim_ref, f"{what}:{k} rel-L2 vs reference-rounding oracle {e_ref:.3e} > {lim_ref}"
+        assert e_truth <= lim_truth, f"{what}:{k} rel-L2 vs fp64 truth {e_truth:.3e} > {lim_truth}"
+        scale = float(ref[k].float().abs().max())
+        assert qlora_oracle.max_abs(out[k], ref[k]) <= 4 * BF16_ULP * scale + 1e-6, f"{what}:{k} max-abs"
+
+
+CASES = [
+    # T, K, N, r, bias, lead
+    (96, 128, 192, 16, False, (2, 48)),
+    (40, 64, 128, 4, True, None),
+    (300, 256, 384, 16, False, None),   # ragged T: one full + one partial 256-token tile
+    (77, 2048, 640, 8, True, None),     # SDXL attn2.to_k on 77 text tokens
+    (1, 640, 640, 16, False, None),     # single token
+    (528, 640, 5120, 16, True, None),   # SDXL ff.net.0.proj, C=640, ragged bucket
+    (264, 3072, 384, 0, False, None),   # NF4-only (AuraFlow double-layer w1*, mlpC)
+]
+
+
+@pytest.mark.parametrize("path", [TC, SIMT])
+@pytest.mark.parametrize("T,K,N,r,bias,lead", CASES)
+def test_layer_fwd_bwd_vs_oracle(ops, T, K, N, r, bias, lead, path):
+    w, x, dy, a, b, bv = _make_case(T, K, N, r, seed=T + K + N + r, bias=bias, lead=lead)
+    p, am = nf4_oracle.nf4_quantize(w)
+    w_deq = qlora_oracle.dequant_weight(p, am, (N, K), "bfloat16")
+    ref = qlora_oracle.qlora_linear_ref(x, w_deq, bv, a, b, 1.0, dy)
+    truth = qlora_oracle.qlora_linear_truth(x, w_deq, bv, a, b, 1.0, dy)
+    out, used = _run_cuda(ops, torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), x, dy, a, b, bv, 1.0, N, K,
+                          torch.bfloat16, path)
+    assert used == path
+    _check(out, ref, truth, ("y", "dx") + (("da", "db") if r else ()), f"T{T}K{K}N{N}r{r}p{path}")
+
+
+def test_golden_lora_vectors_both_paths(ops, golden_dir):
+    """The committed fixtures computed by the REFERENCE's LoRALinear (tests/golden/make_golden.py)."""
+    v = load_file(os.path.join(golden_dir, "lora_vectors.safetensors"))
+    for name in ("r16", "r4_bias"):
+        N, K = v[f"{name}_w"].shape
+        ref = {k: v[f"{name}_{k}"] for k in ("y", "dx", "da", "db")}
+        for path in (TC, SIMT):
+            out, used = _run_cuda(ops, v[f"{name}_packed"].cuda(), v[f"{name}_absmax"].cuda(), v[f"{name}_x"],
+                                  v[f"{name}_dy"], v[f"{name}_a"], v[f"{name}_b"], v.get(f"{name}_bias"),
+                                  float(v[f"{name}_alpha"]), N, K, torch.bfloat16, path)
+            assert used == path
+            for k in ("y", "dx"):
+                assert qlora_oracle.rel_l2(out[k], ref[k]) <= 6e-3, (name, path, k)
+            for k in ("da", "db"):
+                assert qlora_oracle.rel_l2(out[k], ref[k]) <= 2e-2, (name, path, k)
+
+
+def test_k16_layer_blocks_span_rows(ops):
+    """AuraFlow init_x_linear: K = 16, absmax blocks cover 4 rows -> generic kernels, with bias."""
+    w, x, dy, a, b, bv = _make_case(520, 16, 3072, 0, seed=16, bias=True)
+    p, am = nf4_oracle.nf4_quantize(w)
+    w_deq = qlora_oracle.dequant_weight(p, am, (3072, 16), "bfloat16")
+    ref = qlora_oracle.qlora_linear_ref(x, w_deq, bv, None, None, 1.0, dy)
+    truth = qlora_oracle.qlora_linear_truth(x, w_deq, bv, None, None, 1.0, dy)
+    out, used = _run_cuda(ops, torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), x, dy, None, None, bv, 1.0,
+                          3072, 16, torch.bfloat16, 0)
+    assert used == SIMT
+    _check(out, ref, truth, ("y", "dx"), "k16")
+
+
+def test_fp16_checkpoint_bf16_activations(ops):
+    """quant_state.dtype = float16 (AuraFlow ships fp16): W~ is rounded fp32 -> fp16 -> bf16."""
+    w, x, dy, a, b, bv = _make_case(200, 128, 256, 16, seed=3, qdt=torch.float16)
+    p, am = nf4_oracle.nf4_quantize(w)
+    w_deq = qlora_oracle.dequant_weight(p, am, (256, 128), "float16")
+    ref = qlora_oracle.qlora_linear_ref(x, w_deq, None, a, b, 1.0, dy)
+    truth = qlora_oracle.qlora_linear_truth(x, w_deq.to(torch.bfloat16), None, a, b, 1.0, dy)
+    for path in (TC, SIMT):
+        out, used = _run_cuda(ops, torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), x, dy, a, b, None, 1.0, 256,
+                              128, torch.float16, path)
+        assert used == path
+        _check(out, ref, truth, ("y", "dx", "da", "db"), f"fp16ckpt-p{path}")
+
+
+def test_fp16_activations(ops):
+    w, x, dy, a, b, bv = _make_case(130, 192, 128, 8, seed=11, dt=torch.float16)
+    x, dy = x * 0.5, dy * 0.5
+    p, am = nf4_oracle.nf4_quantize(w)
+    w_deq = qlora_oracle.dequant_weight(p, am, (128, 192), "float16")
+    truth = qlora_oracle.qlora_linear_truth(x, w_deq, None, a, b, 1.0, dy)
+    for path in (TC, SIMT):
+        out, used = _run_cuda(ops, torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), x, dy, a, b, None, 1.0, 128,
+                              192, torch.float16, path)
+        assert used == path
+        for k in ("y", "dx", "da", "db"):
+            assert qlora_oracle.rel_l2(out[k], truth[k]) <= 2e-3, (path, k)
+
+
+@pytest.mark.parametrize("N,K", [(3072, 3072), (8192, 3072), (3072, 8192)])
+def test_identity_activation_reproduces_weight_bit_exact(ops, N, K):
+    """Size-independent property at full size: x = I_K  =>  y[k, :] = W~[:, k] exactly (single non-zero term per
+    dot product), and dy = I_N => dx[n, :] = W~[n, :] exactly.  Exercises every tile, stage and lane of the
+    tcgen05 path and compares with the standalone (bit-exact-tested) dequantize kernel."""
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    w = (torch.randn(N, K, generator=g, device="cuda") * 0.02).to(torch.bfloat16)
+    packed, absmax = ops.nf4_quantize(w)
+    w_deq = ops.nf4_dequantize(packed, absmax, (N, K), torch.bfloat16)
+    ops.force_path(TC)
+    eye_k = torch.eye(K, dtype=torch.bfloat16, device="cuda").requires_grad_(True)
+    y = ops.qlora_linear(eye_k, packed, absmax, None, None, None, 0.0, N, K, 64, torch.bfloat16)
+    assert ops.last_path() == TC
+    assert torch.equal(y.detach(), w_deq.t())
+    x = torch.zeros(N, K, dtype=torch.bfloat16, device="cuda", requires_grad=True)
+    y2 = ops.qlora_linear(x, packed, absmax, None, None, None, 0.0, N, K, 64, torch.bfloat16)
+    y2.backward(torch.eye(N, dtype=torch.bfloat16, device="cuda"))
+    ops.force_path(0)
+    assert torch.equal(x.grad, w_deq)
+
+
+def test_config1_full_size_vs_oracle(ops):
+    """BASELINE.json config #1: 3072x3072 NF4 + LoRA r=16, 4096 tokens as [2, 2048, 3072] (SURVEY.md 8d seeds)."""
+    N = K = 3072
+    T, r = 4096, 16
+    w = (torch.randn(N, K, generator=torch.Generator().manual_seed(0)) * 0.02).to(torch.bfloat16)
+    x = torch.randn(2, T // 2, K, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
+    dy = torch.randn(2, T // 2, N, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16)
+    a = torch.empty(r, K)
+    torch.manual_seed(3)
+    torch.nn.init.kaiming_uniform_(a)
+    a = a.to(torch.bfloat16)
+    b = (torch.randn(N, r, generator=torch.Generator().manual_seed(4)) * 0.02).to(torch.bfloat16)
+    packed, absmax = ops.nf4_quantize(w.cuda())
+    p, am = packed.cpu().numpy(), absmax.cpu().numpy()
+    w_deq = qlora_oracle.dequant_weight(p, am, (N, K), "bfloat16")
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = qlora_oracle.qlora_linear_ref(x, w_deq, None, a, b, 1.0, dy)
+    truth = qlora_oracle.qlora_linear_truth(x, w_deq, None, a, b, 1.0, dy)
+    out, used = _run_cuda(ops, packed, absmax, x, dy, a, b, None, 1.0, N, K, torch.bfloat16, 0)
+    assert used == TC
+    _check(out, ref, truth, ("y", "dx", "da", "db"), "config1")
+
+
+def test_auto_dispatch_reports_path(ops):
+    w, x, dy, a, b, bv = _make_case(64, 64, 128, 0, seed=1)
+    p, am = nf4_oracle.nf4_quantize(w)
+    ops.force_path(0)
+    ops.qlora_linear(x.cuda(), torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), None, None, None, 0.0, 128, 64,
+                     64, torch.bfloat16)
+    assert ops.last_path() == TC
+    xf = x.float().cuda()  # fp32 activations are not a tensor-core case
+    ops.qlora_linear(xf, torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), None, None, None, 0.0, 128, 64, 64,
+                     torch.bfloat16)
+    assert ops.last_path() == SIMT

@@ -1,0 +1,232 @@
+"""Module surgery + checkpoint behaviour of the quant API, in the style of
+/root/reference/tests/test_modules_quant.py (same model shapes and assertions; NF4 only)."""
+import pytest
+import torch
+import torch.nn as nn
+
+from src.modules.quant import (
+    BnbLinear4bit,
+    quantize_inplace,
+    quantize_state_dict,
+    replace_by_prequantized_weights,
+    replace_to_quant_linear,
+    validate_quant_type,
+)
+from src.modules.quant.functional import collect_children_dict, get_quant_type_from_children_dict
+
+
+def test_collect_children_keys():
+    cases = [
+        ("abc.def.", {"abc.def.0": 0, "abc.def.1": 0, "abc.def.2": 0, "abc.ooo": 0}, ["0", "1", "2"]),
+        ("abc.def.", {"abc.def.ghi.jkl": 0}, ["ghi.jkl"]),
+        ("abc.def.", {"XYZ": 0}, []),
+    ]
+    for prefix, sd, expected in cases:
+        assert set(collect_children_dict(prefix, sd).keys()) == set(expected)
+
+
+def test_get_quant_type_from_children_keys():
+    z = torch.zeros(1)
+    cases = [
+        ({"absmax": z, "quant_state.bitsandbytes__nf4": z}, "bnb_nf4"),
+        ({"quant_map": z, "quant_state.bitsandbytes__fp4": z}, "bnb_fp4"),
+        ({"weight_format": z}, "bnb_int8"),
+        ({"_data": torch.zeros(1, dtype=torch.int8)}, "quanto_int8"),
+        ({"_data._data": torch.zeros(1, dtype=torch.uint8)}, "quanto_int4"),
+    ]
+    for keys, expected in cases:
+        assert get_quant_type_from_children_dict(keys) == expected
+    with pytest.raises(ValueError):
+        get_quant_type_from_children_dict({"foo": z})
+
+
+def test_validate_quant_type():
+    for q in ["fp8_e4m3fn", "bnb_int8", "bnb_fp4", "bnb_nf4", "quanto_int4", "quanto_int8", "ao_nf4", "ao_fp8"]:
+        validate_quant_type(q)
+    with pytest.raises(ValueError):
+        validate_quant_type("bnb_nf8")
+
+
+class _Model(nn.Module):
+    def __init__(self, dtype=None):
+        super().__init__()
+        self.linear = nn.Linear(128, 256, bias=True, dtype=dtype)
+        self.non_quant = nn.Linear(128, 256, bias=True, dtype=dtype)
+
+
+@torch.no_grad()
+def test_replace_to_quant_linear():
+    model = replace_to_quant_linear(_Model(), quant_type="bnb_nf4", include_keys=["linear"], exclude_keys=[])
+    assert isinstance(model.linear, BnbLinear4bit) and isinstance(model.linear, nn.Linear)
+    assert not isinstance(model.non_quant, BnbLinear4bit)
+    assert model.linear.weight.device.type == "meta" and model.linear.quant_type == "nf4"
+    assert (model.linear.in_features, model.linear.out_features) == (128, 256)
+    assert not any(p.requires_grad for p in model.linear.parameters())
+
+
+@torch.no_grad()
+def test_quantize_inplace_keeps_weights_until_cuda():
+    model = _Model()
+    w = model.linear.weight.detach().clone()
+    quantize_inplace(model, quant_type="bnb_nf4", include_keys=["linear"], exclude_keys=[])
+    assert isinstance(model.linear, BnbLinear4bit)
+    assert torch.equal(model.linear.weight.data, w) and not model.linear.weight.bnb_quantized
+    assert model.linear.compress_statistics is True and model.linear.quant_storage == torch.uint8
+
+
+@torch.no_grad()
+def test_other_backends_raise_not_implemented():
+    for q in ("bnb_fp4", "bnb_int8", "ao_nf4", "ao_fp8", "quanto_int8"):
+        with pytest.raises(NotImplementedError):
+            replace_to_quant_linear(_Model(), quant_type=q, include_keys=["linear"])
+    with pytest.raises(NotImplementedError):
+        quantize_state_dict({}, "bnb_int8", ["x"])
+    with pytest.raises(ValueError):
+        replace_to_quant_linear(_Model(), quant_type="nope", include_keys=["linear"])
+
+
+@torch.no_grad()
+def test_prequantized_checkpoint_loads_on_cpu():
+    """bnb-format keys -> BnbLinear4bit with packed uint8 weight + quant state; state_dict round-trips the keys."""
+    from oracle import nf4_oracle  # fixture generator only
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.linear = nn.Linear(16, 32, bias=True)
+            self.non_quant = nn.Linear(16, 32, bias=True)
+
+    src = M()
+    sd = src.state_dict()
+    p, a = nf4_oracle.nf4_quantize(sd["linear.weight"])
+    sd["linear.weight"] = torch.from_numpy(p)
+    sd["linear.weight.absmax"] = torch.from_numpy(a)
+    sd["linear.weight.quant_map"] = torch.from_numpy(nf4_oracle.NF4_CODEBOOK.copy())
+    sd["linear.weight.quant_state.bitsandbytes__nf4"] = torch.from_numpy(nf4_oracle.pack_quant_state_blob((32, 16), "float32"))
+
+    model = M()
+    replace_by_prequantized_weights(model, sd)
+    assert isinstance(model.linear, BnbLinear4bit) and not isinstance(model.non_quant, BnbLinear4bit)
+    model.load_state_dict(sd)
+    assert model.linear.weight.dtype == torch.uint8 and model.linear.weight.bnb_quantized
+    assert tuple(model.linear.weight.quant_state.shape) == (32, 16)
+    out = model.state_dict()
+    for k in sd:
+        assert k in out, k
+    assert torch.equal(out["linear.weight"], sd["linear.weight"])
+    assert torch.equal(out["linear.weight.absmax"], sd["linear.weight.absmax"])
+    assert bytes(out["linear.weight.quant_state.bitsandbytes__nf4"].tolist()) == bytes(
+        sd["linear.weight.quant_state.bitsandbytes__nf4"].tolist()
+    )
+
+
+@torch.no_grad()
+def test_nested_absmax_checkpoint_is_denested_on_load():
+    """compress_statistics=True checkpoints (tools/quantize_model.py output): absmax uint8 + nested_* keys."""
+    import json
+
+    absmax = torch.rand(512) * 0.1 + 0.01
+    offset = absmax.mean()
+    code = torch.linspace(-1, 1, 256)
+    centered = (absmax - offset).reshape(2, 256)
+    am2 = centered.abs().amax(dim=1)
+    idx = ((centered / am2[:, None])[:, :, None] - code[None, None, :]).abs().argmin(dim=2).to(torch.uint8)
+    want = (code[idx.long()] * am2[:, None]).reshape(-1) + offset
+    meta = {"quant_type": "nf4", "blocksize": 64, "dtype": "bfloat16", "shape": [128, 256],
+            "nested_blocksize": 256, "nested_dtype": "float32", "nested_offset": float(offset)}
+    stats = {
+        "absmax": idx.reshape(-1),
+        "quant_map": torch.zeros(16),
+        "nested_absmax": am2,
+        "nested_quant_map": code,
+        "quant_state.bitsandbytes__nf4": torch.tensor(list(json.dumps(meta).encode()), dtype=torch.uint8),
+    }
+    from vft_b200.nn import Params4bit
+
+    w = Params4bit.from_prequantized(torch.zeros(128 * 256 // 2, 1, dtype=torch.uint8), stats, device="cpu")
+    assert w.quant_state.absmax.dtype == torch.float32 and not w.quant_state.nested
+    assert torch.allclose(w.quant_state.absmax, want, atol=1e-7)
+
+
+# ----------------------------------------------------------------------------- GPU: the reference's numeric tests
+@pytest.mark.gpu
+@torch.no_grad()
+def test_bnb_load_prequantized():
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.linear = nn.Linear(16, 32, bias=True)
+            self.non_quant = nn.Linear(16, 32, bias=True)
+
+    model = M()
+    state_dict = quantize_state_dict(model.state_dict(), quant_type="bnb_nf4", include_keys=["linear.weight"], exclude_keys=[])
+    assert state_dict["linear.weight"].dtype == torch.uint8 and state_dict["linear.weight"].shape == (256, 1)
+    assert "linear.weight.quant_state.bitsandbytes__nf4" in state_dict and "non_quant.weight.absmax" not in state_dict
+    model = M()
+    replace_by_prequantized_weights(model, state_dict)
+    model.load_state_dict(state_dict)
+    assert isinstance(model.linear, BnbLinear4bit)
+
+
+@pytest.mark.gpu
+@torch.no_grad()
+def test_bnb_quantize_inplace_and_load():
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.linear = nn.Linear(16, 32, bias=True, dtype=torch.float16)
+            self.non_quant = nn.Linear(32, 32, bias=True, dtype=torch.float16)
+
+        def forward(self, x):
+            return self.non_quant(self.linear(x))
+
+    model = M()
+    quantize_inplace(model, quant_type="bnb_nf4", include_keys=["linear"], exclude_keys=[])
+    model.cuda()  # do quantization
+    state_dict = model.state_dict()
+    assert state_dict["linear.weight"].dtype == torch.uint8
+
+    inputs = torch.randn(1, 16, dtype=torch.float16).to("cuda")
+    output = model(inputs)
+    assert output.dtype == torch.float16
+
+    del model
+    model = M()
+    assert "linear.weight.quant_state.bitsandbytes__nf4" in state_dict.keys()
+    replace_by_prequantized_weights(model, state_dict)
+    model.load_state_dict(state_dict)
+    model.cuda()
+    assert model.linear.weight.dtype == torch.uint8
+
+    output_2 = model(inputs)
+    assert torch.allclose(output, output_2)
+
+
+@pytest.mark.gpu
+@torch.no_grad()
+def test_quantized_module_matches_oracle_and_moves_between_devices():
+    from oracle import nf4_oracle, qlora_oracle
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.linear = nn.Linear(128, 256, bias=True, dtype=torch.bfloat16)
+
+    model = M()
+    w, b = model.linear.weight.detach().clone(), model.linear.bias.detach().clone()
+    quantize_inplace(model, "bnb_nf4", include_keys=["linear"])
+    model.cuda()
+    p, a = nf4_oracle.nf4_quantize(w)
+    assert torch.equal(model.linear.weight.data.cpu(), torch.from_numpy(p))
+    assert torch.equal(model.linear.weight.quant_state.absmax.cpu(), torch.from_numpy(a))
+    x = torch.randn(3, 50, 128, dtype=torch.bfloat16)
+    y = model.linear(x.cuda())
+    ref = qlora_oracle.qlora_linear_ref(x, qlora_oracle.dequant_weight(p, a, (256, 128)), b, None, None, 1.0)["y"]
+    assert y.shape == (3, 50, 256) and qlora_oracle.rel_l2(y.cpu(), ref) < 6e-3
+    # cuda -> cpu -> cuda keeps the packed weight and its state
+    model.cpu()
+    assert model.linear.weight.dtype == torch.uint8 and model.linear.weight.device.type == "cpu"
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.linear(x)
+    model.cuda()
+    assert torch.equal(model.linear(x.cuda()), y)

@@ -1,0 +1,120 @@
+"""CPU: the oracle against the committed golden vectors and against its own C restatement."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+from safetensors.torch import load_file
+
+from oracle import c_oracle, nf4_oracle, qlora_oracle
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def nf4_vec(golden_dir):
+    return load_file(os.path.join(golden_dir, "nf4_vectors.safetensors"))
+
+
+@pytest.fixture(scope="module")
+def lora_vec(golden_dir):
+    return load_file(os.path.join(golden_dir, "lora_vectors.safetensors"))
+
+
+def test_codebook_thresholds_are_midpoints():
+    cb = nf4_oracle.NF4_CODEBOOK.astype(np.float64)
+    mid = ((cb[:-1] + cb[1:]) / 2).astype(np.float32)
+    assert np.array_equal(mid, nf4_oracle.NF4_THRESHOLDS)
+
+
+def test_probe_vectors(nf4_vec):
+    probe = nf4_vec["probe_f32"]
+    packed, absmax = nf4_oracle.nf4_quantize(probe)
+    assert np.array_equal(packed, nf4_vec["probe_packed"].numpy())
+    assert np.array_equal(absmax, nf4_vec["probe_absmax"].numpy())
+    # semantic anchors: a code-book value encodes to its own index, a threshold to the index below
+    codes = nf4_oracle.nf4_unpack(packed, probe.numel())
+    p = probe.numpy()
+    for j, v in enumerate(nf4_oracle.NF4_CODEBOOK):
+        assert (codes[p == v] == j).all()
+    for j, t in enumerate(nf4_oracle.NF4_THRESHOLDS):
+        assert (codes[p == t] == j).all()
+        assert (codes[p == np.nextafter(t, np.float32(2))] == j + 1).all()
+
+
+@pytest.mark.parametrize("name", ["tail1", "tail63", "tail64", "tail65", "tail127", "odd_rows", "k16", "zero_block"])
+def test_tail_vectors_numpy_and_c(nf4_vec, name):
+    w = nf4_vec[f"{name}_w"]
+    exp_p, exp_a = nf4_vec[f"{name}_packed"].numpy(), nf4_vec[f"{name}_absmax"].numpy()
+    p, a = nf4_oracle.nf4_quantize(w)
+    assert np.array_equal(p, exp_p) and np.array_equal(a, exp_a)
+    pc, ac = c_oracle.quantize(w)
+    assert np.array_equal(pc, exp_p) and np.array_equal(ac, exp_a)
+    assert p.shape == ((w.numel() + 1) // 2, 1)
+    dt = str(w.dtype).replace("torch.", "")
+    d_np = nf4_oracle.nf4_dequantize(p, a, w.shape, dt)
+    d_c = c_oracle.dequantize(p, a, w.numel(), dt).reshape(w.shape)
+    assert torch.equal(d_np, d_c)
+
+
+def test_zero_block_encodes_to_code_zero(nf4_vec):
+    p = nf4_vec["zero_block_packed"].numpy().reshape(-1)
+    assert (p[32:64] == 0).all()
+    assert nf4_vec["zero_block_absmax"].numpy()[1] == 0.0
+
+
+@pytest.mark.parametrize("dt_name,dt", [("bfloat16", torch.bfloat16), ("float16", torch.float16)])
+def test_seeded_3072_hashes(golden_dir, dt_name, dt):
+    with open(os.path.join(golden_dir, "nf4_hashes.json")) as f:
+        ref = json.load(f)[dt_name]
+    g = torch.Generator().manual_seed(ref["seed"])
+    w = (torch.randn(*ref["shape"], generator=g) * ref["std"]).to(dt)
+    p, a = c_oracle.quantize(w)
+    assert _sha(p) == ref["packed_sha256"] and _sha(a) == ref["absmax_sha256"]
+    p2, a2 = nf4_oracle.nf4_quantize(w)
+    assert _sha(p2) == ref["packed_sha256"] and _sha(a2) == ref["absmax_sha256"]
+
+
+def test_quantize_roundtrip_error_bound():
+    g = torch.Generator().manual_seed(5)
+    w = (torch.randn(256, 192, generator=g) * 0.02).to(torch.bfloat16)
+    p, a = nf4_oracle.nf4_quantize(w)
+    d = nf4_oracle.nf4_dequantize(p, a, w.shape, "bfloat16").float()
+    # largest code-book gap is 0.3038 -> error <= half of it (+ bf16 rounding) times the block absmax
+    bound = torch.from_numpy(a).repeat_interleave(64)[: w.numel()].reshape(w.shape) * (0.3038 / 2 + 0.01)
+    assert ((d - w.float()).abs() <= bound).all()
+    # idempotence: re-quantizing the dequantized tensor reproduces the codes
+    p2, a2 = nf4_oracle.nf4_quantize(d.to(torch.bfloat16))
+    assert np.array_equal(p, p2)
+
+
+@pytest.mark.parametrize("name", ["r16", "r4_bias"])
+def test_lora_oracle_pinned_to_reference(lora_vec, name):
+    """qlora_linear_ref must reproduce, bit for bit, what the REFERENCE's LoRALinear computed on CPU
+    (fixtures frozen by tests/golden/make_golden.py from /root/reference/src/modules/peft/lora.py)."""
+    v = lora_vec
+    N, K = v[f"{name}_w"].shape
+    w_deq = qlora_oracle.dequant_weight(v[f"{name}_packed"].numpy(), v[f"{name}_absmax"].numpy(), (N, K), "bfloat16")
+    out = qlora_oracle.qlora_linear_ref(
+        v[f"{name}_x"], w_deq, v.get(f"{name}_bias"), v[f"{name}_a"], v[f"{name}_b"], float(v[f"{name}_alpha"]), v[f"{name}_dy"]
+    )
+    assert torch.equal(out["y"], v[f"{name}_y"])
+    assert torch.equal(out["dx"], v[f"{name}_dx"])
+    assert torch.equal(out["da"], v[f"{name}_da"])
+    assert torch.equal(out["db"], v[f"{name}_db"])
+    # and the fp64 truth stays within bf16 rounding of it
+    truth = qlora_oracle.qlora_linear_truth(
+        v[f"{name}_x"], w_deq, v.get(f"{name}_bias"), v[f"{name}_a"], v[f"{name}_b"], float(v[f"{name}_alpha"]), v[f"{name}_dy"]
+    )
+    for k in ("y", "dx", "da", "db"):
+        assert qlora_oracle.rel_l2(out[k], truth[k]) < 1e-2
+
+
+def test_quant_state_blob_roundtrip():
+    blob = nf4_oracle.pack_quant_state_blob((32, 16), "float16")
+    meta = nf4_oracle.unpack_quant_state_blob(blob)
+    assert meta == {"quant_type": "nf4", "blocksize": 64, "dtype": "float16", "shape": [32, 16]}

@@ -1,0 +1,134 @@
+"""Data-parallel plumbing for the QLoRA step: bucketed sum-allreduce of the LoRA gradients.
+
+The reference shards by batch through HF Accelerate -> torch DDP
+(/root/reference/src/trainer/common.py:198 ``accelerator.prepare(self.model)``,
+``no_sync`` on non-final accumulation steps :302-308).  The NF4 base is frozen and
+replicated; the only exchange per optimizer step is the sum of the adapter
+gradients (21-34 M bf16 parameters for AuraFlow at r = 16).
+
+``LoraGradReducer`` registers post-accumulate-grad hooks on the trainable (adapter)
+parameters, packs gradients into flat buckets in reverse registration order (the
+order backward produces them), and launches one NCCL all-reduce per full bucket on
+a side stream as soon as its last gradient lands, so the transfers overlap the
+remaining backward kernels.  ``wait()`` joins the side stream and scatters the
+averaged values back before the optimizer step.  On CPU tensors (gloo; used by the
+world_size-2 tests) the same logic runs without streams.
+"""
+from __future__ import annotations
+
+from contextlib import contextmanager
+from typing import Iterable
+
+import torch
+import torch.distributed as dist
+
+
+class _Bucket:
+    def __init__(self, params: list[torch.nn.Parameter]):
+        self.params = params
+        self.numel = sum(p.numel() for p in params)
+        p0 = params[0]
+        self.flat = torch.zeros(self.numel, dtype=p0.dtype, device=p0.device)
+        self.pending = len(params)
+        self.work = None
+        self.event = None
+        self.offsets = []
+        off = 0
+        for p in params:
+            self.offsets.append(off)
+            off += p.numel()
+
+
+class LoraGradReducer:
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 8 << 20, average: bool = True,
+                 group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.average = average
+        self.enabled = True
+        plist = [p for p in params if p.requires_grad]
+        # backward visits layers last-to-first: build buckets in that order so they fill contiguously in time
+        plist = list(reversed(plist))
+        self.buckets: list[_Bucket] = []
+        cur: list[torch.nn.Parameter] = []
+        cur_bytes = 0
+        for p in plist:
+            same = not cur or (cur[0].dtype == p.dtype and cur[0].device == p.device)
+            if cur and (not same or cur_bytes + p.numel() * p.element_size() > bucket_bytes):
+                self.buckets.append(_Bucket(cur))
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += p.numel() * p.element_size()
+        if cur:
+            self.buckets.append(_Bucket(cur))
+        self._where = {}
+        for b in self.buckets:
+            for i, p in enumerate(b.params):
+                self._where[id(p)] = (b, i)
+        self._cuda = bool(self.buckets) and self.buckets[0].flat.is_cuda
+        self.stream = torch.cuda.Stream(device=self.buckets[0].flat.device) if self._cuda else None
+        self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in plist]
+
+    # ------------------------------------------------------------------ hooks
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        if not self.enabled or self.world == 1:
+            return
+        b, i = self._where[id(p)]
+        off = b.offsets[i]
+        b.flat[off : off + p.numel()].copy_(p.grad.reshape(-1))
+        b.pending -= 1
+        if b.pending == 0:
+            self._launch(b)
+
+    def _launch(self, b: _Bucket) -> None:
+        if self._cuda:
+            b.event = torch.cuda.Event()
+            b.event.record(torch.cuda.current_stream(b.flat.device))
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(b.event)
+                b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    # ------------------------------------------------------------------ API
+    @contextmanager
+    def no_sync(self):
+        """Gradient-accumulation micro-steps: accumulate locally, exchange nothing (trainer/common.py:302-308)."""
+        prev, self.enabled = self.enabled, False
+        try:
+            yield
+        finally:
+            self.enabled = prev
+
+    def wait(self) -> None:
+        """Block the current stream until every bucket is reduced; write the (averaged) sums back into .grad."""
+        if self.world == 1:
+            return
+        for b in self.buckets:
+            if b.pending != 0:
+                if b.pending != len(b.params):
+                    # parameters that received no gradient this step contribute their current (possibly zero) grads
+                    for i, p in enumerate(b.params):
+                        if p.grad is not None:
+                            off = b.offsets[i]
+                            b.flat[off : off + p.numel()].copy_(p.grad.reshape(-1))
+                    self._launch(b)
+                else:
+                    continue
+            if b.work is not None:
+                b.work.wait()
+            if self._cuda:
+                torch.cuda.current_stream(b.flat.device).wait_stream(self.stream)
+            if self.average:
+                b.flat.div_(self.world)
+            for i, p in enumerate(b.params):
+                if p.grad is not None:
+                    off = b.offsets[i]
+                    p.grad.copy_(b.flat[off : off + p.numel()].view_as(p.grad))
+            b.pending = len(b.params)
+            b.work = None
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
