@@ -60,7 +60,7 @@ enum vft_op { VFT_OP_FWD = 0, VFT_OP_BWD_DX = 1, VFT_OP_BWD_DAB = 2 };
 int vft_abi_version(void);
 const char* vft_last_error(void);
 int vft_last_path(void);
-/* Force a kernel family for subsequent calls on this thread (tests/bench): 0 = auto. */
+/* Force a kernel family for subsequent calls, process-wide (tests/bench): 0 = auto. */
 void vft_force_path(int path);
 
 /* NF4 quantize/pack.  Replaces bitsandbytes.functional.quantize_4bit(quant_type="nf4")

@@ -63,27 +63,32 @@ NF4_CODEBOOK = np.array(
     dtype=np.float32,
 )
 
-# The 15 decision thresholds of bitsandbytes' dQuantizeNF4 (float literals).
+# The 15 decision thresholds of bitsandbytes' dQuantizeNF4.  In the CUDA source they are
+# f-suffixed literals, i.e. the decimal string rounded DIRECTLY to fp32.  Each decimal is the
+# float64 midpoint of two adjacent code-book entries, which sits (almost) exactly halfway
+# between two fp32 values, so float32(float64(decimal)) -- what numpy would do -- lands 1 ulp
+# away from the literal in 4 of the 15 cases (t0, t8, t12, t14).  The bit patterns below are
+# strtof() of each literal (== what gcc/nvcc emit for "<decimal>f").
 NF4_THRESHOLDS = np.array(
     [
-        -0.8480964004993439,
-        -0.6106329262256622,
-        -0.4599952697753906,
-        -0.33967943489551544,
-        -0.23460740596055984,
-        -0.13791173323988914,
-        -0.045525018125772476,
-        0.03979014977812767,
-        0.1202552504837513,
-        0.2035212516784668,
-        0.2920137718319893,
-        0.3893125355243683,
-        0.5016634166240692,
-        0.6427869200706482,
-        0.8614784181118011,
+        0xBF591CD9,  # -0.8480964004993439f
+        0xBF1C5270,  # -0.6106329262256622f
+        0xBEEB8480,  # -0.4599952697753906f
+        0xBEADEA76,  # -0.33967943489551544f
+        0xBE703CEC,  # -0.23460740596055984f
+        0xBE0D38BC,  # -0.13791173323988914f
+        0xBD3A7871,  # -0.045525018125772476f
+        0x3D22FAFF,  # 0.03979014977812767f
+        0x3DF64863,  # 0.1202552504837513f
+        0x3E5067E0,  # 0.2035212516784668f
+        0x3E9582D4,  # 0.2920137718319893f
+        0x3EC753F9,  # 0.3893125355243683f
+        0x3F006D03,  # 0.5016634166240692f
+        0x3F248DAF,  # 0.6427869200706482f
+        0x3F5C89D9,  # 0.8614784181118011f
     ],
-    dtype=np.float32,
-)
+    dtype=np.uint32,
+).view(np.float32)
 
 
 def _as_f32(w) -> np.ndarray:

@@ -26,9 +26,21 @@ def lora_vec(golden_dir):
 
 
 def test_codebook_thresholds_are_midpoints():
+    """Thresholds = bitsandbytes' f-suffixed literals (decimal -> fp32 directly): the fp32 neighbour of the
+    float64 midpoint of adjacent code-book entries, at most 1 ulp from float32(midpoint)."""
+    import ctypes
+
     cb = nf4_oracle.NF4_CODEBOOK.astype(np.float64)
-    mid = ((cb[:-1] + cb[1:]) / 2).astype(np.float32)
-    assert np.array_equal(mid, nf4_oracle.NF4_THRESHOLDS)
+    mid64 = (cb[:-1] + cb[1:]) / 2
+    thr = nf4_oracle.NF4_THRESHOLDS
+    assert thr.dtype == np.float32 and (np.diff(thr) > 0).all()
+    ulp = np.spacing(np.abs(thr))
+    assert (np.abs(thr.astype(np.float64) - mid64) <= ulp).all()
+    libc = ctypes.CDLL(None)
+    libc.strtof.restype = ctypes.c_float
+    libc.strtof.argtypes = [ctypes.c_char_p, ctypes.c_void_p]
+    for t, m in zip(thr, mid64):
+        assert np.float32(libc.strtof(repr(float(m)).encode(), None)) == t  # the literal bnb compiles
 
 
 def test_probe_vectors(nf4_vec):
@@ -36,6 +48,8 @@ def test_probe_vectors(nf4_vec):
     packed, absmax = nf4_oracle.nf4_quantize(probe)
     assert np.array_equal(packed, nf4_vec["probe_packed"].numpy())
     assert np.array_equal(absmax, nf4_vec["probe_absmax"].numpy())
+    pc, ac = c_oracle.quantize(probe)  # gcc parses the f-literals: must agree on every +-1 ulp probe
+    assert np.array_equal(pc, packed) and np.array_equal(ac, absmax)
     # semantic anchors: a code-book value encodes to its own index, a threshold to the index below
     codes = nf4_oracle.nf4_unpack(packed, probe.numel())
     p = probe.numpy()

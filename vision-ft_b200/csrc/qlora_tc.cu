@@ -300,6 +300,16 @@ static EncodeTiledFn get_encode_fn() {
 
 static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
                        uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
+  // The driver entry point needs a current context; a thread whose first CUDA call is this one (an autograd
+  // worker running an NF4-only backward) has none until a runtime call binds the primary context.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    if (cudaFree(nullptr) != cudaSuccess) {
+      set_error("no usable CUDA context: %s", cudaGetErrorString(cudaGetLastError()));
+      return VFT_ERR_CUDA;
+    }
+    ctx_bound = true;
+  }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");

@@ -2,13 +2,15 @@
 // dispatcher between the tcgen05 family (qlora_tc.cu) and the generic family (qlora_simt.cu).
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "vft_common.cuh"
 
 namespace vft {
 
 static thread_local char g_error[512] = "";
 static thread_local int g_path = VFT_PATH_NONE;
-static thread_local int g_forced = 0;
+static std::atomic<int> g_forced{0};  // process-wide: backward runs on autograd worker threads
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -17,7 +19,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void set_path(int path) { g_path = path; }
-int forced_path() { return g_forced; }
+int forced_path() { return g_forced.load(std::memory_order_relaxed); }
 
 static int check_layer(const LayerArgs& a, const void* act, const void* out, bool out_optional = false) {
   VFT_REQUIRE(a.T >= 0 && a.N > 0 && a.K > 0, "bad shape T=%lld N=%lld K=%lld", (long long)a.T, (long long)a.N,
@@ -57,7 +59,7 @@ extern "C" {
 int vft_abi_version(void) { return VFT_ABI_VERSION; }
 const char* vft_last_error(void) { return g_error; }
 int vft_last_path(void) { return g_path; }
-void vft_force_path(int path) { g_forced = path; }
+void vft_force_path(int path) { g_forced.store(path, std::memory_order_relaxed); }
 
 int vft_nf4_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t* packed, float* absmax,
                      void* stream) {
