@@ -1,0 +1,45 @@
+"""Time the fused tcgen05 kernel alone (forward and backward launches, NF4-only) for a shape; used with the
+VFT_TC_DEBUG triage mask.  Not part of the product."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "vision-ft_b200")):
+    sys.path.insert(0, p)
+import torch
+from vft_b200 import _cabi, ops
+
+def main():
+    T, N, K = [int(v) for v in (sys.argv[1:4] if len(sys.argv) > 3 else (4096, 3072, 3072))]
+    dev = torch.device("cuda")
+    w = (torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16)
+    packed, absmax = ops.nf4_quantize(w)
+    xs = [torch.randn(T, K, device=dev, dtype=torch.bfloat16) for _ in range(4)]
+    gs = [torch.randn(T, N, device=dev, dtype=torch.bfloat16) for _ in range(4)]
+    y = torch.empty(T, N, device=dev, dtype=torch.bfloat16)
+    dx = torch.empty(T, K, device=dev, dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+    def fwd(i):
+        _cabi.check(_cabi.lib.vft_qlora_fwd(xs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, None, 0, 0.0, y.data_ptr(), None, None, 0, st))
+    def bwd(i):
+        _cabi.check(_cabi.lib.vft_qlora_bwd_dx(gs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, 0, 0.0, dx.data_ptr(), None, None, 0, st))
+    res = {}
+    for name, fn in (("fwd", fwd), ("bwd", bwd)):
+        for i in range(5): fn(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(40): fn(i)
+        b.record(); torch.cuda.synchronize()
+        res[name] = a.elapsed_time(b) / 40 * 1e3
+    if int(os.environ.get("VFT_TC_DEBUG", "0")) & 16:
+        import ctypes
+        fwd(0); torch.cuda.synchronize()
+        buf = (ctypes.c_ulonglong * 512)()
+        _cabi.lib.vft_debug_tc_timeline(buf, 512)
+        names = ["entry", "setup done", "first stage ready", "block 8 ready", "last block ready", "accum ready", "epilogue done", "exit"]
+        c0, n0 = buf[0], buf[1]
+        for i, nm in enumerate(names):
+            print(f"   {nm:18s} +{buf[2*i]-c0:8d} cyc  +{(buf[2*i+1]-n0)/1e3:8.2f} us")
+    fl = 2 * T * N * K
+    print(f"VFT_TC_DEBUG={os.environ.get('VFT_TC_DEBUG','0'):>2} T={T} N={N} K={K}: fwd {res['fwd']:.1f} us ({fl/res['fwd']/1e6:.0f} TF/s)  bwd {res['bwd']:.1f} us ({fl/res['bwd']/1e6:.0f} TF/s)")
+
+main()

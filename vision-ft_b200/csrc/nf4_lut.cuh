@@ -21,6 +21,9 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <string.h>
+
+#include <type_traits>
 
 #include "../../include/vft_b200.h"
 
@@ -50,19 +53,44 @@ template <typename ActT>
 VFT_HD uint32_t pack2(float lo, float hi);
 template <>
 VFT_HD uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
-  const __nv_bfloat16 a = __float2bfloat16_rn(lo), b = __float2bfloat16_rn(hi);
-  return (uint32_t)(*reinterpret_cast<const uint16_t*>(&a)) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&b)) << 16);
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // one cvt.rn.bf16x2.f32 (F2FP), not two F2F
+  return *reinterpret_cast<const uint32_t*>(&v);
 }
 template <>
 VFT_HD uint32_t pack2<__half>(float lo, float hi) {
-  const __half a = __float2half_rn(lo), b = __float2half_rn(hi);
-  return (uint32_t)(*reinterpret_cast<const uint16_t*>(&a)) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&b)) << 16);
+  const __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
 }
 
 VFT_HD float round_to_qdtype(float v, int qdtype) {
   if (qdtype == VFT_F16) return __half2float(__float2half_rn(v));
   if (qdtype == VFT_BF16) return __bfloat162float(__float2bfloat16_rn(v));
   return v;
+}
+
+// Round a pair through quant_state.dtype when it differs from the activation dtype (double rounding, as
+// bitsandbytes' dequantize_4bit(...).to(x.dtype) does).  Packed conversions only: the scalar F2F path runs on
+// the XU pipe at 1/8 rate and was THE bottleneck of the first version of the fused kernel (74 % XU busy).
+template <typename ActT>
+VFT_HD void round_pair_through(float& a, float& b, int qdtype) {
+  constexpr int kAct = sizeof(ActT) == 2 ? (std::is_same<ActT, __half>::value ? VFT_F16 : VFT_BF16) : VFT_F32;
+  if (qdtype == kAct || qdtype == VFT_F32) return;  // a second rounding to the same format changes nothing
+  if (qdtype == VFT_F16) {
+    const float2 f = __half22float2(__floats2half2_rn(a, b));
+    a = f.x;
+    b = f.y;
+  } else {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(&v);
+#ifdef __CUDA_ARCH__
+    a = __uint_as_float(u << 16);
+    b = __uint_as_float(u & 0xffff0000u);
+#else
+    const uint32_t ua = u << 16, ub = u & 0xffff0000u;
+    memcpy(&a, &ua, 4);
+    memcpy(&b, &ub, 4);
+#endif
+  }
 }
 
 struct Nf4Lut {
@@ -80,10 +108,7 @@ VFT_HD void nf4_build_lut(float absmax, int qdtype, Nf4Lut& t) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float a = kCode[2 * i] * absmax, b = kCode[2 * i + 1] * absmax;
-    if (qdtype != VFT_F32) {
-      a = round_to_qdtype(a, qdtype);
-      b = round_to_qdtype(b, qdtype);
-    }
+    round_pair_through<ActT>(a, b, qdtype);
     p[i] = pack2<ActT>(a, b);
   }
 #pragma unroll

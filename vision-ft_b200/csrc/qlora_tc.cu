@@ -8,25 +8,31 @@
 // scale + add of lora.py:100-104.  No bf16 copy of W ever exists outside shared memory.
 //
 // Tile: 128 "features" (MMA M; out-features forward, in-features backward) x BN tokens (MMA N)
-// x 64 contraction elements per pipeline stage.  The weight is the A operand, the activations
+// x 64 contraction elements per pipeline step.  The weight is the A operand, the activations
 // are the B operand ("swap-AB"): the accumulator D[feature, token] lives in tensor memory with
-// one feature per TMEM lane, so bias is a per-thread scalar and the epilogue thread that owns a
-// lane also owns the quantization row it decodes.
+// one feature per TMEM lane, so bias is a per-thread scalar and the thread that decodes a
+// quantization row forward is the thread that owns that accumulator lane.
 //
-// Warp roles (256 threads):
-//   warp 0      TMA producer: activation tile [BN x 64] (SWIZZLE_128B, K-major) and the packed
-//               4-bit codes of the weight tile (4 KB) into a 4-stage shared-memory ring
-//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.kind::f16 (M=128, N=BN, K=16),
-//               tcgen05.commit releases the stage / publishes the accumulator
-//   warp 2      TMEM allocation / deallocation
-//   warps 4-7   decode: 128 threads, each owns one 64-element quantization block per stage:
-//               builds the absmax-scaled 16-entry table in registers (nf4_lut.cuh), decodes 64
-//               codes with byte permutes and writes the bf16 operand tile in the canonical
-//               UMMA shared-memory layout (forward: K-major, backward: MN-major, both 128B
-//               swizzle).  After the main loop the same warps run the epilogue
-//               (tcgen05.ld -> bias -> convert -> global).
-// The adapter enters as ONE extra pipeline stage: activations = saved x.A^T (or dy.B), weight
+// Warp roles (640 threads):
+//   warp 0       TMA producer: activation tile [BN x 64] (SWIZZLE_128B, K-major) into a 4-deep ring
+//   warp 1       MMA issuer: one elected thread issues tcgen05.mma.kind::f16 (M=128, N=BN, K=16);
+//                tcgen05.commit releases the activation stage and the weight stage, and finally
+//                publishes the accumulator
+//   warp 2       TMEM allocation / deallocation
+//   warps 4-19   decode: four groups of 128 threads.  Group g owns contraction blocks g, g+4, ...;
+//                each thread owns one 64-element quantization block per step: its 32 bytes of
+//                packed codes and its absmax are prefetched from global memory one step ahead,
+//                the absmax-scaled 16-entry table is built in registers (nf4_lut.cuh), the 64
+//                codes are decoded with byte permutes and written as the bf16 operand tile in
+//                the canonical UMMA shared-memory layout (forward: K-major, backward: MN-major,
+//                both 128B swizzle) into a 5-deep ring.  Four groups keep ~4 warps per scheduler
+//                busy, which is what hides the permute-chain latency (one group alone reaches
+//                36 % tensor-pipe utilisation, profiles/r01_*).  The same 16 warps then run the
+//                epilogue (tcgen05.ld -> bias -> convert -> global), 4 column slices in parallel.
+// The adapter enters as ONE extra pipeline step: activations = saved x.A^T (or dy.B), weight
 // tile = scale*B rows (or A rows); its MMAs accumulate into the same TMEM tile.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "nf4_lut.cuh"
@@ -36,23 +42,23 @@
 namespace vft {
 namespace {
 
-constexpr int kBM = 128;       // features per CTA tile (MMA M)
-constexpr int kBK = 64;        // contraction elements per stage (= NF4 blocksize)
-constexpr int kStages = 4;
-constexpr int kThreads = 256;
-constexpr int kDecodeWarp0 = 4;  // warps 4..7 decode + epilogue
-constexpr int kATileBytes = kBM * kBK * 2;  // 16 KB operand tile produced by the decode warps
-constexpr int kCodeTileBytes = kBM * kBK / 2;  // 4 KB of packed codes per stage
+constexpr int kBM = 128;        // features per CTA tile (MMA M)
+constexpr int kBK = 64;         // contraction elements per step (= NF4 blocksize)
+constexpr int kStages = 4;      // pipeline depth: one stage = activation tile (TMA) + decoded weight tile
+constexpr int kGroups = 4;      // decode groups of 128 threads; group g fills stage g (kGroups == kStages)
+constexpr int kDecodeWarp0 = 4;
+constexpr int kThreads = (kDecodeWarp0 + 4 * kGroups) * 32;  // 640
+constexpr int kATileBytes = kBM * kBK * 2;                   // 16 KB operand tile
 
 template <int BN>
 struct SmemLayout {
   static constexpr int act_bytes = BN * kBK * 2;
   static constexpr int act_off = 0;
   static constexpr int a_off = act_off + kStages * act_bytes;
-  static constexpr int code_off = a_off + kStages * kATileBytes;
-  static constexpr int bar_off = code_off + kStages * kCodeTileBytes;
-  // barriers: full_act[kStages], full_a[kStages], empty[kStages], accum_full, then the TMEM base address
-  static constexpr int total = bar_off + (3 * kStages + 1) * 8 + 16;
+  static constexpr int bar_off = a_off + kStages * kATileBytes;
+  // barriers: full[kStages], empty[kStages], accum; then the TMEM base address
+  static constexpr int n_bars = 2 * kStages + 1;
+  static constexpr int total = bar_off + n_bars * 8 + 16;
   static constexpr int dyn_bytes = total + 1024;  // slack to align the base to 1024 B
 };
 
@@ -61,16 +67,38 @@ struct TcParams {
   int r;
   int qdtype;
   float scale;
+  const uint8_t* packed;
   const float* absmax;
   const void* bias;
   const void* lora_w;  // forward: B [N, r]; backward: A [r, K]
   void* out;           // forward: Y [T, N]; backward: dX [T, K]
+  int debug;           // VFT_TC_DEBUG bit mask (performance triage only; results are garbage when non-zero):
+                       //   1 = skip the decode work, 2 = skip the MMAs, 4 = skip the epilogue stores, 8 = skip the TMA loads
 };
+
+// Timeline of CTA (0,0) for performance triage (VFT_TC_DEBUG & 16): SM clock + global ns timer per phase.
+__device__ unsigned long long g_tc_timeline[512];
+__device__ __forceinline__ void tl_mark(const TcParams& p, int slot) {
+  if ((p.debug & 16) && blockIdx.x == 0 && blockIdx.y == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    g_tc_timeline[2 * slot] = (unsigned long long)clock64();
+    g_tc_timeline[2 * slot + 1] = ns;
+  }
+}
+
+__device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
 
 template <typename ActT, bool kBackward, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_codes,
-                const __grid_constant__ CUtensorMap map_lora, const TcParams p) {
+qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_lora,
+                const TcParams p) {
   using L = SmemLayout<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -78,6 +106,7 @@ qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) tl_mark(p, 0);
   const int64_t OUT = kBackward ? p.K : p.N;  // feature dimension of this GEMM
   const int64_t RED = kBackward ? p.N : p.K;  // contraction dimension
   const int64_t f0 = (int64_t)blockIdx.x * kBM;
@@ -86,22 +115,23 @@ qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_consta
   const int n_blocks = n_main + (p.r > 0 ? 1 : 0);
   const int KB = (int)(p.K / kBK);  // absmax entries per weight row
 
-  auto bar_full_act = [&](int s) { return smem_base + L::bar_off + 8 * s; };
-  auto bar_full_a = [&](int s) { return smem_base + L::bar_off + 8 * (kStages + s); };
-  auto bar_empty = [&](int s) { return smem_base + L::bar_off + 8 * (2 * kStages + s); };
-  const uint32_t bar_accum = smem_base + L::bar_off + 8 * (3 * kStages);
+  // full[s]: 1 arrive.expect_tx by the TMA producer + 4 arrives by the warps of the decoding group
+  // empty[s]: 1 arrive by tcgen05.commit; waited on by the producer AND by the decode group of that stage.
+  // One wait + one commit per 64-wide step keeps the single MMA-issuing thread (~250 cycles per mbarrier
+  // round trip) under the 512 cycles the four MMAs of a step take.
+  auto bar_full = [&](int s) { return smem_base + L::bar_off + 8 * s; };
+  auto bar_empty = [&](int s) { return smem_base + L::bar_off + 8 * (kStages + s); };
+  const uint32_t bar_accum = smem_base + L::bar_off + 8 * (L::n_bars - 1);
   const uint32_t tmem_slot = bar_accum + 8;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L::bar_off + 8 * (3 * kStages) + 8);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L::bar_off + 8 * L::n_bars);
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::tma_prefetch_desc(&map_act);
-    ptx::tma_prefetch_desc(&map_codes);
     if (p.r > 0) ptx::tma_prefetch_desc(&map_lora);
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(bar_full_act(s), 1);
-      ptx::mbar_init(bar_full_a(s), 4);  // one arrive per decode warp
+      ptx::mbar_init(bar_full(s), 5);
       ptx::mbar_init(bar_empty(s), 1);
     }
     ptx::mbar_init(bar_accum, 1);
@@ -112,41 +142,38 @@ qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_consta
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_d = *tmem_slot_gen;
+  if (threadIdx.x == 0) tl_mark(p, 1);
 
   if (warp == 0) {
-    // ------------------------------------------------------------- TMA producer
+    // ------------------------------------------------------------- TMA producer (activations)
     if (ptx::elect_one()) {
-      int s = 0;
-      uint32_t phase = 0;
       for (int b = 0; b < n_blocks; ++b) {
-        ptx::mbar_wait(bar_empty(s), phase ^ 1u);
-        const uint32_t dst_act = smem_base + L::act_off + s * L::act_bytes;
-        if (b < n_main) {
-          ptx::mbar_arrive_expect_tx(bar_full_act(s), L::act_bytes + kCodeTileBytes);
-          ptx::tma_load_2d(&map_act, dst_act, bar_full_act(s), b * kBK, (int)t0);
-          const uint32_t dst_code = smem_base + L::code_off + s * kCodeTileBytes;
-          if (kBackward)  // codes of W[n-block b (64 rows), k = f0 .. f0+127]  -> [64 rows][64 bytes]
-            ptx::tma_load_2d(&map_codes, dst_code, bar_full_act(s), (int)(f0 / 2), b * kBK);
-          else            // codes of W[n = f0 .. f0+127, k-block b (64 cols)]  -> [128 rows][32 bytes]
-            ptx::tma_load_2d(&map_codes, dst_code, bar_full_act(s), b * (kBK / 2), (int)f0);
-        } else {
-          ptx::mbar_arrive_expect_tx(bar_full_act(s), L::act_bytes);
-          ptx::tma_load_2d(&map_lora, dst_act, bar_full_act(s), 0, (int)t0);
+        const int s = b % kStages;
+        ptx::mbar_wait(bar_empty(s), ((uint32_t)(b / kStages) & 1u) ^ 1u);
+        const uint32_t dst = smem_base + L::act_off + s * L::act_bytes;
+        if (p.debug & 8) {
+          ptx::mbar_arrive(bar_full(s));
+          continue;
         }
-        if (++s == kStages) { s = 0; phase ^= 1u; }
+        ptx::mbar_arrive_expect_tx(bar_full(s), L::act_bytes);
+        if (b < n_main)
+          ptx::tma_load_2d(&map_act, dst, bar_full(s), b * kBK, (int)t0);
+        else
+          ptx::tma_load_2d(&map_lora, dst, bar_full(s), 0, (int)t0);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(sizeof(ActT) == 2 && std::is_same<ActT, __nv_bfloat16>::value,
+      constexpr uint32_t idesc = ptx::make_idesc_f16(std::is_same<ActT, __nv_bfloat16>::value,
                                                      /*a_mn_major=*/kBackward, /*b_mn_major=*/false, kBM, BN);
-      int s = 0;
-      uint32_t phase = 0;
       for (int b = 0; b < n_blocks; ++b) {
-        ptx::mbar_wait(bar_full_act(s), phase);
-        ptx::mbar_wait(bar_full_a(s), phase);
+        const int s = b % kStages;
+        ptx::mbar_wait(bar_full(s), (uint32_t)(b / kStages) & 1u);
         ptx::tc_fence_after();
+        if (b == 0) tl_mark(p, 2);
+        if (b == 8) tl_mark(p, 3);
+        if (b == n_blocks - 1) tl_mark(p, 4);
         const uint32_t a_addr = smem_base + L::a_off + s * kATileBytes;
         const uint32_t b_addr = smem_base + L::act_off + s * L::act_bytes;
         // A: forward  K-major  [128 rows x 128 B], 8-row groups 1024 B apart
@@ -156,73 +183,87 @@ qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_consta
                                           : ptx::make_smem_desc_sw128(a_addr, 16, 1024);
         const uint64_t b_desc = ptx::make_smem_desc_sw128(b_addr, 16, 1024);
         const int ksteps = (b < n_main) ? (kBK / 16) : ((p.r + 15) / 16);
-        for (int k = 0; k < ksteps; ++k) {
+        for (int k = 0; k < ksteps && !(p.debug & 2); ++k) {
           // advance 16 contraction elements: 32 B inside a K-major swizzle row, 16 rows (2048 B) MN-major
           const uint64_t a_k = a_desc + (uint64_t)(kBackward ? (k * 2048) >> 4 : (k * 32) >> 4);
           const uint64_t b_k = b_desc + (uint64_t)((k * 32) >> 4);
           ptx::umma_ss(tmem_d, a_k, b_k, idesc, (b | k) != 0 ? 1u : 0u);
         }
-        ptx::umma_commit(bar_empty(s));  // stage reusable once these MMAs have read it
-        if (++s == kStages) { s = 0; phase ^= 1u; }
+        ptx::umma_commit(bar_empty(s));  // the stage is reusable once these MMAs have read it
       }
       ptx::umma_commit(bar_accum);
     }
   } else if (warp >= kDecodeWarp0) {
     // ------------------------------------------------------------- decode warps
-    const int m = threadIdx.x - kDecodeWarp0 * 32;  // 0..127
-    // forward : thread m owns weight row n = f0 + m, one 64-wide k-block per stage
+    const int dw = warp - kDecodeWarp0;  // 0..15
+    const int group = dw >> 2;           // owns blocks group, group + 4, ...
+    const int quad = dw & 3;             // == warp % 4: the TMEM lane quadrant this warp may access
+    const int m = quad * 32 + lane;      // 0..127
+    // forward : thread m owns weight row n = f0 + m, one 64-wide k-block per step
     // backward: thread m owns contraction row n = 64 b + (m & 63), in-feature half (m >> 6)
     const int row = kBackward ? (m & 63) : m;
     const int half = kBackward ? (m >> 6) : 0;
-    const uint32_t code_row_off = kBackward ? (uint32_t)(row * 64 + half * 32) : (uint32_t)(row * 32);
-    // swizzle applied by TMA to the code tile (SWIZZLE_64B backward, SWIZZLE_32B forward): 16-byte chunk
-    // index ^= address bits [7, 7 + log2(span/16))
-    const uint32_t code_xor = kBackward ? (uint32_t)(((row >> 1) & 3) << 4) : (uint32_t)(((row >> 2) & 1) << 4);
     const uint32_t a_row_off = kBackward ? (uint32_t)(half * 8192 + (row >> 3) * 1024 + (row & 7) * 128)
                                          : (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
     const uint32_t a_xor = (uint32_t)(row & 7) << 4;
+    const int64_t half_k = f0 + half * 64;  // backward: first in-feature of this thread's block
 
-    // absmax of the block this thread decodes in stage b
-    const int64_t am_feature = kBackward ? (f0 / kBK + half) : 0;  // k-block index (backward)
-    auto absmax_at = [&](int b) -> float {
-      if (kBackward) {
-        const int64_t n = (int64_t)b * kBK + row;
-        return (n < p.N && am_feature < KB) ? __ldg(p.absmax + n * KB + am_feature) : 0.0f;
-      } else {
-        const int64_t n = f0 + row;
-        return (n < p.N) ? __ldg(p.absmax + n * KB + b) : 0.0f;
+    // global sources of the block this thread decodes at step b: 32 bytes of codes + one absmax
+    auto block_valid = [&](int b) -> bool {
+      if (kBackward) return ((int64_t)b * kBK + row) < p.N && half_k < p.K;
+      return (f0 + row) < p.N;
+    };
+    auto codes_ptr = [&](int b) -> const uint8_t* {
+      if (kBackward) return p.packed + (((int64_t)b * kBK + row) * p.K + half_k) / 2;
+      return p.packed + ((f0 + row) * p.K + (int64_t)b * kBK) / 2;
+    };
+    auto absmax_ptr = [&](int b) -> const float* {
+      if (kBackward) return p.absmax + ((int64_t)b * kBK + row) * KB + half_k / kBK;
+      return p.absmax + (f0 + row) * KB + b;
+    };
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+    float am = 0.0f;
+    auto prefetch = [&](int b) {
+      q0 = q1 = make_uint4(0, 0, 0, 0);
+      am = 0.0f;
+      if (b < n_main && block_valid(b)) {
+        const uint8_t* c = codes_ptr(b);
+        q0 = ldg_stream_u4(c);
+        q1 = ldg_stream_u4(c + 16);
+        am = __ldg(absmax_ptr(b));
       }
     };
 
-    int s = 0;
-    uint32_t phase = 0;
-    float am_next = absmax_at(0);
-    for (int b = 0; b < n_blocks; ++b) {
-      const float am = am_next;
-      if (b + 1 < n_main) am_next = absmax_at(b + 1);
-      ptx::mbar_wait(bar_full_act(s), phase);
-      const uint32_t a_tile = smem_base + L::a_off + s * kATileBytes + a_row_off;
+    prefetch(group);
+    for (int b = group; b < n_blocks; b += kGroups) {
+      const int sa = b % kStages;
+      const uint32_t a_tile = smem_base + L::a_off + sa * kATileBytes + a_row_off;
       if (b < n_main) {
-        const uint32_t code_addr = smem_base + L::code_off + s * kCodeTileBytes + code_row_off;
-        const uint4 q0 = ptx::lds128(code_addr ^ code_xor);
-        const uint4 q1 = ptx::lds128((code_addr + 16) ^ code_xor);
         Nf4Lut lut;
         nf4_build_lut<ActT>(am, p.qdtype, lut);
         const uint32_t words[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        prefetch(b + kGroups);  // next block's codes are in flight while this one is decoded
+        // Decode into registers BEFORE waiting for the stage: the permute work (~1700 cycles of latency with four
+        // warps per scheduler) then overlaps the MMAs still reading the stage, and only 8 stores + a fence sit
+        // between "stage free" and "stage full".
+        uint32_t v[8][4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint32_t v[4];
-          nf4_decode_word(words[c], lut, v);
-          ptx::sts128(a_tile + (((uint32_t)c << 4) ^ a_xor), v[0], v[1], v[2], v[3]);
+        for (int c = 0; c < 8; ++c) nf4_decode_word(words[c], lut, v[c]);
+        ptx::mbar_wait(bar_empty(sa), ((uint32_t)(b / kStages) & 1u) ^ 1u);
+        if (!(p.debug & 1)) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            ptx::sts128(a_tile + (((uint32_t)c << 4) ^ a_xor), v[c][0], v[c][1], v[c][2], v[c][3]);
         }
       } else {
-        // adapter stage: forward row n of scale*B (r values), backward row j of A (64 in-features)
+        // adapter step: forward row n of scale*B (r values), backward row j of A (64 in-features)
         const ActT* lw = static_cast<const ActT*>(p.lora_w);
+        ptx::mbar_wait(bar_empty(sa), ((uint32_t)(b / kStages) & 1u) ^ 1u);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint32_t v[4] = {0u, 0u, 0u, 0u};
           if (kBackward) {
-            const int64_t k = f0 + half * 64 + c * 8;
+            const int64_t k = half_k + c * 8;
             if (row < p.r && k < p.K) {
               const uint4 q = __ldg(reinterpret_cast<const uint4*>(lw + (int64_t)row * p.K + k));
               v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
@@ -244,24 +285,25 @@ qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_consta
       }
       ptx::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_full_a(s));
-      if (++s == kStages) { s = 0; phase ^= 1u; }
+      if (lane == 0) ptx::mbar_arrive(bar_full(sa));
     }
 
-    // ----------------------------------------------------------- epilogue (same 4 warps)
+    // ----------------------------------------------------------- epilogue: 16 warps, 32-column chunks
     ptx::mbar_wait(bar_accum, 0);
     ptx::tc_fence_after();
+    if (dw == 0 && lane == 0) tl_mark(p, 5);
     const int64_t feat = f0 + m;
-    const uint32_t lane_base = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t lane_base = tmem_d + ((uint32_t)(quad * 32) << 16);
     float bias_v = 0.0f;
     if (!kBackward && p.bias != nullptr && feat < OUT) bias_v = to_f32<ActT>(static_cast<const ActT*>(p.bias)[feat]);
     ActT* out = static_cast<ActT*>(p.out);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = group * 32; c0 < BN; c0 += kGroups * 32) {
+      if (t0 + c0 >= p.T) break;  // warp-uniform
       uint32_t v[32];
       ptx::tmem_ld_32x32b_x32(lane_base + (uint32_t)c0, v);
       ptx::tmem_ld_wait();
-      if (feat < OUT) {
+      if (feat < OUT && !(p.debug & 4)) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int64_t t = t0 + c0 + j;
@@ -270,6 +312,7 @@ qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_consta
       }
     }
     ptx::tc_fence_before();
+    if (dw == 0 && lane == 0) tl_mark(p, 6);
   }
 
   __syncthreads();
@@ -277,6 +320,7 @@ qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_consta
     ptx::tc_fence_after();
     ptx::tmem_dealloc<BN>(tmem_d);
   }
+  if (threadIdx.x == 0) tl_mark(p, 7);
 }
 
 // ---------------------------------------------------------------------------
@@ -337,16 +381,9 @@ static int launch_tc(const LayerArgs& a, const void* act, void* out, const void*
   const int64_t RED = kBackward ? a.N : a.K;
   const CUtensorMapDataType dt =
       std::is_same<ActT, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  CUtensorMap map_act, map_codes, map_lora;
+  CUtensorMap map_act, map_lora;
   int rc = make_map_2d(&map_act, dt, act, (uint64_t)RED, (uint64_t)a.T, (uint64_t)RED * 2, kBK, BN,
                        CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc != VFT_OK) return rc;
-  if (kBackward)
-    rc = make_map_2d(&map_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.packed, (uint64_t)a.K / 2, (uint64_t)a.N,
-                     (uint64_t)a.K / 2, 64, 64, CU_TENSOR_MAP_SWIZZLE_64B);
-  else
-    rc = make_map_2d(&map_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.packed, (uint64_t)a.K / 2, (uint64_t)a.N,
-                     (uint64_t)a.K / 2, 32, 128, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc != VFT_OK) return rc;
   if (a.r > 0) {
     rc = make_map_2d(&map_lora, dt, lora_act, VFT_LORA_LD, (uint64_t)a.T, VFT_LORA_LD * 2, kBK, BN,
@@ -357,14 +394,17 @@ static int launch_tc(const LayerArgs& a, const void* act, void* out, const void*
   }
   TcParams p;
   p.T = a.T; p.N = a.N; p.K = a.K; p.r = a.r; p.qdtype = a.qdtype; p.scale = a.scale;
+  p.packed = a.packed;
   p.absmax = a.absmax;
   p.bias = kBackward ? nullptr : a.bias;
   p.lora_w = kBackward ? a.lora_a : a.lora_b;
   p.out = out;
+  const char* dbg = getenv("VFT_TC_DEBUG");
+  p.debug = dbg ? atoi(dbg) : 0;
   auto kern = qlora_tc_kernel<ActT, kBackward, BN>;
   VFT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn_bytes));
   dim3 grid((unsigned)ceil_div64(OUT, kBM), (unsigned)ceil_div64(a.T, BN));
-  kern<<<grid, kThreads, L::dyn_bytes, st>>>(map_act, map_codes, map_lora, p);
+  kern<<<grid, kThreads, L::dyn_bytes, st>>>(map_act, map_lora, p);
   VFT_CUDA_OK(cudaGetLastError());
   return VFT_OK;
 }
@@ -379,6 +419,16 @@ static int launch_tc_bn(const LayerArgs& a, const void* act, void* out, const vo
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
+
+}  // namespace vft
+
+// Debug export (not part of the public ABI): copy the CTA-(0,0) timeline of the last VFT_TC_DEBUG&16 launch.
+extern "C" int vft_debug_tc_timeline(unsigned long long* out, int n) {
+  if (n > 512) n = 512;
+  return cudaMemcpyFromSymbol(out, vft::g_tc_timeline, sizeof(unsigned long long) * n) == cudaSuccess ? 0 : -3;
+}
+
+namespace vft {
 
 bool tc_supported(const LayerArgs& a, bool backward) {
   if (a.act_dtype != VFT_BF16 && a.act_dtype != VFT_F16) return false;

@@ -135,7 +135,8 @@ int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* 
   VFT_REQUIRE(r == 0 || t_save != nullptr, "t_save is required when r > 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (r > 0) {
-    rc = simt_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st);
+    rc = (forced_path() == VFT_PATH_SIMT) ? simt_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st)
+                                          : mma_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st);
     if (rc != VFT_OK) return rc;
   }
   const bool tc = use_tc(a, false, &rc);
@@ -155,7 +156,8 @@ int vft_qlora_bwd_dx(const void* dy, int64_t T, const uint8_t* packed, const flo
   VFT_REQUIRE(r == 0 || dt_save != nullptr, "dt_save is required when r > 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (r > 0) {
-    rc = simt_lora_dt(dy, lora_b, T, N, r, scale, act_dtype, dt_save, st);
+    rc = (forced_path() == VFT_PATH_SIMT) ? simt_lora_dt(dy, lora_b, T, N, r, scale, act_dtype, dt_save, st)
+                                          : mma_lora_dt(dy, lora_b, T, N, r, scale, act_dtype, dt_save, st);
     if (rc != VFT_OK) return rc;
   }
   if (dx == nullptr) {
@@ -180,8 +182,11 @@ int vft_lora_bwd_dab(const void* dy, const void* x, const void* t_save, const vo
     return VFT_ERR_WORKSPACE;
   }
   set_path(VFT_PATH_SIMT);
-  return simt_dab(dy, x, t_save, dt_save, T, N, K, r, act_dtype, scale, dA, dB, static_cast<float*>(ws),
-                  static_cast<cudaStream_t>(stream));
+  if (forced_path() == VFT_PATH_SIMT)
+    return simt_dab(dy, x, t_save, dt_save, T, N, K, r, act_dtype, scale, dA, dB, static_cast<float*>(ws),
+                    static_cast<cudaStream_t>(stream));
+  return mma_dab(dy, x, t_save, dt_save, T, N, K, r, act_dtype, scale, dA, dB, static_cast<float*>(ws),
+                 static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

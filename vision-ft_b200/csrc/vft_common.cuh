@@ -118,6 +118,14 @@ int simt_bwd_dx(const LayerArgs& a, const void* dy, void* dx, const void* dt_sav
 int simt_dab(const void* dy, const void* x, const void* t_save, const void* dt_save, int64_t T, int64_t N, int64_t K,
              int r, int act_dtype, float scale, void* dA, void* dB, float* ws, cudaStream_t st);
 
+// warp-level tensor path (mma.sync) for the rank-r adapter contractions; falls back to simt_* when unsupported
+int mma_lora_down(const void* x, const void* a, int64_t T, int64_t K, int r, int act_dtype, void* t_save,
+                  cudaStream_t st);
+int mma_lora_dt(const void* dy, const void* b, int64_t T, int64_t N, int r, float scale, int act_dtype, void* dt_save,
+                cudaStream_t st);
+int mma_dab(const void* dy, const void* x, const void* t_save, const void* dt_save, int64_t T, int64_t N, int64_t K,
+            int r, int act_dtype, float scale, void* dA, void* dB, float* ws, cudaStream_t st);
+
 // tcgen05 family
 bool tc_supported(const LayerArgs& a, bool backward);
 int tc_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st);
