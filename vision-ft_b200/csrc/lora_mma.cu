@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t pack_pair<__half>(float lo, float hi) {
 // ---------------------------------------------------------------------------------------------
 // rowproj: CTA = 2 warps = 32 token rows; contraction streamed in chunks of 128 through a 4-stage ring
 // ---------------------------------------------------------------------------------------------
-constexpr int kRpTok = 32, kRpChunk = 128, kRpStages = 4, kRpThreads = 64;
+constexpr int kRpTok = 32, kRpChunk = 128, kRpStages = 8, kRpThreads = 64;  // 7 x 8 KB of x in flight per CTA
 
 template <int kNT>
 struct RowProjSmem {
@@ -121,7 +121,15 @@ lora_rowproj_kernel(const ActT* __restrict__ M, const ActT* __restrict__ V, int6
         const bool ok = j < r && c < C;
         cp_async_16(vb + j * 256 + ((chunk ^ (j & 7)) << 4), ok ? (const void*)(V + (int64_t)j * C + c) : (const void*)V, ok);
       }
-    } else {  // V = [C, r]: rows c, r values each, copied in 8-byte units
+    } else if ((r & 7) == 0) {  // V = [C, r]: rows c, r values each, copied in 16-byte units
+      const int units = r >> 3;
+      for (int i = threadIdx.x; i < kRpChunk * units; i += kRpThreads) {
+        const int row = i / units, u = i - row * units;
+        const int64_t c = c0 + row;
+        const bool ok = c < C;
+        cp_async_16(vb + row * (RP * 2) + u * 16, ok ? (const void*)(V + c * r + u * 8) : (const void*)V, ok);
+      }
+    } else {  // ... or in 8-byte units (r = 4, 12, ...)
       const int units = r >> 2;
       for (int i = threadIdx.x; i < kRpChunk * units; i += kRpThreads) {
         const int row = i / units, u = i - row * units;
@@ -197,7 +205,7 @@ lora_rowproj_kernel(const ActT* __restrict__ M, const ActT* __restrict__ V, int6
 // ---------------------------------------------------------------------------------------------
 // colproj: CTA = 4 warps = 128 output columns (32 per warp); tokens of this split streamed 32 at a time
 // ---------------------------------------------------------------------------------------------
-constexpr int kCpCols = 128, kCpTok = 32, kCpStages = 4, kCpThreads = 128;
+constexpr int kCpCols = 128, kCpTok = 32, kCpStages = 6, kCpThreads = 128;
 
 template <int kNT>
 struct ColProjSmem {
@@ -398,8 +406,7 @@ int mma_lora_down(const void* x, const void* a, int64_t T, int64_t K, int r, int
 int mma_lora_dt(const void* dy, const void* b, int64_t T, int64_t N, int r, float scale, int act_dtype, void* dt_save,
                 cudaStream_t st) {
   if (T == 0) return VFT_OK;
-  if (!mma_lora_supported(act_dtype, N, r) || r % 4 != 0 || !aligned16(dy) || (reinterpret_cast<uintptr_t>(b) & 7u) ||
-      !aligned16(dt_save))
+  if (!mma_lora_supported(act_dtype, N, r) || r % 4 != 0 || !aligned16(dy) || !aligned16(b) || !aligned16(dt_save))
     return simt_lora_dt(dy, b, T, N, r, scale, act_dtype, dt_save, st);
   if (act_dtype == VFT_BF16) return rowproj_rank<__nv_bfloat16, true>(dy, b, T, N, r, scale, dt_save, st);
   return rowproj_rank<__half, true>(dy, b, T, N, r, scale, dt_save, st);

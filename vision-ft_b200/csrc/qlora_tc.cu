@@ -44,15 +44,21 @@ namespace {
 
 constexpr int kBM = 128;        // features per CTA tile (MMA M)
 constexpr int kBK = 64;         // contraction elements per step (= NF4 blocksize)
-constexpr int kStages = 4;      // pipeline depth: one stage = activation tile (TMA) + decoded weight tile
-constexpr int kGroups = 4;      // decode groups of 128 threads; group g fills stage g (kGroups == kStages)
+constexpr int kGroups = 4;      // decode groups of 128 threads; group g decodes blocks g, g + 4, ...
 constexpr int kDecodeWarp0 = 4;
 constexpr int kThreads = (kDecodeWarp0 + 4 * kGroups) * 32;  // 640
 constexpr int kATileBytes = kBM * kBK * 2;                   // 16 KB operand tile
 
-template <int BN>
+// kPair: two CTAs on the two SMs of a TPC form one tcgen05 cta_group::2 pair.  The pair computes 256 features
+// x BN tokens: each CTA decodes ITS 128 weight rows and TMA-loads HALF of the activation tile (BN/2 token rows),
+// so per CTA the shared-memory traffic per step drops from 96 KB (MMA operand reads 48 + TMA 32 + decode 16) to
+// 64 KB, the L2->SM traffic halves, and the smaller stage allows a 6-deep ring.  The single-CTA form was
+// shared-memory-bandwidth bound at ~690 cycles per 512-cycle step (profiles/r01_*).
+template <int BN, bool kPair>
 struct SmemLayout {
-  static constexpr int act_bytes = BN * kBK * 2;
+  static constexpr int kStages = kPair ? 6 : 4;  // one stage = activation tile (TMA) + decoded weight tile
+  static constexpr int act_rows = kPair ? BN / 2 : BN;
+  static constexpr int act_bytes = act_rows * kBK * 2;
   static constexpr int act_off = 0;
   static constexpr int a_off = act_off + kStages * act_bytes;
   static constexpr int bar_off = a_off + kStages * kATileBytes;
@@ -95,11 +101,13 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
   return v;
 }
 
-template <typename ActT, bool kBackward, int BN>
+template <typename ActT, bool kBackward, int BN, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_lora,
                 const TcParams p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, kPair>;
+  constexpr int kStages = L::kStages;
+  const uint32_t cta_rank = kPair ? ptx::cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
@@ -121,6 +129,12 @@ qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_consta
   // round trip) under the 512 cycles the four MMAs of a step take.
   auto bar_full = [&](int s) { return smem_base + L::bar_off + 8 * s; };
   auto bar_empty = [&](int s) { return smem_base + L::bar_off + 8 * (kStages + s); };
+  // pair: full[] lives in the leader CTA (both producers' TMA bytes and all 8 decode warps arrive there); empty[]
+  // and accum exist in both CTAs and are arrived on by a multicast tcgen05.commit.
+  // Plain (CTA-scope) waits also in pair mode: the data the waits order travels through the async proxy (TMA
+  // bytes, tcgen05.commit, generic stores published by fence.proxy.async), and a cluster-scope acquire costs an
+  // L1 invalidate per wait (measured: 930 vs 480 cycles per step for the bare handshake).
+  auto wait_bar = [&](uint32_t bar, uint32_t parity) { ptx::mbar_wait(bar, parity); };
   const uint32_t bar_accum = smem_base + L::bar_off + 8 * (L::n_bars - 1);
   const uint32_t tmem_slot = bar_accum + 8;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L::bar_off + 8 * L::n_bars);
@@ -131,15 +145,19 @@ qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_consta
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(bar_full(s), 5);
+      ptx::mbar_init(bar_full(s), kPair ? 9 : 5);
       ptx::mbar_init(bar_empty(s), 1);
     }
     ptx::mbar_init(bar_accum, 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 2) ptx::tmem_alloc<BN>(tmem_slot);
+  if (warp == 2) {
+    if (kPair) ptx::tmem_alloc_pair<BN>(tmem_slot);
+    else ptx::tmem_alloc<BN>(tmem_slot);
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kPair) ptx::cluster_sync();  // barrier inits of both CTAs visible before any remote arrive / multicast
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_d = *tmem_slot_gen;
   if (threadIdx.x == 0) tl_mark(p, 1);
@@ -149,27 +167,39 @@ qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_consta
     if (ptx::elect_one()) {
       for (int b = 0; b < n_blocks; ++b) {
         const int s = b % kStages;
-        ptx::mbar_wait(bar_empty(s), ((uint32_t)(b / kStages) & 1u) ^ 1u);
+        wait_bar(bar_empty(s), ((uint32_t)(b / kStages) & 1u) ^ 1u);
         const uint32_t dst = smem_base + L::act_off + s * L::act_bytes;
         if (p.debug & 8) {
-          ptx::mbar_arrive(bar_full(s));
+          if (cta_rank == 0) ptx::mbar_arrive(bar_full(s));
           continue;
         }
-        ptx::mbar_arrive_expect_tx(bar_full(s), L::act_bytes);
-        if (b < n_main)
-          ptx::tma_load_2d(&map_act, dst, bar_full(s), b * kBK, (int)t0);
-        else
-          ptx::tma_load_2d(&map_lora, dst, bar_full(s), 0, (int)t0);
+        if (kPair) {
+          // the leader arms its barrier for the bytes of BOTH halves; each CTA loads its BN/2 token rows
+          if (cta_rank == 0) ptx::mbar_arrive_expect_tx(bar_full(s), 2 * L::act_bytes);
+          const uint32_t leader_bar = ptx::mapa(bar_full(s), 0);
+          const int trow = (int)t0 + (int)cta_rank * L::act_rows;
+          if (b < n_main)
+            ptx::tma_load_2d_pair(&map_act, dst, leader_bar, b * kBK, trow);
+          else
+            ptx::tma_load_2d_pair(&map_lora, dst, leader_bar, 0, trow);
+        } else {
+          ptx::mbar_arrive_expect_tx(bar_full(s), L::act_bytes);
+          if (b < n_main)
+            ptx::tma_load_2d(&map_act, dst, bar_full(s), b * kBK, (int)t0);
+          else
+            ptx::tma_load_2d(&map_lora, dst, bar_full(s), 0, (int)t0);
+        }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------- MMA issuer
-    if (ptx::elect_one()) {
+    // ------------------------------------------------------------- MMA issuer (leader CTA only in a pair)
+    if (cta_rank == 0 && ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(std::is_same<ActT, __nv_bfloat16>::value,
-                                                     /*a_mn_major=*/kBackward, /*b_mn_major=*/false, kBM, BN);
+                                                     /*a_mn_major=*/kBackward, /*b_mn_major=*/false,
+                                                     kPair ? 2 * kBM : kBM, BN);
       for (int b = 0; b < n_blocks; ++b) {
         const int s = b % kStages;
-        ptx::mbar_wait(bar_full(s), (uint32_t)(b / kStages) & 1u);
+        wait_bar(bar_full(s), (uint32_t)(b / kStages) & 1u);
         ptx::tc_fence_after();
         if (b == 0) tl_mark(p, 2);
         if (b == 8) tl_mark(p, 3);
@@ -187,11 +217,15 @@ qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_consta
           // advance 16 contraction elements: 32 B inside a K-major swizzle row, 16 rows (2048 B) MN-major
           const uint64_t a_k = a_desc + (uint64_t)(kBackward ? (k * 2048) >> 4 : (k * 32) >> 4);
           const uint64_t b_k = b_desc + (uint64_t)((k * 32) >> 4);
-          ptx::umma_ss(tmem_d, a_k, b_k, idesc, (b | k) != 0 ? 1u : 0u);
+          if (kPair) ptx::umma_ss_pair(tmem_d, a_k, b_k, idesc, (b | k) != 0 ? 1u : 0u);
+          else ptx::umma_ss(tmem_d, a_k, b_k, idesc, (b | k) != 0 ? 1u : 0u);
         }
-        ptx::umma_commit(bar_empty(s));  // the stage is reusable once these MMAs have read it
+        // the stage is reusable (in both CTAs of a pair) once these MMAs have read it
+        if (kPair) ptx::umma_commit_pair(bar_empty(s));
+        else ptx::umma_commit(bar_empty(s));
       }
-      ptx::umma_commit(bar_accum);
+      if (kPair) ptx::umma_commit_pair(bar_accum);
+      else ptx::umma_commit(bar_accum);
     }
   } else if (warp >= kDecodeWarp0) {
     // ------------------------------------------------------------- decode warps
@@ -249,7 +283,7 @@ qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_consta
         uint32_t v[8][4];
 #pragma unroll
         for (int c = 0; c < 8; ++c) nf4_decode_word(words[c], lut, v[c]);
-        ptx::mbar_wait(bar_empty(sa), ((uint32_t)(b / kStages) & 1u) ^ 1u);
+        wait_bar(bar_empty(sa), ((uint32_t)(b / kStages) & 1u) ^ 1u);
         if (!(p.debug & 1)) {
 #pragma unroll
           for (int c = 0; c < 8; ++c)
@@ -258,7 +292,7 @@ qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_consta
       } else {
         // adapter step: forward row n of scale*B (r values), backward row j of A (64 in-features)
         const ActT* lw = static_cast<const ActT*>(p.lora_w);
-        ptx::mbar_wait(bar_empty(sa), ((uint32_t)(b / kStages) & 1u) ^ 1u);
+        wait_bar(bar_empty(sa), ((uint32_t)(b / kStages) & 1u) ^ 1u);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint32_t v[4] = {0u, 0u, 0u, 0u};
@@ -285,11 +319,14 @@ qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_consta
       }
       ptx::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_full(sa));
+      if (lane == 0) {
+        if (kPair) ptx::mbar_arrive_cluster(ptx::mapa(bar_full(sa), 0));
+        else ptx::mbar_arrive(bar_full(sa));
+      }
     }
 
     // ----------------------------------------------------------- epilogue: 16 warps, 32-column chunks
-    ptx::mbar_wait(bar_accum, 0);
+    wait_bar(bar_accum, 0);
     ptx::tc_fence_after();
     if (dw == 0 && lane == 0) tl_mark(p, 5);
     const int64_t feat = f0 + m;
@@ -315,10 +352,12 @@ qlora_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_consta
     if (dw == 0 && lane == 0) tl_mark(p, 6);
   }
 
-  __syncthreads();
+  if (kPair) ptx::cluster_sync();  // the peer may still be reading / being read
+  else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<BN>(tmem_d);
+    if (kPair) ptx::tmem_dealloc_pair<BN>(tmem_d);
+    else ptx::tmem_dealloc<BN>(tmem_d);
   }
   if (threadIdx.x == 0) tl_mark(p, 7);
 }
@@ -374,19 +413,19 @@ static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* bas
   return VFT_OK;
 }
 
-template <typename ActT, bool kBackward, int BN>
+template <typename ActT, bool kBackward, int BN, bool kPair>
 static int launch_tc(const LayerArgs& a, const void* act, void* out, const void* lora_act, cudaStream_t st) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, kPair>;
   const int64_t OUT = kBackward ? a.K : a.N;
   const int64_t RED = kBackward ? a.N : a.K;
   const CUtensorMapDataType dt =
       std::is_same<ActT, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap map_act, map_lora;
-  int rc = make_map_2d(&map_act, dt, act, (uint64_t)RED, (uint64_t)a.T, (uint64_t)RED * 2, kBK, BN,
+  int rc = make_map_2d(&map_act, dt, act, (uint64_t)RED, (uint64_t)a.T, (uint64_t)RED * 2, kBK, L::act_rows,
                        CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != VFT_OK) return rc;
   if (a.r > 0) {
-    rc = make_map_2d(&map_lora, dt, lora_act, VFT_LORA_LD, (uint64_t)a.T, VFT_LORA_LD * 2, kBK, BN,
+    rc = make_map_2d(&map_lora, dt, lora_act, VFT_LORA_LD, (uint64_t)a.T, VFT_LORA_LD * 2, kBK, L::act_rows,
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != VFT_OK) return rc;
   } else {
@@ -401,19 +440,41 @@ static int launch_tc(const LayerArgs& a, const void* act, void* out, const void*
   p.out = out;
   const char* dbg = getenv("VFT_TC_DEBUG");
   p.debug = dbg ? atoi(dbg) : 0;
-  auto kern = qlora_tc_kernel<ActT, kBackward, BN>;
+  auto kern = qlora_tc_kernel<ActT, kBackward, BN, kPair>;
   VFT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn_bytes));
-  dim3 grid((unsigned)ceil_div64(OUT, kBM), (unsigned)ceil_div64(a.T, BN));
-  kern<<<grid, kThreads, L::dyn_bytes, st>>>(map_act, map_lora, p);
+  if (kPair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * ceil_div64(OUT, 2 * kBM)), (unsigned)ceil_div64(a.T, BN));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = L::dyn_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VFT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, map_act, map_lora, p));
+  } else {
+    dim3 grid((unsigned)ceil_div64(OUT, kBM), (unsigned)ceil_div64(a.T, BN));
+    kern<<<grid, kThreads, L::dyn_bytes, st>>>(map_act, map_lora, p);
+  }
   VFT_CUDA_OK(cudaGetLastError());
   return VFT_OK;
 }
 
 template <typename ActT, bool kBackward>
 static int launch_tc_bn(const LayerArgs& a, const void* act, void* out, const void* lora_act, cudaStream_t st) {
-  if (a.T > 128) return launch_tc<ActT, kBackward, 256>(a, act, out, lora_act, st);
-  if (a.T > 64) return launch_tc<ActT, kBackward, 128>(a, act, out, lora_act, st);
-  return launch_tc<ActT, kBackward, 64>(a, act, out, lora_act, st);
+  const int64_t OUT = kBackward ? a.K : a.N;
+  // Measured on B200 (T=4096, 3072x3072): 86.8 us with the pair vs 83.2 us without -- this kernel is bound by the
+  // decode warps' ALU work, not by shared-memory bandwidth, so pairing alone buys nothing.  Opt-in for triage.
+  const char* pair = getenv("VFT_TC_PAIR");
+  if (a.T > 128 && OUT >= 2 * kBM && pair && pair[0] == '1')
+    return launch_tc<ActT, kBackward, 256, true>(a, act, out, lora_act, st);
+  if (a.T > 128) return launch_tc<ActT, kBackward, 256, false>(a, act, out, lora_act, st);
+  if (a.T > 64) return launch_tc<ActT, kBackward, 128, false>(a, act, out, lora_act, st);
+  return launch_tc<ActT, kBackward, 64, false>(a, act, out, lora_act, st);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
