@@ -260,6 +260,48 @@ def test_identity_activation_reproduces_weight_bit_exact(ops, N, K):
     assert torch.equal(x.grad, w_deq)
 
 
+# persistent CTA-pair kernel (qlora_tc2.cu): forced tile shapes on ragged problems, so that partial token blocks,
+# unused second accumulators, feature blocks whose second CTA is out of range and multi-tile persistence are all hit
+@pytest.mark.parametrize("nacc", ["1x32", "2x48", "1x176", "2x176", "1x256", "2x256", "auto"])
+@pytest.mark.parametrize("T,K,N,r,bias", [(700, 256, 640, 16, True), (1300, 192, 384, 0, False), (333, 64, 136, 8, False)])
+def test_pair_kernel_forced_tiles(ops, monkeypatch, nacc, T, K, N, r, bias):
+    monkeypatch.setenv("VFT_TC2", "1")
+    if nacc != "auto":
+        monkeypatch.setenv("VFT_TC2_NACC", nacc)
+    w, x, dy, a, b, bv = _make_case(T, K, N, r, seed=T + K + N + r, bias=bias)
+    p, am = nf4_oracle.nf4_quantize(w)
+    w_deq = qlora_oracle.dequant_weight(p, am, (N, K), "bfloat16")
+    ref = qlora_oracle.qlora_linear_ref(x, w_deq, bv, a, b, 1.0, dy)
+    truth = qlora_oracle.qlora_linear_truth(x, w_deq, bv, a, b, 1.0, dy)
+    out, used = _run_cuda(ops, torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), x, dy, a, b, bv, 1.0, N, K,
+                          torch.bfloat16, TC)
+    assert used == TC
+    _check(out, ref, truth, ("y", "dx") + (("da", "db") if r else ()), f"pair{nacc}-T{T}K{K}N{N}r{r}")
+
+
+@pytest.mark.parametrize("stages", ["4", "5", "8"])
+def test_pair_kernel_many_tiles_per_pair(ops, monkeypatch, stages):
+    """More tiles than SM pairs with a tiny tile (1x32): every pair walks several tiles, ring phases wrap many times."""
+    monkeypatch.setenv("VFT_TC2", "1")
+    monkeypatch.setenv("VFT_TC2_NACC", "1x32")
+    monkeypatch.setenv("VFT_TC2_STAGES", stages)
+    N, K, T = 1024, 320, 2500
+    g = torch.Generator(device="cuda").manual_seed(5)
+    w = (torch.randn(N, K, generator=g, device="cuda") * 0.02).to(torch.bfloat16)
+    packed, absmax = ops.nf4_quantize(w)
+    w_deq = ops.nf4_dequantize(packed, absmax, (N, K), torch.bfloat16)
+    x = torch.randn(T, K, generator=g, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    dy = torch.randn(T, N, generator=g, device="cuda").to(torch.bfloat16)
+    ops.force_path(TC)
+    y = ops.qlora_linear(x, packed, absmax, None, None, None, 0.0, N, K, 64, torch.bfloat16)
+    y.backward(dy)
+    ops.force_path(0)
+    ref_y = (x.detach().float() @ w_deq.float().t())
+    ref_dx = (dy.float() @ w_deq.float())
+    assert qlora_oracle.rel_l2(y.detach().cpu(), ref_y.cpu()) < 4e-3
+    assert qlora_oracle.rel_l2(x.grad.cpu(), ref_dx.cpu()) < 4e-3
+
+
 def test_config1_full_size_vs_oracle(ops):
     """BASELINE.json config #1: 3072x3072 NF4 + LoRA r=16, 4096 tokens as [2, 2048, 3072] (SURVEY.md 8d seeds)."""
     N = K = 3072

@@ -30,7 +30,7 @@ def main():
         for i in range(40): fn(i)
         b.record(); torch.cuda.synchronize()
         res[name] = a.elapsed_time(b) / 40 * 1e3
-    if int(os.environ.get("VFT_TC_DEBUG", "0")) & 16:
+    if int(os.environ.get("VFT_TC_DEBUG", "0")) & 16 and T < 512:
         import ctypes
         fwd(0); torch.cuda.synchronize()
         buf = (ctypes.c_ulonglong * 512)()
@@ -39,6 +39,28 @@ def main():
         c0, n0 = buf[0], buf[1]
         for i, nm in enumerate(names):
             print(f"   {nm:18s} +{buf[2*i]-c0:8d} cyc  +{(buf[2*i+1]-n0)/1e3:8.2f} us")
+    if int(os.environ.get("VFT_TC_DEBUG", "0")) & 16 and hasattr(_cabi.lib, "vft_debug_tc2_timeline") and T >= 512:
+        import ctypes
+        for nm, fn in (("fwd", fwd), ("bwd", bwd)):
+            fn(0); torch.cuda.synchronize()
+            R, C = 6, 256
+            buf = (ctypes.c_ulonglong * (R * C))()
+            _cabi.lib.vft_debug_tc2_timeline(buf, R * C)
+            rows = [[buf[r * C + c] for c in range(C)] for r in range(R)]
+            t0 = min(v for v in rows[5][:4] if v) if any(rows[5][:4]) else rows[0][0]
+            def rel(v): return (v - t0) if v else -1
+            print(f"  [{nm}] pair-kernel timeline (cycles since first producer wait), leader CTA of pair 0")
+            print("   step: mma_full_seen  mma_commit   | prod_empty_seen")
+            for g in list(range(0, 12)) + list(range(40, 56)) + list(range(88, 100)):
+                print(f"   {g:4d}: {rel(rows[0][g]):10d} {rel(rows[1][g]):10d}   | {rel(rows[5][g]):10d}")
+            print("   decode group0 (steps 0,4,8..): empty_seen, arrived")
+            for i in list(range(0, 6)) + list(range(10, 14)):
+                print(f"   {4*i:4d}: {rel(rows[2][i]):10d} {rel(rows[3][i]):10d}")
+            print("   epilogue: acc_full seen / drained per tile:", [rel(v) for v in rows[4][:6]])
+            steps = [v for v in rows[0] if v]
+            if len(steps) > 20:
+                d = [steps[i + 1] - steps[i] for i in range(8, len(steps) - 1)]
+                print(f"   mma steps seen {len(steps)}, median step interval {sorted(d)[len(d)//2]} cyc, mean {sum(d)/len(d):.0f}")
     fl = 2 * T * N * K
     print(f"VFT_TC_DEBUG={os.environ.get('VFT_TC_DEBUG','0'):>2} T={T} N={N} K={K}: fwd {res['fwd']:.1f} us ({fl/res['fwd']/1e6:.0f} TF/s)  bwd {res['bwd']:.1f} us ({fl/res['bwd']/1e6:.0f} TF/s)")
 

@@ -1,0 +1,592 @@
+// Persistent CTA-pair form of the fused NF4-dequant + LoRA GEMM (tcgen05 cta_group::2, sm_100a), used for
+// token counts large enough to fill the machine.  Same arithmetic and operand layouts as qlora_tc.cu
+// (read its header first); what changes is the schedule:
+//
+//   * One cluster of two CTAs per TPC, launched once per SM pair and kept resident: each pair walks a static
+//     list of output tiles (tile = 256 features x n_acc*N_acc tokens), so barrier/TMEM set-up, the first
+//     cold global loads and the tensor-map fetches are paid once per SM instead of once per tile.
+//   * A decoded weight tile (128 features x 64 contraction elements per CTA) feeds up to TWO accumulators of
+//     N_acc <= 256 tokens each (all 512 TMEM columns).  The first kernel was bound by the decode warps' ALU
+//     work (~480 ALU-pipe cycles per tile against 512 tensor cycles at 256 tokens; profiles/r01_*): doubling
+//     the tokens per decoded tile halves that ratio, and pairing the CTAs halves the activation traffic through
+//     shared memory (each CTA stages N_acc/2 token rows per accumulator; the tensor cores of both SMs read both
+//     halves), which is what keeps 128 B/clk of shared-memory bandwidth sufficient.
+//   * N_acc is a run-time multiple of 16 chosen on the host so that the tile count is a near-multiple of the
+//     number of SM pairs (T = 4096, 3072 features: 2 x 176 tokens -> 144 tiles on 74 pairs, 2 full waves,
+//     instead of 96 tiles of 512 tokens = 1.3 waves).
+//   * The epilogue has its own four warps and drains accumulator a of tile i (tcgen05.ld -> bias -> convert
+//     -> global) while the decode warps and the MMA issuer are already on tile i+1; the issuer only waits for
+//     "accumulator a drained" before its first MMA into a.
+//
+// Warp roles (768 threads per CTA, both CTAs of a pair run all roles except the MMA issuer):
+//   warp 20     TMA producer: for every stage, n_acc boxes [N_acc/2 tokens x 64] of the activations
+//               (SWIZZLE_128B); completion bytes of BOTH CTAs are counted on the leader's barrier
+//   warp 23     MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::f16, M = 256, N = N_acc, K = 16;
+//               multicast tcgen05.commit frees the stage in both CTAs / publishes the accumulators
+//   warp 21     TMEM allocation (512 columns per CTA)
+//   warps 16-19 epilogue, one TMEM lane quadrant each
+//   warps 0-15  decode: four groups of 128 threads, group g owns pipeline steps g, g+4, ...
+#include <stdlib.h>
+
+#include <type_traits>
+
+#include "nf4_lut.cuh"
+#include "ptx_sm100.cuh"
+#include "tensor_map.cuh"
+#include "vft_common.cuh"
+
+namespace vft {
+namespace {
+
+constexpr int kBM = 128;   // features per CTA (256 per pair = MMA M)
+constexpr int kBK = 64;    // contraction elements per pipeline step (= NF4 blocksize)
+constexpr int kGroups = 4;
+// Warp numbering follows the issue arbiter, which favours HIGHER warp ids within a scheduler (measured: with the
+// MMA issuer in warp 1 under 16 ALU-saturating decode warps it needed ~1400 cycles per pipeline step for 8 MMAs,
+// one wait and one commit; profiles/r01_*): the latency-critical single-thread roles sit on top, the decode
+// warps at the bottom.
+constexpr int kDecWarp0 = 0;                    // warps 0..15: decode
+constexpr int kEpiWarp0 = 4 * kGroups;          // warps 16..19: epilogue (warp % 4 = TMEM lane quadrant)
+constexpr int kTmaWarp = kEpiWarp0 + 4;         // warp 20: TMA producer
+constexpr int kAllocWarp = kEpiWarp0 + 5;       // warp 21: TMEM allocation
+constexpr int kMmaWarp = kEpiWarp0 + 7;         // warp 23: MMA issuer
+constexpr int kThreads = (kEpiWarp0 + 8) * 32;  // 768
+constexpr int kATileBytes = kBM * kBK * 2;                // 16 KB decoded weight tile
+constexpr int kMaxStages = 8;
+constexpr int kMaxAcc = 2;
+constexpr int kAccCols = 256;  // TMEM column pitch between the accumulators
+constexpr int kTmemCols = 512;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr int kBarBytes = (2 * kMaxStages + 1 + kMaxAcc) * 8 + 16;
+constexpr int kEpiBytes = 2 * 32 * kBM * 2;  // two staging tiles [32 tokens][128 features] of 16-bit outputs
+
+struct Tc2Params {
+  int64_t T, N, K;
+  int r;
+  int qdtype;
+  float scale;
+  const uint8_t* packed;
+  const float* absmax;
+  const void* bias;
+  const void* lora_w;  // forward: B [N, r]; backward: A [r, K]
+  void* out;           // forward: Y [T, N]; backward: dX [T, K]
+  int n_acc, N_acc;    // accumulators per tile, tokens per accumulator (multiple of 16, <= 256)
+  int stages;
+  int b_bytes;      // bytes of one accumulator's activation box in one CTA: (N_acc / 2) * 128
+  int stage_bytes;  // kATileBytes + n_acc * b_bytes
+  int n_fblk;       // feature blocks of 256
+  int n_tiles;      // n_fblk * token blocks
+  int debug;        // VFT_TC_DEBUG triage mask (results are garbage when non-zero): 1 = no decode stores,
+                    // 2 = no MMAs, 4 = no epilogue stores, 8 = no TMA loads
+};
+
+// Timeline of the leader CTA of pair 0 for performance triage (VFT_TC_DEBUG & 16): SM clock per event.
+constexpr int kTlRows = 6, kTlCols = 256;
+__device__ unsigned long long g_tc2_timeline[kTlRows * kTlCols];
+__device__ __forceinline__ void tl_mark(const Tc2Params& p, int row, int col) {
+  if ((p.debug & 16) && blockIdx.x == 0 && col < kTlCols) g_tc2_timeline[row * kTlCols + col] = (unsigned long long)clock64();
+}
+
+__device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+template <typename ActT, bool kBackward>
+__global__ void __launch_bounds__(kThreads, 1)
+qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_lora,
+                 const __grid_constant__ CUtensorMap map_out, const Tc2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+
+  const uint32_t rank = ptx::cluster_ctarank();  // 0 = leader (issues the MMAs, owns the full/acc_empty barriers)
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t OUT = kBackward ? p.K : p.N;  // feature dimension of this GEMM
+  const int64_t RED = kBackward ? p.N : p.K;  // contraction dimension
+  const int n_main = (int)((RED + kBK - 1) / kBK);
+  const int n_blocks = n_main + (p.r > 0 ? 1 : 0);
+  const int KB = (int)(p.K / kBK);  // absmax entries per weight row
+  const int S = p.stages;
+  const int n_pairs = (int)(gridDim.x >> 1);
+  const int pair = (int)(blockIdx.x >> 1);
+  const int tok_tile = p.n_acc * p.N_acc;
+
+  // shared memory: [S stages: decoded weight tile | n_acc activation boxes][epilogue staging][barriers, TMEM slot]
+  const uint32_t bar_base = smem_base + (uint32_t)(S * p.stage_bytes + kEpiBytes);
+  auto bar_full = [&](int s) { return bar_base + 8u * s; };
+  auto bar_empty = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  const uint32_t bar_acc_full = bar_base + 8u * (2 * kMaxStages);
+  auto bar_acc_empty = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 1 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + S * p.stage_bytes + kEpiBytes + 8 * (2 * kMaxStages + 1 + kMaxAcc));
+  auto stage_a = [&](int s) { return smem_base + (uint32_t)(s * p.stage_bytes); };
+  auto stage_b = [&](int s, int a) { return smem_base + (uint32_t)(s * p.stage_bytes + kATileBytes + a * p.b_bytes); };
+  // accumulators of a tile that hold at least one real token (all roles derive it the same way)
+  auto accs_of = [&](int64_t t0) -> int {
+    const int64_t left = p.T - t0;
+    return left >= tok_tile ? p.n_acc : (int)((left + p.N_acc - 1) / p.N_acc);
+  };
+
+  if (warp == kTmaWarp && ptx::elect_one()) {
+    ptx::tma_prefetch_desc(&map_act);
+    if (p.r > 0) ptx::tma_prefetch_desc(&map_lora);
+    ptx::tma_prefetch_desc(&map_out);
+  }
+  if (warp == kMmaWarp && ptx::elect_one()) {
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(bar_full(s), 1 + 2 * 4);  // leader's producer (expect_tx) + the decode warps of both CTAs
+      ptx::mbar_init(bar_empty(s), 1);         // multicast tcgen05.commit
+    }
+    ptx::mbar_init(bar_acc_full, 1);
+    for (int a = 0; a < kMaxAcc; ++a) ptx::mbar_init(bar_acc_empty(a), 2 * 4);  // epilogue warps of both CTAs
+    ptx::fence_mbar_init();
+  }
+  if (warp == kAllocWarp) ptx::tmem_alloc_pair<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();  // barrier inits of both CTAs visible before any remote arrive / multicast commit
+  ptx::tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_gen;
+
+  if (warp == kTmaWarp) {
+    // ------------------------------------------------------------- TMA producer (activations)
+    if (ptx::elect_one()) {
+      int g = 0, s = 0;
+      uint32_t empty_par = 1;
+      for (int tile = pair; tile < p.n_tiles; tile += n_pairs) {
+        const int64_t t0 = (int64_t)(tile / p.n_fblk) * tok_tile;
+        const int na = accs_of(t0);
+        for (int b = 0; b < n_blocks; ++b, ++g) {
+          ptx::mbar_wait(bar_empty(s), empty_par);
+          tl_mark(p, 5, g);
+          if (p.debug & 8) {
+            if (rank == 0) ptx::mbar_arrive(bar_full(s));
+          } else {
+            // the leader arms its barrier for the bytes of BOTH CTAs; each CTA loads its N_acc/2 token rows
+            if (rank == 0) ptx::mbar_arrive_expect_tx(bar_full(s), (uint32_t)(2 * na * p.b_bytes));
+            const uint32_t leader_bar = ptx::mapa(bar_full(s), 0);
+            for (int a = 0; a < na; ++a) {
+              const int trow = (int)(t0 + (int64_t)a * p.N_acc) + (int)rank * (p.N_acc >> 1);
+              if (b < n_main)
+                ptx::tma_load_2d_pair(&map_act, stage_b(s, a), leader_bar, b * kBK, trow);
+              else
+                ptx::tma_load_2d_pair(&map_lora, stage_b(s, a), leader_bar, 0, trow);
+            }
+          }
+          if (++s == S) {
+            s = 0;
+            empty_par ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------- MMA issuer (leader CTA only)
+    // The whole warp walks the loop with warp-uniform state (descriptors stay in uniform registers; inside an
+    // elect_one region the compiler has to treat them as per-thread values and pays an R2UR chain per MMA);
+    // only the tcgen05 instructions themselves are issued by one elected lane.  Ring stage and parity are
+    // tracked incrementally -- the first version spent ~1400 cycles per step in this thread (8 MMAs, two integer
+    // divisions, descriptor rebuilds), twice the 704 cycles the MMAs of a 2 x 176-token step need.
+    if (rank == 0) {
+      const uint32_t idesc = ptx::make_idesc_f16(std::is_same<ActT, __nv_bfloat16>::value,
+                                                 /*a_mn_major=*/kBackward, /*b_mn_major=*/false, 2 * kBM, p.N_acc);
+      // advance 16 contraction elements: 32 B inside a K-major swizzle row, 16 rows (2048 B) MN-major
+      constexpr uint32_t kAStep = kBackward ? (2048u >> 4) : (32u >> 4);
+      constexpr uint32_t kBStep = 32u >> 4;
+      const int k_lora = (p.r + 15) / 16;
+      const bool do_mma = !(p.debug & 2);
+      int g = 0, s = 0;
+      uint32_t full_par = 0, acc_par = 1;
+      for (int tile = pair; tile < p.n_tiles; tile += n_pairs) {
+        const int64_t t0 = (int64_t)(tile / p.n_fblk) * tok_tile;
+        const int na = accs_of(t0);
+        for (int b = 0; b < n_blocks; ++b, ++g) {
+          ptx::mbar_wait(bar_full(s), full_par);
+          if (b == 0) {  // the epilogue must have drained the accumulators of the previous tile
+            for (int a = 0; a < na; ++a) ptx::mbar_wait(bar_acc_empty(a), acc_par);
+          }
+          ptx::tc_fence_after();
+          tl_mark(p, 0, g);
+          // A: forward  K-major  [128 rows x 128 B], 8-row groups 1024 B apart
+          //    backward MN-major [2 atoms of 64 features][64 contraction rows x 128 B]: atoms 8192 B apart
+          const uint64_t a_desc = kBackward ? ptx::make_smem_desc_sw128(stage_a(s), 8192, 1024)
+                                            : ptx::make_smem_desc_sw128(stage_a(s), 16, 1024);
+          const uint64_t b_desc0 = ptx::make_smem_desc_sw128(stage_b(s, 0), 16, 1024);
+          const uint64_t b_desc1 = ptx::make_smem_desc_sw128(stage_b(s, 1), 16, 1024);
+          const uint32_t acc0 = b > 0 ? 1u : 0u;
+          if (ptx::elect_one()) {
+            if (do_mma) {
+              if (b < n_main) {
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k)
+                  ptx::umma_ss_pair(tmem_d, a_desc + k * kAStep, b_desc0 + k * kBStep, idesc, k > 0 ? 1u : acc0);
+                if (na > 1) {
+#pragma unroll
+                  for (int k = 0; k < kBK / 16; ++k)
+                    ptx::umma_ss_pair(tmem_d + kAccCols, a_desc + k * kAStep, b_desc1 + k * kBStep, idesc,
+                                      k > 0 ? 1u : acc0);
+                }
+              } else {  // adapter step: ceil(r / 16) MMAs per accumulator
+                for (int k = 0; k < k_lora; ++k)
+                  ptx::umma_ss_pair(tmem_d, a_desc + k * kAStep, b_desc0 + k * kBStep, idesc, (b | k) != 0 ? 1u : 0u);
+                if (na > 1) {
+                  for (int k = 0; k < k_lora; ++k)
+                    ptx::umma_ss_pair(tmem_d + kAccCols, a_desc + k * kAStep, b_desc1 + k * kBStep, idesc,
+                                      (b | k) != 0 ? 1u : 0u);
+                }
+              }
+            }
+            ptx::umma_commit_pair(bar_empty(s));  // the stage is reusable in both CTAs once these MMAs have read it
+            if (b == n_blocks - 1) ptx::umma_commit_pair(bar_acc_full);  // tile complete -> epilogue warps, both CTAs
+          }
+          __syncwarp();
+          tl_mark(p, 1, g);
+          if (++s == S) {
+            s = 0;
+            full_par ^= 1u;
+          }
+        }
+        acc_par ^= 1u;
+      }
+    }
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
+    // ------------------------------------------------------------- epilogue warps
+    // TMEM holds D[feature (lane), token (column)] but the output is [token, feature]: each warp converts its
+    // 32 features x 32 tokens to 16-bit and writes them TRANSPOSED into a staging tile [32 tokens][128 features]
+    // (64 contiguous bytes per token per warp: conflict-free); one thread then hands the tile to the TMA store
+    // engine, which writes full 256-byte rows and clips rows >= T / features >= OUT.  Two staging tiles: the
+    // store of chunk c overlaps the TMEM load + conversion of chunk c + 1.
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int et = (warp - kEpiWarp0) * 32 + lane;
+    const uint32_t lane_base = tmem_d + ((uint32_t)(quad * 32) << 16);
+    const uint32_t epi_smem = bar_base - (uint32_t)kEpiBytes + (uint32_t)(quad * 32 + lane) * 2u;
+    uint32_t it = 0, chunk = 0;
+    for (int tile = pair; tile < p.n_tiles; tile += n_pairs, ++it) {
+      const int64_t t0 = (int64_t)(tile / p.n_fblk) * tok_tile;
+      const int na = accs_of(t0);
+      const int64_t feat0 = (int64_t)(tile % p.n_fblk) * (2 * kBM) + (int64_t)rank * kBM;
+      const int64_t feat = feat0 + quad * 32 + lane;
+      float bias_v = 0.0f;
+      if (!kBackward && p.bias != nullptr && feat < OUT) bias_v = to_f32<ActT>(static_cast<const ActT*>(p.bias)[feat]);
+      ptx::mbar_wait(bar_acc_full, it & 1u);
+      ptx::tc_fence_after();
+      if (et == 0) tl_mark(p, 4, 2 * (int)it);
+      for (int a = 0; a < na; ++a) {
+        const int64_t ta = t0 + (int64_t)a * p.N_acc;
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.N_acc; c0 += 32) {
+          const bool live = ta + c0 < p.T;  // warp-uniform; dead chunks still release the accumulator below
+          uint32_t v[32];
+          if (live) {
+            ptx::tmem_ld_32x32b_x32(lane_base + (uint32_t)(a * kAccCols + c0), v);
+            ptx::tmem_ld_wait();
+          }
+          if (c0 + 32 >= p.N_acc) {  // accumulator a is in registers / not needed: the issuer may overwrite it
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar_acc_empty(a), 0));
+          }
+          if (!live) continue;
+          const uint32_t buf = epi_smem + (chunk & 1u) * (uint32_t)(kEpiBytes / 2);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const uint32_t pk = pack2<ActT>(__uint_as_float(v[j]) + bias_v, __uint_as_float(v[j + 1]) + bias_v);
+            ptx::sts16(buf + (uint32_t)j * 256u, pk);
+            ptx::sts16(buf + (uint32_t)(j + 1) * 256u, pk >> 16);
+          }
+          ptx::fence_proxy_async_smem();
+          // the store issued one chunk ago (other staging tile) has finished READING by the time this thread
+          // reaches the barrier, so after the barrier everyone may overwrite that tile for chunk c + 1
+          if (et == 0) ptx::bulk_wait_group_read<0>();
+          ptx::named_bar_sync(1, 128);
+          if (et == 0 && feat0 < OUT && !(p.debug & 4)) {
+            const uint32_t src = buf - (uint32_t)(quad * 32 + lane) * 2u;
+            ptx::tma_store_2d(&map_out, src, (int)feat0, (int)(ta + c0));
+            if (c0 + 16 < p.N_acc) ptx::tma_store_2d(&map_out, src + 16u * 256u, (int)feat0, (int)(ta + c0 + 16));
+            ptx::bulk_commit_group();
+          }
+          ++chunk;  // live chunks alternate between the two staging tiles
+        }
+      }
+      if (et == 0) tl_mark(p, 4, 2 * (int)it + 1);
+      for (int a = na; a < p.n_acc; ++a) {  // unused accumulators of a ragged last token block: keep phases in step
+        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar_acc_empty(a), 0));
+      }
+    }
+    if (et == 0) ptx::bulk_wait_group<0>();  // all output rows written before the CTA retires
+  } else if (warp < kEpiWarp0) {
+    // ------------------------------------------------------------- decode warps
+    const int dw = warp - kDecWarp0;  // 0..15
+    const int group = dw >> 2;        // owns pipeline steps group, group + 4, ...
+    const int quad = dw & 3;
+    const int m = quad * 32 + lane;  // 0..127
+    // forward : thread m owns weight row n = f0 + m, one 64-wide k-block per step
+    // backward: thread m owns contraction row n = 64 b + (m & 63), in-feature half (m >> 6)
+    const int row = kBackward ? (m & 63) : m;
+    const int half = kBackward ? (m >> 6) : 0;
+    const uint32_t a_row_off = kBackward ? (uint32_t)(half * 8192 + (row >> 3) * 1024 + (row & 7) * 128)
+                                         : (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+    const uint32_t a_xor = (uint32_t)(row & 7) << 4;
+
+    struct Pos {
+      int b;     // pipeline step within the tile
+      int tile;  // global tile index
+    };
+    auto normalize = [&](Pos& q) {
+      while (q.b >= n_blocks) {
+        q.b -= n_blocks;
+        q.tile += n_pairs;
+      }
+    };
+    // first feature of this CTA's half of the tile (forward: out-feature n; backward: in-feature k)
+    auto f0_of = [&](int tile) -> int64_t { return (int64_t)(tile % p.n_fblk) * (2 * kBM) + (int64_t)rank * kBM; };
+
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+    float am = 0.0f;
+    auto prefetch = [&](const Pos& q) {
+      q0 = q1 = make_uint4(0, 0, 0, 0);
+      am = 0.0f;
+      if (q.tile >= p.n_tiles || q.b >= n_main) return;
+      const int64_t f0 = f0_of(q.tile);
+      int64_t wrow, wcol;  // element coordinates of this thread's quantization block in W [N, K]
+      if (kBackward) {
+        wrow = (int64_t)q.b * kBK + row;
+        wcol = f0 + half * 64;
+        if (wrow >= p.N || wcol >= p.K) return;
+      } else {
+        wrow = f0 + row;
+        wcol = (int64_t)q.b * kBK;
+        if (wrow >= p.N) return;
+      }
+      const uint8_t* c = p.packed + ((wrow * p.K + wcol) >> 1);
+      q0 = ldg_stream_u4(c);
+      q1 = ldg_stream_u4(c + 16);
+      am = __ldg(p.absmax + wrow * KB + (wcol >> 6));
+    };
+
+    Pos cur{group, pair};
+    normalize(cur);
+    prefetch(cur);
+    int s = group;  // S >= kGroups: at most one ring wrap per step of kGroups
+    uint32_t empty_parity = 1;
+    for (int g = group; cur.tile < p.n_tiles; g += kGroups) {
+      const uint32_t a_tile = stage_a(s) + a_row_off;
+      Pos nxt{cur.b + kGroups, cur.tile};
+      normalize(nxt);
+      if (cur.b < n_main) {
+        Nf4Lut lut;
+        nf4_build_lut<ActT>(am, p.qdtype, lut);
+        const uint32_t words[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        prefetch(nxt);  // next block's codes are in flight while this one is decoded
+        ptx::mbar_wait(bar_empty(s), empty_parity);
+        if (dw == 0 && lane == 0) tl_mark(p, 2, g >> 2);
+        if (!(p.debug & 1)) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t v[4];
+            nf4_decode_word(words[c], lut, v);
+            ptx::sts128(a_tile + (((uint32_t)c << 4) ^ a_xor), v[0], v[1], v[2], v[3]);
+          }
+        }
+      } else {
+        // adapter step: forward row n of scale*B (r values), backward row j of A (64 in-features)
+        const ActT* lw = static_cast<const ActT*>(p.lora_w);
+        const int64_t f0 = f0_of(cur.tile);
+        prefetch(nxt);
+        ptx::mbar_wait(bar_empty(s), empty_parity);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t v[4] = {0u, 0u, 0u, 0u};
+          if (kBackward) {
+            const int64_t k = f0 + half * 64 + c * 8;
+            if (row < p.r && k < p.K) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(lw + (int64_t)row * p.K + k));
+              v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+            }
+          } else {
+            const int64_t n = f0 + row;
+            if (n < p.N) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = c * 8 + 2 * e;
+                const float b0 = (j < p.r) ? p.scale * to_f32<ActT>(lw[n * p.r + j]) : 0.0f;
+                const float b1 = (j + 1 < p.r) ? p.scale * to_f32<ActT>(lw[n * p.r + j + 1]) : 0.0f;
+                v[e] = pack2<ActT>(b0, b1);
+              }
+            }
+          }
+          ptx::sts128(a_tile + (((uint32_t)c << 4) ^ a_xor), v[0], v[1], v[2], v[3]);
+        }
+      }
+      ptx::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar_full(s), 0));
+      if (dw == 0 && lane == 0) tl_mark(p, 3, g >> 2);
+      cur = nxt;
+      s += kGroups;
+      if (s >= S) {
+        s -= S;
+        empty_parity ^= 1u;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();  // the peer may still be reading this CTA's shared memory / arriving on its barriers
+  if (warp == kAllocWarp) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair<kTmemCols>(tmem_d);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side: tile shape selection + launch
+// ---------------------------------------------------------------------------
+struct Tc2Config {
+  int n_acc, N_acc, stages;
+  double cost;
+};
+
+// Cycle model per pipeline step (one CTA): tensor pipe 2*N_acc cycles per accumulator (M = 256 over the pair,
+// K = 64), decode ~520 ALU-pipe cycles per 128 x 64 weight tile, shared memory 128 B/clk over the decoded tile
+// (written once, read once per accumulator) and the activation boxes (written by TMA, read by the MMA).
+static Tc2Config choose_config(int64_t T, int64_t OUT, int n_blocks, int n_pairs) {
+  Tc2Config best{0, 0, 0, 1e300};
+  const int64_t n_f = ceil_div64(OUT, 2 * kBM);
+  for (int n_acc = 1; n_acc <= kMaxAcc; ++n_acc) {
+    for (int N_acc = 32; N_acc <= 256; N_acc += 16) {
+      const int b_bytes = (N_acc / 2) * 128;
+      const int stage_bytes = kATileBytes + n_acc * b_bytes;
+      int stages = (kSmemLimit - kBarBytes - kEpiBytes - 1024) / stage_bytes;
+      if (stages > kMaxStages) stages = kMaxStages;
+      if (stages < kGroups) continue;  // a decode group may run at most one ring phase ahead of its barrier
+      const int64_t tok = (int64_t)n_acc * N_acc;
+      const int64_t tiles = n_f * ceil_div64(T, tok);
+      const double waves = (double)ceil_div64(tiles, n_pairs);
+      const double mma = 2.0 * N_acc * n_acc;
+      const double smem = (kATileBytes * (1.0 + n_acc) + 2.0 * n_acc * b_bytes) / 128.0;
+      double step = mma > smem ? mma : smem;
+      if (step < 520.0) step = 520.0;
+      const double cost = waves * (n_blocks * step + 2500.0 + 6.0 * tok);
+      if (cost < best.cost * 0.999 || (cost < best.cost * 1.001 && N_acc > best.N_acc)) best = {n_acc, N_acc, stages, cost};
+    }
+  }
+  return best;
+}
+
+template <typename ActT, bool kBackward>
+static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void* lora_act, cudaStream_t st) {
+  const int64_t OUT = kBackward ? a.K : a.N;
+  const int64_t RED = kBackward ? a.N : a.K;
+  int dev = 0, n_sm = 0;
+  VFT_CUDA_OK(cudaGetDevice(&dev));
+  VFT_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  int n_pairs = n_sm / 2;
+  if (n_pairs < 1) n_pairs = 1;
+  const int n_blocks = (int)ceil_div64(RED, kBK) + (a.r > 0 ? 1 : 0);
+  Tc2Config cfg = choose_config(a.T, OUT, n_blocks, n_pairs);
+  if (const char* e = getenv("VFT_TC2_NACC")) {  // triage override: "<n_acc>x<N_acc>"
+    int na = 0, nn = 0;
+    if (sscanf(e, "%dx%d", &na, &nn) == 2 && na >= 1 && na <= kMaxAcc && nn >= 16 && nn <= 256 && nn % 16 == 0) {
+      cfg.n_acc = na;
+      cfg.N_acc = nn;
+      cfg.stages = (kSmemLimit - kBarBytes - kEpiBytes - 1024) / (kATileBytes + na * (nn / 2) * 128);
+      if (cfg.stages > kMaxStages) cfg.stages = kMaxStages;
+    }
+  }
+  if (const char* e = getenv("VFT_TC2_STAGES")) {
+    const int s = atoi(e);
+    if (s >= kGroups && s <= cfg.stages) cfg.stages = s;
+  }
+
+  Tc2Params p;
+  p.T = a.T; p.N = a.N; p.K = a.K; p.r = a.r; p.qdtype = a.qdtype; p.scale = a.scale;
+  p.packed = a.packed;
+  p.absmax = a.absmax;
+  p.bias = kBackward ? nullptr : a.bias;
+  p.lora_w = kBackward ? a.lora_a : a.lora_b;
+  p.out = out;
+  p.n_acc = cfg.n_acc;
+  p.N_acc = cfg.N_acc;
+  p.stages = cfg.stages;
+  p.b_bytes = (cfg.N_acc / 2) * 128;
+  p.stage_bytes = kATileBytes + cfg.n_acc * p.b_bytes;
+  p.n_fblk = (int)ceil_div64(OUT, 2 * kBM);
+  p.n_tiles = p.n_fblk * (int)ceil_div64(a.T, (int64_t)cfg.n_acc * cfg.N_acc);
+  const char* dbg = getenv("VFT_TC_DEBUG");
+  p.debug = dbg ? atoi(dbg) : 0;
+
+  const CUtensorMapDataType dt =
+      std::is_same<ActT, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap map_act, map_lora, map_out;
+  int rc = make_map_2d(&map_act, dt, act, (uint64_t)RED, (uint64_t)a.T, (uint64_t)RED * 2, kBK, cfg.N_acc / 2,
+                       CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != VFT_OK) return rc;
+  // output rows leave through TMA stores of [16 tokens x 128 features] boxes (clipped at T / OUT)
+  rc = make_map_2d(&map_out, dt, out, (uint64_t)OUT, (uint64_t)a.T, (uint64_t)OUT * 2, kBM, 16, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc != VFT_OK) return rc;
+  if (a.r > 0) {
+    rc = make_map_2d(&map_lora, dt, lora_act, VFT_LORA_LD, (uint64_t)a.T, VFT_LORA_LD * 2, kBK, cfg.N_acc / 2,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != VFT_OK) return rc;
+  } else {
+    map_lora = map_act;
+  }
+
+  const int dyn_bytes = cfg.stages * p.stage_bytes + kEpiBytes + kBarBytes + 1024;  // + slack to align the base to 1024 B
+  auto kern = qlora_tc2_kernel<ActT, kBackward>;
+  VFT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_bytes));
+  const int pairs = p.n_tiles < n_pairs ? p.n_tiles : n_pairs;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)(2 * pairs));
+  lc.blockDim = dim3(kThreads);
+  lc.dynamicSmemBytes = (size_t)dyn_bytes;
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  lc.attrs = attr;
+  lc.numAttrs = 1;
+  VFT_CUDA_OK(cudaLaunchKernelEx(&lc, kern, map_act, map_lora, map_out, p));
+  VFT_CUDA_OK(cudaGetLastError());
+  return VFT_OK;
+}
+
+}  // namespace
+}  // namespace vft
+
+// Debug export (not part of the public ABI): timeline of the last VFT_TC_DEBUG&16 launch of the pair kernel.
+extern "C" int vft_debug_tc2_timeline(unsigned long long* out, int n) {
+  if (n > vft::kTlRows * vft::kTlCols) n = vft::kTlRows * vft::kTlCols;
+  return cudaMemcpyFromSymbol(out, vft::g_tc2_timeline, sizeof(unsigned long long) * n) == cudaSuccess ? 0 : -3;
+}
+
+namespace vft {
+
+// The persistent pair kernel pays off once there are enough tokens to give every SM pair work and to make the
+// GEMM tensor-bound; below that the one-tile-per-CTA kernel of qlora_tc.cu (more, smaller CTAs) is used.
+bool tc2_preferred(const LayerArgs& a, bool backward) {
+  const int64_t OUT = backward ? a.K : a.N;
+  if (OUT % 8 != 0) return false;  // row stride of the output must be a multiple of 16 bytes (TMA store)
+  if (const char* e = getenv("VFT_TC2")) return e[0] != '0' && OUT >= kBM + 1 && a.T >= 32;
+  return a.T >= 512 && OUT >= 2 * kBM;
+}
+
+int tc2_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st) {
+  if (a.act_dtype == VFT_BF16) return launch_tc2<__nv_bfloat16, false>(a, x, y, t_save, st);
+  return launch_tc2<__half, false>(a, x, y, t_save, st);
+}
+
+int tc2_bwd_dx(const LayerArgs& a, const void* dy, void* dx, const void* dt_save, cudaStream_t st) {
+  if (a.act_dtype == VFT_BF16) return launch_tc2<__nv_bfloat16, true>(a, dy, dx, dt_save, st);
+  return launch_tc2<__half, true>(a, dy, dx, dt_save, st);
+}
+
+}  // namespace vft

@@ -130,5 +130,9 @@ int mma_dab(const void* dy, const void* x, const void* t_save, const void* dt_sa
 bool tc_supported(const LayerArgs& a, bool backward);
 int tc_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st);
 int tc_bwd_dx(const LayerArgs& a, const void* dy, void* dx, const void* dt_save, cudaStream_t st);
+// persistent CTA-pair form (qlora_tc2.cu); same contract, used by tc_fwd / tc_bwd_dx for large token counts
+bool tc2_preferred(const LayerArgs& a, bool backward);
+int tc2_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st);
+int tc2_bwd_dx(const LayerArgs& a, const void* dy, void* dx, const void* dt_save, cudaStream_t st);
 
 }  // namespace vft
