@@ -51,10 +51,23 @@ constexpr int kTmaWarp = kEpiWarp0 + 4;         // warp 20: TMA producer
 constexpr int kAllocWarp = kEpiWarp0 + 5;       // warp 21: TMEM allocation
 constexpr int kMmaWarp = kEpiWarp0 + 7;         // warp 23: MMA issuer
 constexpr int kThreads = (kEpiWarp0 + 8) * 32;  // 768
+// registers per thread after the role split (launch: 80 x 768): 4 x 128 x (88 - 80) <= 128 x (80 - 40) + 128 x (80 - 72)
+constexpr int kCtrlRegs = 40, kEpiRegs = 72, kDecRegs = 88;
 constexpr int kATileBytes = kBM * kBK * 2;                // 16 KB decoded weight tile
 constexpr int kMaxStages = 8;
 constexpr int kMaxAcc = 2;
-constexpr int kAccCols = 256;  // TMEM column pitch between the accumulators
+// TMEM columns.  Backward (weights staged in shared memory): two accumulators of up to 256 columns.  Forward
+// (kTmemA): the decoded weight tile itself lives in tensor memory -- 4 ring stages of 32 columns (64 16-bit values
+// per lane) above two accumulators of up to 192 columns -- so it costs no shared-memory bandwidth at all: the
+// tcgen05.mma reads A from TMEM, and shared memory only carries the activation boxes.  (Measured before this:
+// with A in shared memory the pipe ran at ~138 B/clk of demand against 128 B/clk, and the decode warps' stores
+// queued for 2-3 k cycles per block.)
+constexpr int kTmemAStages = 4;
+constexpr int kTmemACol0 = 384;
+template <bool kTmemA>
+struct AccLayout {
+  static constexpr int pitch = kTmemA ? 192 : 256;  // column pitch between the accumulators = max N_acc
+};
 constexpr int kTmemCols = 512;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kBarBytes = (2 * kMaxStages + 1 + kMaxAcc) * 8 + 16;
@@ -73,7 +86,7 @@ struct Tc2Params {
   int n_acc, N_acc;    // accumulators per tile, tokens per accumulator (multiple of 16, <= 256)
   int stages;
   int b_bytes;      // bytes of one accumulator's activation box in one CTA: (N_acc / 2) * 128
-  int stage_bytes;  // kATileBytes + n_acc * b_bytes
+  int stage_bytes;  // (backward: kATileBytes +) n_acc * b_bytes
   int n_fblk;       // feature blocks of 256
   int n_tiles;      // n_fblk * token blocks
   int debug;        // VFT_TC_DEBUG triage mask (results are garbage when non-zero): 1 = no decode stores,
@@ -99,6 +112,9 @@ template <typename ActT, bool kBackward>
 __global__ void __launch_bounds__(kThreads, 1)
 qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_lora,
                  const __grid_constant__ CUtensorMap map_out, const Tc2Params p) {
+  constexpr bool kTmemA = !kBackward;  // forward: decoded weights go to tensor memory, backward: shared memory
+  constexpr int kAccCols = AccLayout<kTmemA>::pitch;
+  constexpr int kAOff = kTmemA ? 0 : kATileBytes;  // offset of the activation boxes inside a stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
@@ -126,7 +142,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + S * p.stage_bytes + kEpiBytes + 8 * (2 * kMaxStages + 1 + kMaxAcc));
   auto stage_a = [&](int s) { return smem_base + (uint32_t)(s * p.stage_bytes); };
-  auto stage_b = [&](int s, int a) { return smem_base + (uint32_t)(s * p.stage_bytes + kATileBytes + a * p.b_bytes); };
+  auto stage_b = [&](int s, int a) { return smem_base + (uint32_t)(s * p.stage_bytes + kAOff + a * p.b_bytes); };
   // accumulators of a tile that hold at least one real token (all roles derive it the same way)
   auto accs_of = [&](int64_t t0) -> int {
     const int64_t left = p.T - t0;
@@ -153,6 +169,13 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   ptx::tc_fence_after();
   const uint32_t tmem_d = *tmem_slot_gen;
 
+  // Register budget: 768 threads start with 80 registers each.  The control warpgroup (warps 20-23) gives most of
+  // its share back so that the four decode warpgroups can hold a fully decoded block (32 registers) while they
+  // wait for their ring stage: decode then overlaps the MMAs that still read the stage.
+  // (setmaxnreg sits INSIDE each role's exclusive branch so that ptxas applies the limit to that role only; the
+  //  registers a warpgroup gains must have been released by another warpgroup of the SAME CTA.)
+  if (warp >= kTmaWarp) {
+  ptx::setmaxnreg_dec<kCtrlRegs>();
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------- TMA producer (activations)
     if (ptx::elect_one()) {
@@ -219,25 +242,25 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
           const uint64_t b_desc0 = ptx::make_smem_desc_sw128(stage_b(s, 0), 16, 1024);
           const uint64_t b_desc1 = ptx::make_smem_desc_sw128(stage_b(s, 1), 16, 1024);
           const uint32_t acc0 = b > 0 ? 1u : 0u;
+          // forward: A = TMEM stage s, 8 columns (16 packed 16-bit values per lane) per MMA
+          const uint32_t a_tmem = tmem_d + (uint32_t)(kTmemACol0 + 32 * s);
+          auto mma = [&](uint32_t d, int k, uint64_t b_desc, uint32_t accumulate) {
+            if (kTmemA) ptx::umma_ts_pair(d, a_tmem + (uint32_t)(8 * k), b_desc + k * kBStep, idesc, accumulate);
+            else ptx::umma_ss_pair(d, a_desc + k * kAStep, b_desc + k * kBStep, idesc, accumulate);
+          };
           if (ptx::elect_one()) {
             if (do_mma) {
               if (b < n_main) {
 #pragma unroll
-                for (int k = 0; k < kBK / 16; ++k)
-                  ptx::umma_ss_pair(tmem_d, a_desc + k * kAStep, b_desc0 + k * kBStep, idesc, k > 0 ? 1u : acc0);
+                for (int k = 0; k < kBK / 16; ++k) mma(tmem_d, k, b_desc0, k > 0 ? 1u : acc0);
                 if (na > 1) {
 #pragma unroll
-                  for (int k = 0; k < kBK / 16; ++k)
-                    ptx::umma_ss_pair(tmem_d + kAccCols, a_desc + k * kAStep, b_desc1 + k * kBStep, idesc,
-                                      k > 0 ? 1u : acc0);
+                  for (int k = 0; k < kBK / 16; ++k) mma(tmem_d + kAccCols, k, b_desc1, k > 0 ? 1u : acc0);
                 }
               } else {  // adapter step: ceil(r / 16) MMAs per accumulator
-                for (int k = 0; k < k_lora; ++k)
-                  ptx::umma_ss_pair(tmem_d, a_desc + k * kAStep, b_desc0 + k * kBStep, idesc, (b | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < k_lora; ++k) mma(tmem_d, k, b_desc0, (b | k) != 0 ? 1u : 0u);
                 if (na > 1) {
-                  for (int k = 0; k < k_lora; ++k)
-                    ptx::umma_ss_pair(tmem_d + kAccCols, a_desc + k * kAStep, b_desc1 + k * kBStep, idesc,
-                                      (b | k) != 0 ? 1u : 0u);
+                  for (int k = 0; k < k_lora; ++k) mma(tmem_d + kAccCols, k, b_desc1, (b | k) != 0 ? 1u : 0u);
                 }
               }
             }
@@ -254,8 +277,10 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         acc_par ^= 1u;
       }
     }
-  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
+  }
+  } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------- epilogue warps
+    ptx::setmaxnreg_dec<kEpiRegs>();
     // TMEM holds D[feature (lane), token (column)] but the output is [token, feature]: each warp converts its
     // 32 features x 32 tokens to 16-bit and writes them TRANSPOSED into a staging tile [32 tokens][128 features]
     // (64 contiguous bytes per token per warp: conflict-free); one thread then hands the tile to the TMA store
@@ -319,8 +344,9 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       }
     }
     if (et == 0) ptx::bulk_wait_group<0>();  // all output rows written before the CTA retires
-  } else if (warp < kEpiWarp0) {
+  } else {
     // ------------------------------------------------------------- decode warps
+    ptx::setmaxnreg_inc<kDecRegs>();
     const int dw = warp - kDecWarp0;  // 0..15
     const int group = dw >> 2;        // owns pipeline steps group, group + 4, ...
     const int quad = dw & 3;
@@ -372,41 +398,37 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     Pos cur{group, pair};
     normalize(cur);
     prefetch(cur);
+    // forward: this thread's lane of the TMEM weight ring (warp % 4 = lane quadrant the warp may access)
+    const uint32_t a_tmem_lane = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)kTmemACol0;
     int s = group;  // S >= kGroups: at most one ring wrap per step of kGroups
     uint32_t empty_parity = 1;
     for (int g = group; cur.tile < p.n_tiles; g += kGroups) {
       const uint32_t a_tile = stage_a(s) + a_row_off;
       Pos nxt{cur.b + kGroups, cur.tile};
       normalize(nxt);
+      uint32_t v[8][4];  // this thread's 64 decoded 16-bit values, in contraction order
       if (cur.b < n_main) {
         Nf4Lut lut;
         nf4_build_lut<ActT>(am, p.qdtype, lut);
         const uint32_t words[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
         prefetch(nxt);  // next block's codes are in flight while this one is decoded
-        ptx::mbar_wait(bar_empty(s), empty_parity);
-        if (dw == 0 && lane == 0) tl_mark(p, 2, g >> 2);
-        if (!(p.debug & 1)) {
+        // Decode into registers BEFORE waiting for the stage: the permute work then overlaps the MMAs still
+        // reading the stage, and only the stores + a fence sit between "stage free" and "stage full".
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint32_t v[4];
-            nf4_decode_word(words[c], lut, v);
-            ptx::sts128(a_tile + (((uint32_t)c << 4) ^ a_xor), v[0], v[1], v[2], v[3]);
-          }
-        }
+        for (int c = 0; c < 8; ++c) nf4_decode_word(words[c], lut, v[c]);
       } else {
         // adapter step: forward row n of scale*B (r values), backward row j of A (64 in-features)
         const ActT* lw = static_cast<const ActT*>(p.lora_w);
         const int64_t f0 = f0_of(cur.tile);
         prefetch(nxt);
-        ptx::mbar_wait(bar_empty(s), empty_parity);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          uint32_t v[4] = {0u, 0u, 0u, 0u};
+          v[c][0] = v[c][1] = v[c][2] = v[c][3] = 0u;
           if (kBackward) {
             const int64_t k = f0 + half * 64 + c * 8;
             if (row < p.r && k < p.K) {
               const uint4 q = __ldg(reinterpret_cast<const uint4*>(lw + (int64_t)row * p.K + k));
-              v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+              v[c][0] = q.x; v[c][1] = q.y; v[c][2] = q.z; v[c][3] = q.w;
             }
           } else {
             const int64_t n = f0 + row;
@@ -416,14 +438,34 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
                 const int j = c * 8 + 2 * e;
                 const float b0 = (j < p.r) ? p.scale * to_f32<ActT>(lw[n * p.r + j]) : 0.0f;
                 const float b1 = (j + 1 < p.r) ? p.scale * to_f32<ActT>(lw[n * p.r + j + 1]) : 0.0f;
-                v[e] = pack2<ActT>(b0, b1);
+                v[c][e] = pack2<ActT>(b0, b1);
               }
             }
           }
-          ptx::sts128(a_tile + (((uint32_t)c << 4) ^ a_xor), v[0], v[1], v[2], v[3]);
         }
       }
-      ptx::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      ptx::mbar_wait(bar_empty(s), empty_parity);
+      if (dw == 0 && lane == 0) tl_mark(p, 2, g >> 2);
+      if (!(p.debug & 1)) {
+        if (kTmemA) {
+          uint32_t flat[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            flat[4 * c] = v[c][0]; flat[4 * c + 1] = v[c][1]; flat[4 * c + 2] = v[c][2]; flat[4 * c + 3] = v[c][3];
+          }
+          ptx::tmem_st_32x32b_x32(a_tmem_lane + (uint32_t)(32 * s), flat);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            ptx::sts128(a_tile + (((uint32_t)c << 4) ^ a_xor), v[c][0], v[c][1], v[c][2], v[c][3]);
+        }
+      }
+      if (kTmemA) {
+        ptx::tmem_st_wait();     // the tile is in tensor memory ...
+        ptx::tc_fence_before();  // ... before the arrive that lets the issuer's tcgen05.mma read it
+      } else {
+        ptx::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar_full(s), 0));
       if (dw == 0 && lane == 0) tl_mark(p, 3, g >> 2);
@@ -453,27 +495,40 @@ struct Tc2Config {
 };
 
 // Cycle model per pipeline step (one CTA): tensor pipe 2*N_acc cycles per accumulator (M = 256 over the pair,
-// K = 64), decode ~520 ALU-pipe cycles per 128 x 64 weight tile, shared memory 128 B/clk over the decoded tile
-// (written once, read once per accumulator) and the activation boxes (written by TMA, read by the MMA).
-static Tc2Config choose_config(int64_t T, int64_t OUT, int n_blocks, int n_pairs) {
+// K = 64), decode ~600 ALU-pipe cycles per 128 x 64 weight tile, shared memory 128 B/clk over the activation
+// boxes (written by TMA, read by the MMA) and -- backward only -- the decoded tile (written once, read once per
+// accumulator).
+static int max_stages(bool tmem_a, int n_acc, int N_acc) {
+  const int stage_bytes = (tmem_a ? 0 : kATileBytes) + n_acc * (N_acc / 2) * 128;
+  int stages = (kSmemLimit - kBarBytes - kEpiBytes - 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (tmem_a && stages > kTmemAStages) stages = kTmemAStages;  // the weight ring in tensor memory has 4 slots
+  return stages;
+}
+
+static bool config_ok(bool tmem_a, int n_acc, int N_acc) {
+  if (n_acc < 1 || n_acc > kMaxAcc || N_acc < 16 || N_acc > 256 || N_acc % 16 != 0) return false;
+  if (tmem_a && n_acc == 2 && N_acc > AccLayout<true>::pitch) return false;
+  return max_stages(tmem_a, n_acc, N_acc) >= kGroups;  // a decode group may run at most one ring phase ahead
+}
+
+static Tc2Config choose_config(int64_t T, int64_t OUT, int n_blocks, int n_pairs, bool tmem_a) {
   Tc2Config best{0, 0, 0, 1e300};
   const int64_t n_f = ceil_div64(OUT, 2 * kBM);
   for (int n_acc = 1; n_acc <= kMaxAcc; ++n_acc) {
     for (int N_acc = 32; N_acc <= 256; N_acc += 16) {
+      if (!config_ok(tmem_a, n_acc, N_acc)) continue;
       const int b_bytes = (N_acc / 2) * 128;
-      const int stage_bytes = kATileBytes + n_acc * b_bytes;
-      int stages = (kSmemLimit - kBarBytes - kEpiBytes - 1024) / stage_bytes;
-      if (stages > kMaxStages) stages = kMaxStages;
-      if (stages < kGroups) continue;  // a decode group may run at most one ring phase ahead of its barrier
       const int64_t tok = (int64_t)n_acc * N_acc;
       const int64_t tiles = n_f * ceil_div64(T, tok);
       const double waves = (double)ceil_div64(tiles, n_pairs);
       const double mma = 2.0 * N_acc * n_acc;
-      const double smem = (kATileBytes * (1.0 + n_acc) + 2.0 * n_acc * b_bytes) / 128.0;
+      const double smem = ((tmem_a ? 0.0 : kATileBytes * (1.0 + n_acc)) + 2.0 * n_acc * b_bytes) / 128.0;
       double step = mma > smem ? mma : smem;
-      if (step < 520.0) step = 520.0;
+      if (step < 620.0) step = 620.0;  // decode: ~600 ALU-pipe cycles per 128 x 64 weight tile
       const double cost = waves * (n_blocks * step + 2500.0 + 6.0 * tok);
-      if (cost < best.cost * 0.999 || (cost < best.cost * 1.001 && N_acc > best.N_acc)) best = {n_acc, N_acc, stages, cost};
+      if (cost < best.cost * 0.999 || (cost < best.cost * 1.001 && N_acc > best.N_acc))
+        best = {n_acc, N_acc, max_stages(tmem_a, n_acc, N_acc), cost};
     }
   }
   return best;
@@ -489,14 +544,17 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
   int n_pairs = n_sm / 2;
   if (n_pairs < 1) n_pairs = 1;
   const int n_blocks = (int)ceil_div64(RED, kBK) + (a.r > 0 ? 1 : 0);
-  Tc2Config cfg = choose_config(a.T, OUT, n_blocks, n_pairs);
-  if (const char* e = getenv("VFT_TC2_NACC")) {  // triage override: "<n_acc>x<N_acc>"
+  constexpr bool kTmemA = !kBackward;
+  Tc2Config cfg = choose_config(a.T, OUT, n_blocks, n_pairs, kTmemA);
+  if (const char* e = getenv("VFT_TC2_NACC")) {  // triage override: "<n_acc>x<N_acc>" (clamped to what the path allows)
     int na = 0, nn = 0;
-    if (sscanf(e, "%dx%d", &na, &nn) == 2 && na >= 1 && na <= kMaxAcc && nn >= 16 && nn <= 256 && nn % 16 == 0) {
-      cfg.n_acc = na;
-      cfg.N_acc = nn;
-      cfg.stages = (kSmemLimit - kBarBytes - kEpiBytes - 1024) / (kATileBytes + na * (nn / 2) * 128);
-      if (cfg.stages > kMaxStages) cfg.stages = kMaxStages;
+    if (sscanf(e, "%dx%d", &na, &nn) == 2) {
+      if (kTmemA && na == 2 && nn > AccLayout<true>::pitch) nn = AccLayout<true>::pitch;
+      if (config_ok(kTmemA, na, nn)) {
+        cfg.n_acc = na;
+        cfg.N_acc = nn;
+        cfg.stages = max_stages(kTmemA, na, nn);
+      }
     }
   }
   if (const char* e = getenv("VFT_TC2_STAGES")) {
@@ -515,7 +573,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
   p.N_acc = cfg.N_acc;
   p.stages = cfg.stages;
   p.b_bytes = (cfg.N_acc / 2) * 128;
-  p.stage_bytes = kATileBytes + cfg.n_acc * p.b_bytes;
+  p.stage_bytes = (kTmemA ? 0 : kATileBytes) + cfg.n_acc * p.b_bytes;
   p.n_fblk = (int)ceil_div64(OUT, 2 * kBM);
   p.n_tiles = p.n_fblk * (int)ceil_div64(a.T, (int64_t)cfg.n_acc * cfg.N_acc);
   const char* dbg = getenv("VFT_TC_DEBUG");
