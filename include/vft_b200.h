@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define VFT_ABI_VERSION 1
+#define VFT_ABI_VERSION 2
 #define VFT_LORA_LD 64 /* leading dimension (elements) of the saved LoRA activations t_save / dt_save */
 
 enum vft_dtype { VFT_F32 = 0, VFT_F16 = 1, VFT_BF16 = 2 };
@@ -83,6 +83,15 @@ int vft_nf4_dequantize(const uint8_t* packed, const float* absmax, int64_t n, in
 int vft_nf4_quantize_host(const void* w_host, int dtype, int64_t n, int blocksize, uint8_t* packed_host,
                           float* absmax_host);
 
+/* Optional kernel-friendly copy of a packed weight (blocksize 64, K % 64 == 0): 64 x 64 micro-tiles so that the
+ * 32 lanes of a decode warp read contiguous bytes (layout: csrc/nf4_quant.cu).  The checkpoint format -- what
+ * Params4bit holds and state_dict() emits, /root/reference/src/modules/quant/bnb.py:91-107 -- is unchanged; this is
+ * a derived, caller-owned device buffer that the fused entry points accept next to packed/absmax.
+ *   codes_t  [vft_nf4_tiled_bytes(N,K,0)] bytes, 16-byte aligned;  absmax_t [vft_nf4_tiled_bytes(N,K,1)] bytes */
+int64_t vft_nf4_tiled_bytes(int64_t N, int64_t K, int which);
+int vft_nf4_tile_weight(const uint8_t* packed, const float* absmax, int64_t N, int64_t K, int blocksize,
+                        uint8_t* codes_t, float* absmax_t, void* stream);
+
 /* Scratch the caller must provide for an op (bytes; 0 is possible). */
 int64_t vft_workspace_bytes(int op, int64_t T, int64_t N, int64_t K, int r);
 
@@ -96,10 +105,12 @@ int64_t vft_workspace_bytes(int op, int64_t T, int64_t N, int64_t K, int r);
  *   lora_a [r,K] (lora_down.weight), lora_b [N,r] (lora_up.weight); both NULL and
  *   r = 0 for an NF4-only layer.  scale = alpha / rank.
  *   t_save [T, VFT_LORA_LD] out: x . A^T rounded to act_dtype, zero padded; required
- *   when r > 0 (the backward reads it). */
+ *   when r > 0 (the backward reads it).
+ *   codes_t / absmax_t: the micro-tiled copy of the same weight, or both NULL. */
 int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
                   int blocksize, int act_dtype, int qdtype, const void* bias, const void* lora_a, const void* lora_b,
-                  int r, float scale, void* y, void* t_save, void* ws, int64_t ws_bytes, void* stream);
+                  int r, float scale, void* y, void* t_save, void* ws, int64_t ws_bytes, const uint8_t* codes_t,
+                  const float* absmax_t, void* stream);
 
 /* Fused backward w.r.t. the input.  Replaces MatMul4Bit.backward (second dequant +
  * cuBLAS) and the dX half of the adapter's autograd:
@@ -108,7 +119,8 @@ int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* 
  * dx may be NULL when only dt_save is wanted (input does not require grad). */
 int vft_qlora_bwd_dx(const void* dy, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
                      int blocksize, int act_dtype, int qdtype, const void* lora_a, const void* lora_b, int r,
-                     float scale, void* dx, void* dt_save, void* ws, int64_t ws_bytes, void* stream);
+                     float scale, void* dx, void* dt_save, void* ws, int64_t ws_bytes, const uint8_t* codes_t,
+                     const float* absmax_t, void* stream);
 
 /* Adapter weight gradients (autograd of lora.py:100-104):
  *     dA[r,K] = dt^T . x        dB[N,r] = scale * dy^T . t

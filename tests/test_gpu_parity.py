@@ -127,13 +127,15 @@ def _make_case(T, K, N, r, seed, dt=torch.bfloat16, bias=False, qdt=None, lead=N
     return w, x, dy, a, b, bv
 
 
-def _run_cuda(ops, packed, absmax, x, dy, a, b, bias, alpha, N, K, qdt, path):
+def _run_cuda(ops, packed, absmax, x, dy, a, b, bias, alpha, N, K, qdt, path, tiled=False):
     ops.force_path(path)
+    tiles = ops.nf4_tile_weight(packed, absmax, N, K) if tiled else None
+    assert not tiled or tiles is not None
     xc = x.cuda().requires_grad_(True)
     ac = a.cuda().requires_grad_(True) if a is not None else None
     bc = b.cuda().requires_grad_(True) if b is not None else None
     scale = alpha / a.shape[0] if a is not None else 0.0
-    y = ops.qlora_linear(xc, packed, absmax, None if bias is None else bias.cuda(), ac, bc, scale, N, K, 64, qdt)
+    y = ops.qlora_linear(xc, packed, absmax, None if bias is None else bias.cuda(), ac, bc, scale, N, K, 64, qdt, tiles)
     used_fwd = ops.last_path()
     y.backward(dy.cuda())
     torch.cuda.synchronize()
@@ -239,8 +241,9 @@ def test_fp16_activations(ops):
             assert qlora_oracle.rel_l2(out[k], truth[k]) <= 2e-3, (path, k)
 
 
+@pytest.mark.parametrize("tiled", [False, True])
 @pytest.mark.parametrize("N,K", [(3072, 3072), (8192, 3072), (3072, 8192)])
-def test_identity_activation_reproduces_weight_bit_exact(ops, N, K):
+def test_identity_activation_reproduces_weight_bit_exact(ops, N, K, tiled):
     """Size-independent property at full size: x = I_K  =>  y[k, :] = W~[:, k] exactly (single non-zero term per
     dot product), and dy = I_N => dx[n, :] = W~[n, :] exactly.  Exercises every tile, stage and lane of the
     tcgen05 path and compares with the standalone (bit-exact-tested) dequantize kernel."""
@@ -248,13 +251,14 @@ def test_identity_activation_reproduces_weight_bit_exact(ops, N, K):
     w = (torch.randn(N, K, generator=g, device="cuda") * 0.02).to(torch.bfloat16)
     packed, absmax = ops.nf4_quantize(w)
     w_deq = ops.nf4_dequantize(packed, absmax, (N, K), torch.bfloat16)
+    tiles = ops.nf4_tile_weight(packed, absmax, N, K) if tiled else None
     ops.force_path(TC)
     eye_k = torch.eye(K, dtype=torch.bfloat16, device="cuda").requires_grad_(True)
-    y = ops.qlora_linear(eye_k, packed, absmax, None, None, None, 0.0, N, K, 64, torch.bfloat16)
+    y = ops.qlora_linear(eye_k, packed, absmax, None, None, None, 0.0, N, K, 64, torch.bfloat16, tiles)
     assert ops.last_path() == TC
     assert torch.equal(y.detach(), w_deq.t())
     x = torch.zeros(N, K, dtype=torch.bfloat16, device="cuda", requires_grad=True)
-    y2 = ops.qlora_linear(x, packed, absmax, None, None, None, 0.0, N, K, 64, torch.bfloat16)
+    y2 = ops.qlora_linear(x, packed, absmax, None, None, None, 0.0, N, K, 64, torch.bfloat16, tiles)
     y2.backward(torch.eye(N, dtype=torch.bfloat16, device="cuda"))
     ops.force_path(0)
     assert torch.equal(x.grad, w_deq)
@@ -262,9 +266,10 @@ def test_identity_activation_reproduces_weight_bit_exact(ops, N, K):
 
 # persistent CTA-pair kernel (qlora_tc2.cu): forced tile shapes on ragged problems, so that partial token blocks,
 # unused second accumulators, feature blocks whose second CTA is out of range and multi-tile persistence are all hit
+@pytest.mark.parametrize("tiled", [False, True])
 @pytest.mark.parametrize("nacc", ["1x32", "2x48", "1x176", "2x176", "1x256", "2x256", "auto"])
 @pytest.mark.parametrize("T,K,N,r,bias", [(700, 256, 640, 16, True), (1300, 192, 384, 0, False), (333, 64, 136, 8, False)])
-def test_pair_kernel_forced_tiles(ops, monkeypatch, nacc, T, K, N, r, bias):
+def test_pair_kernel_forced_tiles(ops, monkeypatch, nacc, T, K, N, r, bias, tiled):
     monkeypatch.setenv("VFT_TC2", "1")
     if nacc != "auto":
         monkeypatch.setenv("VFT_TC2_NACC", nacc)
@@ -274,7 +279,7 @@ def test_pair_kernel_forced_tiles(ops, monkeypatch, nacc, T, K, N, r, bias):
     ref = qlora_oracle.qlora_linear_ref(x, w_deq, bv, a, b, 1.0, dy)
     truth = qlora_oracle.qlora_linear_truth(x, w_deq, bv, a, b, 1.0, dy)
     out, used = _run_cuda(ops, torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), x, dy, a, b, bv, 1.0, N, K,
-                          torch.bfloat16, TC)
+                          torch.bfloat16, TC, tiled=tiled)
     assert used == TC
     _check(out, ref, truth, ("y", "dx") + (("da", "db") if r else ()), f"pair{nacc}-T{T}K{K}N{N}r{r}")
 
@@ -320,7 +325,7 @@ def test_config1_full_size_vs_oracle(ops):
     torch.set_num_threads(os.cpu_count() or 1)
     ref = qlora_oracle.qlora_linear_ref(x, w_deq, None, a, b, 1.0, dy)
     truth = qlora_oracle.qlora_linear_truth(x, w_deq, None, a, b, 1.0, dy)
-    out, used = _run_cuda(ops, packed, absmax, x, dy, a, b, None, 1.0, N, K, torch.bfloat16, 0)
+    out, used = _run_cuda(ops, packed, absmax, x, dy, a, b, None, 1.0, N, K, torch.bfloat16, 0, tiled=True)
     assert used == TC
     _check(out, ref, truth, ("y", "dx", "da", "db"), "config1")
 

@@ -12,15 +12,17 @@ def main():
     dev = torch.device("cuda")
     w = (torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16)
     packed, absmax = ops.nf4_quantize(w)
+    tiles = None if os.environ.get('VFT_NOTILE') else ops.nf4_tile_weight(packed, absmax, N, K)
+    TC, TA = (tiles[0].data_ptr(), tiles[1].data_ptr()) if tiles else (None, None)
     xs = [torch.randn(T, K, device=dev, dtype=torch.bfloat16) for _ in range(4)]
     gs = [torch.randn(T, N, device=dev, dtype=torch.bfloat16) for _ in range(4)]
     y = torch.empty(T, N, device=dev, dtype=torch.bfloat16)
     dx = torch.empty(T, K, device=dev, dtype=torch.bfloat16)
     st = torch.cuda.current_stream().cuda_stream
     def fwd(i):
-        _cabi.check(_cabi.lib.vft_qlora_fwd(xs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, None, 0, 0.0, y.data_ptr(), None, None, 0, st))
+        _cabi.check(_cabi.lib.vft_qlora_fwd(xs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, None, 0, 0.0, y.data_ptr(), None, None, 0, TC, TA, st))
     def bwd(i):
-        _cabi.check(_cabi.lib.vft_qlora_bwd_dx(gs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, 0, 0.0, dx.data_ptr(), None, None, 0, st))
+        _cabi.check(_cabi.lib.vft_qlora_bwd_dx(gs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, 0, 0.0, dx.data_ptr(), None, None, 0, TC, TA, st))
     res = {}
     for name, fn in (("fwd", fwd), ("bwd", bwd)):
         for i in range(5): fn(i)
@@ -43,7 +45,7 @@ def main():
         import ctypes
         for nm, fn in (("fwd", fwd), ("bwd", bwd)):
             fn(0); torch.cuda.synchronize()
-            R, C = 6, 256
+            R, C = 7, 256
             buf = (ctypes.c_ulonglong * (R * C))()
             _cabi.lib.vft_debug_tc2_timeline(buf, R * C)
             rows = [[buf[r * C + c] for c in range(C)] for r in range(R)]
@@ -53,9 +55,9 @@ def main():
             print("   step: mma_full_seen  mma_commit   | prod_empty_seen")
             for g in list(range(0, 12)) + list(range(40, 56)) + list(range(88, 100)):
                 print(f"   {g:4d}: {rel(rows[0][g]):10d} {rel(rows[1][g]):10d}   | {rel(rows[5][g]):10d}")
-            print("   decode group0 (steps 0,4,8..): empty_seen, arrived")
+            print("   decode group0 (steps 0,4,8..): empty_seen, stores issued, arrived")
             for i in list(range(0, 6)) + list(range(10, 14)):
-                print(f"   {4*i:4d}: {rel(rows[2][i]):10d} {rel(rows[3][i]):10d}")
+                print(f"   {4*i:4d}: {rel(rows[2][i]):10d} {rel(rows[6][i]):10d} {rel(rows[3][i]):10d}")
             print("   epilogue: acc_full seen / drained per tile:", [rel(v) for v in rows[4][:6]])
             steps = [v for v in rows[0] if v]
             if len(steps) > 20:

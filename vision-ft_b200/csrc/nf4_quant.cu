@@ -308,4 +308,42 @@ int launch_dequantize(const uint8_t* packed, const float* absmax, int64_t n, int
   }
 }
 
+// ---------------------------------------------------------------------------
+// Micro-tiled copy of a packed weight for the fused kernels.
+//
+// bitsandbytes' layout keeps a weight row contiguous, so the 32 lanes of a decode warp -- one weight row each -- read
+// 32 different 128-byte lines per load instruction (ncu, profiles/r01_*: 425 L1 wavefronts per pipeline step for the
+// codes + absmax of one 128 x 64 tile, more than the tile's shared-memory stores).  The tiled copy groups
+// 64 rows x 64 columns (one quantization block per row):
+//   codes_t  [N/64][K/64][2 halves][64 rows][16 bytes]   half h = bytes 16h..16h+15 of the row's 32-byte block
+//   absmax_t [N/64][K/64][64 rows] fp32
+// so a warp's 32 rows are 512 contiguous bytes per LDG.128 and one 128-byte line of absmax.  Rows >= N are zero
+// (code 0, absmax 0 -> decodes to 0).  The same copy serves forward (128 rows x 1 block) and backward (64 rows x
+// 2 blocks).  Only defined for blocksize 64 and K % 64 == 0 (quantization blocks do not span rows).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+nf4_tile_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ absmax, int64_t N, int64_t K,
+                uint8_t* __restrict__ codes_t, float* __restrict__ absmax_t) {
+  const int64_t KB = K >> 6;
+  const int64_t kb = blockIdx.x, nb = blockIdx.y;
+  const int r = threadIdx.x & 63, h = threadIdx.x >> 6;
+  const int64_t row = nb * 64 + r;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (row < N) v = *reinterpret_cast<const uint4*>(packed + ((row * K + kb * 64) >> 1) + h * 16);
+  *reinterpret_cast<uint4*>(codes_t + ((nb * KB + kb) * 2 + h) * 1024 + r * 16) = v;
+  if (h == 0) absmax_t[(nb * KB + kb) * 64 + r] = row < N ? absmax[row * KB + kb] : 0.0f;
+}
+
+int launch_tile_weight(const uint8_t* packed, const float* absmax, int64_t N, int64_t K, int blocksize,
+                       uint8_t* codes_t, float* absmax_t, cudaStream_t st) {
+  VFT_REQUIRE(blocksize == 64 && K % 64 == 0 && N > 0 && K > 0, "tiled weights need blocksize 64 and K %% 64 == 0");
+  VFT_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15u) == 0 && (reinterpret_cast<uintptr_t>(codes_t) & 15u) == 0,
+              "packed / codes_t must be 16-byte aligned");
+  const int64_t nb = ceil_div64(N, 64), kb = K / 64;
+  VFT_REQUIRE(nb <= 65535, "N too large for the tiling grid");
+  nf4_tile_kernel<<<dim3((unsigned)kb, (unsigned)nb), 128, 0, st>>>(packed, absmax, N, K, codes_t, absmax_t);
+  VFT_CUDA_OK(cudaGetLastError());
+  return VFT_OK;
+}
+
 }  // namespace vft

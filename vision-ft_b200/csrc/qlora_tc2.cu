@@ -78,8 +78,9 @@ struct Tc2Params {
   int r;
   int qdtype;
   float scale;
-  const uint8_t* packed;
+  const uint8_t* packed;  // bitsandbytes layout, or the micro-tiled copy when tiled != 0 (nf4_quant.cu)
   const float* absmax;
+  int tiled;
   const void* bias;
   const void* lora_w;  // forward: B [N, r]; backward: A [r, K]
   void* out;           // forward: Y [T, N]; backward: dX [T, K]
@@ -94,7 +95,7 @@ struct Tc2Params {
 };
 
 // Timeline of the leader CTA of pair 0 for performance triage (VFT_TC_DEBUG & 16): SM clock per event.
-constexpr int kTlRows = 6, kTlCols = 256;
+constexpr int kTlRows = 7, kTlCols = 256;
 __device__ unsigned long long g_tc2_timeline[kTlRows * kTlCols];
 __device__ __forceinline__ void tl_mark(const Tc2Params& p, int row, int col) {
   if ((p.debug & 16) && blockIdx.x == 0 && col < kTlCols) g_tc2_timeline[row * kTlCols + col] = (unsigned long long)clock64();
@@ -389,10 +390,19 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         wcol = (int64_t)q.b * kBK;
         if (wrow >= p.N) return;
       }
-      const uint8_t* c = p.packed + ((wrow * p.K + wcol) >> 1);
-      q0 = ldg_stream_u4(c);
-      q1 = ldg_stream_u4(c + 16);
-      am = __ldg(p.absmax + wrow * KB + (wcol >> 6));
+      if (p.tiled) {  // 64 x 64 micro-tiles: the warp's 32 rows are contiguous (512 B per load, one line of absmax)
+        const int64_t mt = (wrow >> 6) * KB + (wcol >> 6);
+        const int r = (int)(wrow & 63);
+        const uint8_t* c = p.packed + mt * 2048 + r * 16;
+        q0 = ldg_stream_u4(c);
+        q1 = ldg_stream_u4(c + 1024);
+        am = __ldg(p.absmax + mt * 64 + r);
+      } else {
+        const uint8_t* c = p.packed + ((wrow * p.K + wcol) >> 1);
+        q0 = ldg_stream_u4(c);
+        q1 = ldg_stream_u4(c + 16);
+        am = __ldg(p.absmax + wrow * KB + (wcol >> 6));
+      }
     };
 
     Pos cur{group, pair};
@@ -460,6 +470,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             ptx::sts128(a_tile + (((uint32_t)c << 4) ^ a_xor), v[c][0], v[c][1], v[c][2], v[c][3]);
         }
       }
+      if (dw == 0 && lane == 0) tl_mark(p, 6, g >> 2);
       if (kTmemA) {
         ptx::tmem_st_wait();     // the tile is in tensor memory ...
         ptx::tc_fence_before();  // ... before the arrive that lets the issuer's tcgen05.mma read it
@@ -564,8 +575,9 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
 
   Tc2Params p;
   p.T = a.T; p.N = a.N; p.K = a.K; p.r = a.r; p.qdtype = a.qdtype; p.scale = a.scale;
-  p.packed = a.packed;
-  p.absmax = a.absmax;
+  p.tiled = a.codes_t != nullptr;
+  p.packed = p.tiled ? a.codes_t : a.packed;
+  p.absmax = p.tiled ? a.absmax_t : a.absmax;
   p.bias = kBackward ? nullptr : a.bias;
   p.lora_w = kBackward ? a.lora_a : a.lora_b;
   p.out = out;

@@ -118,6 +118,18 @@ int vft_nf4_quantize_host(const void* w_host, int dtype, int64_t n, int blocksiz
   return VFT_OK;
 }
 
+int64_t vft_nf4_tiled_bytes(int64_t N, int64_t K, int which) {
+  if (N <= 0 || K <= 0 || K % 64 != 0) return 0;
+  const int64_t rows = ceil_div64(N, 64) * 64;
+  return which == 0 ? rows * K / 2 : rows * (K / 64) * (int64_t)sizeof(float);
+}
+
+int vft_nf4_tile_weight(const uint8_t* packed, const float* absmax, int64_t N, int64_t K, int blocksize,
+                        uint8_t* codes_t, float* absmax_t, void* stream) {
+  VFT_REQUIRE(packed && absmax && codes_t && absmax_t, "null pointer");
+  return launch_tile_weight(packed, absmax, N, K, blocksize, codes_t, absmax_t, static_cast<cudaStream_t>(stream));
+}
+
 int64_t vft_workspace_bytes(int op, int64_t T, int64_t N, int64_t K, int r) {
   (void)T;
   if (op == VFT_OP_BWD_DAB) return (int64_t)sizeof(float) * (N + K) * (r > 0 ? r : 0);
@@ -126,10 +138,12 @@ int64_t vft_workspace_bytes(int op, int64_t T, int64_t N, int64_t K, int r) {
 
 int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
                   int blocksize, int act_dtype, int qdtype, const void* bias, const void* lora_a, const void* lora_b,
-                  int r, float scale, void* y, void* t_save, void* ws, int64_t ws_bytes, void* stream) {
+                  int r, float scale, void* y, void* t_save, void* ws, int64_t ws_bytes, const uint8_t* codes_t,
+                  const float* absmax_t, void* stream) {
   (void)ws;
   (void)ws_bytes;
-  LayerArgs a{T, N, K, blocksize, act_dtype, qdtype, r, scale, packed, absmax, bias, lora_a, lora_b};
+  VFT_REQUIRE((codes_t == nullptr) == (absmax_t == nullptr), "codes_t / absmax_t must be given together");
+  LayerArgs a{T, N, K, blocksize, act_dtype, qdtype, r, scale, packed, absmax, bias, lora_a, lora_b, codes_t, absmax_t};
   int rc = check_layer(a, x, y);
   if (rc != VFT_OK) return rc;
   VFT_REQUIRE(r == 0 || t_save != nullptr, "t_save is required when r > 0");
@@ -147,10 +161,12 @@ int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* 
 
 int vft_qlora_bwd_dx(const void* dy, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
                      int blocksize, int act_dtype, int qdtype, const void* lora_a, const void* lora_b, int r,
-                     float scale, void* dx, void* dt_save, void* ws, int64_t ws_bytes, void* stream) {
+                     float scale, void* dx, void* dt_save, void* ws, int64_t ws_bytes, const uint8_t* codes_t,
+                     const float* absmax_t, void* stream) {
   (void)ws;
   (void)ws_bytes;
-  LayerArgs a{T, N, K, blocksize, act_dtype, qdtype, r, scale, packed, absmax, nullptr, lora_a, lora_b};
+  VFT_REQUIRE((codes_t == nullptr) == (absmax_t == nullptr), "codes_t / absmax_t must be given together");
+  LayerArgs a{T, N, K, blocksize, act_dtype, qdtype, r, scale, packed, absmax, nullptr, lora_a, lora_b, codes_t, absmax_t};
   int rc = check_layer(a, dy, dx, /*out_optional=*/true);  // dx == NULL: only dt_save is wanted
   if (rc != VFT_OK) return rc;
   VFT_REQUIRE(r == 0 || dt_save != nullptr, "dt_save is required when r > 0");

@@ -96,6 +96,8 @@ int launch_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t*
                     cudaStream_t st);
 int launch_dequantize(const uint8_t* packed, const float* absmax, int64_t n, int blocksize, void* out, int dtype,
                       cudaStream_t st);
+int launch_tile_weight(const uint8_t* packed, const float* absmax, int64_t N, int64_t K, int blocksize,
+                       uint8_t* codes_t, float* absmax_t, cudaStream_t st);
 
 struct LayerArgs {
   int64_t T, N, K;
@@ -106,6 +108,8 @@ struct LayerArgs {
   const void* bias;
   const void* lora_a;
   const void* lora_b;
+  const uint8_t* codes_t = nullptr;  // optional micro-tiled copy (vft_nf4_tile_weight); both or neither
+  const float* absmax_t = nullptr;
 };
 
 // generic CUDA-core family

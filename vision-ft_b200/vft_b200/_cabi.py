@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvft_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 LORA_LD = 64
 F32, F16, BF16 = 0, 1, 2
 PATH_NONE, PATH_TCGEN05, PATH_SIMT = 0, 1, 2
@@ -29,9 +29,11 @@ SYMBOLS = {
     "vft_nf4_quantize": (_i, [_p, _i, _i64, _i, _p, _p, _p]),
     "vft_nf4_dequantize": (_i, [_p, _p, _i64, _i, _p, _i, _p]),
     "vft_nf4_quantize_host": (_i, [_p, _i, _i64, _i, _p, _p]),
+    "vft_nf4_tiled_bytes": (_i64, [_i64, _i64, _i]),
+    "vft_nf4_tile_weight": (_i, [_p, _p, _i64, _i64, _i, _p, _p, _p]),
     "vft_workspace_bytes": (_i64, [_i, _i64, _i64, _i64, _i]),
-    "vft_qlora_fwd": (_i, [_p, _i64, _p, _p, _i64, _i64, _i, _i, _i, _p, _p, _p, _i, _f, _p, _p, _p, _i64, _p]),
-    "vft_qlora_bwd_dx": (_i, [_p, _i64, _p, _p, _i64, _i64, _i, _i, _i, _p, _p, _i, _f, _p, _p, _p, _i64, _p]),
+    "vft_qlora_fwd": (_i, [_p, _i64, _p, _p, _i64, _i64, _i, _i, _i, _p, _p, _p, _i, _f, _p, _p, _p, _i64, _p, _p, _p]),
+    "vft_qlora_bwd_dx": (_i, [_p, _i64, _p, _p, _i64, _i64, _i, _i, _i, _p, _p, _i, _f, _p, _p, _p, _i64, _p, _p, _p]),
     "vft_lora_bwd_dab": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i, _i, _f, _p, _p, _p, _i64, _p]),
 }
 

@@ -250,6 +250,17 @@ class Linear4bit(nn.Linear):
         qs.denest()
         return w.data, qs
 
+    def _tiled(self, packed: torch.Tensor, qs: "QuantState"):
+        """Micro-tiled copy of the packed weight for the fused kernels, built once per (storage, device) on first
+        use.  Derived data: not a parameter, not a buffer, never in state_dict()."""
+        key = (packed.data_ptr(), qs.absmax.data_ptr(), packed.device)
+        cache = self.__dict__.get("_vft_tiled")
+        if cache is None or cache[0] != key:
+            tiles = ops.nf4_tile_weight(packed, qs.absmax, self.out_features, self.in_features, qs.blocksize)
+            cache = (key, tiles)
+            self.__dict__["_vft_tiled"] = cache
+        return cache[1]
+
     def _cast_input(self, x: torch.Tensor) -> torch.Tensor:
         if torch.is_autocast_enabled("cuda") and x.is_cuda:
             return x.to(torch.get_autocast_dtype("cuda"))
@@ -262,7 +273,7 @@ class Linear4bit(nn.Linear):
         inp_dtype = x.dtype
         x = self._cast_input(x)
         out = ops.qlora_linear(x, packed, qs.absmax, self.bias, None, None, 0.0, self.out_features, self.in_features,
-                               qs.blocksize, qs.dtype)
+                               qs.blocksize, qs.dtype, self._tiled(packed, qs))
         return out.to(inp_dtype)
 
     def forward_with_lora(self, x: torch.Tensor, lora_a: torch.Tensor, lora_b: torch.Tensor, scale: float) -> torch.Tensor:
@@ -271,7 +282,7 @@ class Linear4bit(nn.Linear):
         inp_dtype = x.dtype
         x = self._cast_input(x)
         out = ops.qlora_linear(x, packed, qs.absmax, self.bias, lora_a, lora_b, scale, self.out_features,
-                               self.in_features, qs.blocksize, qs.dtype)
+                               self.in_features, qs.blocksize, qs.dtype, self._tiled(packed, qs))
         return out.to(inp_dtype)
 
     def _save_to_state_dict(self, destination, prefix, keep_vars):

@@ -98,6 +98,22 @@ def nf4_quantize_host(w: torch.Tensor, blocksize: int = 64) -> tuple[torch.Tenso
     return packed, absmax
 
 
+def nf4_tile_weight(packed: torch.Tensor, absmax: torch.Tensor, out_features: int, in_features: int,
+                    blocksize: int = 64) -> tuple[torch.Tensor, torch.Tensor] | None:
+    """Kernel-friendly 64x64 micro-tiled copy of a packed weight (see csrc/nf4_quant.cu); None when the layout does
+    not apply (blocksize != 64 or in_features % 64 != 0).  Derived data: never part of a checkpoint."""
+    dev = _require_cuda(packed, absmax)
+    N, K = int(out_features), int(in_features)
+    if blocksize != 64 or K % 64 != 0 or packed.data_ptr() % 16 != 0:
+        return None
+    codes_t = torch.empty((lib.vft_nf4_tiled_bytes(N, K, 0),), dtype=torch.uint8, device=dev)
+    absmax_t = torch.empty((lib.vft_nf4_tiled_bytes(N, K, 1) // 4,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.vft_nf4_tile_weight(packed.data_ptr(), absmax.contiguous().float().data_ptr(), N, K, blocksize,
+                                      codes_t.data_ptr(), absmax_t.data_ptr(), _stream()))
+    return codes_t, absmax_t
+
+
 # ----------------------------------------------------------------------------- fused layer
 class QLoRALinearFunction(torch.autograd.Function):
     """y = x . W~^T (+bias) + scale * (x . A^T) . B^T with W~ decoded from NF4 inside the GEMM.
@@ -108,8 +124,10 @@ class QLoRALinearFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, packed, absmax, bias, lora_a, lora_b, scale, out_features, in_features, blocksize, qdtype):
+    def forward(ctx, x, packed, absmax, bias, lora_a, lora_b, scale, out_features, in_features, blocksize, qdtype,
+                tiled=None):
         dev = _require_cuda(x, packed, absmax, bias, lora_a, lora_b)
+        codes_t, absmax_t = tiled if tiled is not None else (None, None)
         N, K = int(out_features), int(in_features)
         if x.shape[-1] != K:
             raise RuntimeError(f"input feature size {x.shape[-1]} does not match in_features {K}")
@@ -132,10 +150,12 @@ class QLoRALinearFunction(torch.autograd.Function):
             check(
                 lib.vft_qlora_fwd(
                     x2.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, blocksize, act, dtype_code(qdtype),
-                    _ptr(bias), _ptr(lora_a), _ptr(lora_b), r, float(scale), y.data_ptr(), _ptr(t_save), None, 0, _stream(),
+                    _ptr(bias), _ptr(lora_a), _ptr(lora_b), r, float(scale), y.data_ptr(), _ptr(t_save), None, 0,
+                    _ptr(codes_t), _ptr(absmax_t), _stream(),
                 )
             )
         ctx.meta = (N, K, blocksize, act, dtype_code(qdtype), r, float(scale), x.shape)
+        ctx.tiled = (codes_t, absmax_t)  # frozen derived buffers, not autograd-tracked
         ctx.save_for_backward(x2 if r else None, packed, absmax, lora_a, lora_b, t_save)
         return y.reshape(*x.shape[:-1], N)
 
@@ -143,6 +163,7 @@ class QLoRALinearFunction(torch.autograd.Function):
     def backward(ctx, dy):
         N, K, blocksize, act, qd, r, scale, x_shape = ctx.meta
         x2, packed, absmax, lora_a, lora_b, t_save = ctx.saved_tensors
+        codes_t, absmax_t = ctx.tiled
         dev = dy.device
         dy2 = dy.reshape(-1, N)
         if dy2.dtype != _TORCH_DT[act]:
@@ -160,7 +181,8 @@ class QLoRALinearFunction(torch.autograd.Function):
                 check(
                     lib.vft_qlora_bwd_dx(
                         dy2.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, blocksize, act, qd,
-                        _ptr(lora_a), _ptr(lora_b), r, scale, _ptr(dx), _ptr(dt_save), None, 0, _stream(),
+                        _ptr(lora_a), _ptr(lora_b), r, scale, _ptr(dx), _ptr(dt_save), None, 0,
+                        _ptr(codes_t), _ptr(absmax_t), _stream(),
                     )
                 )
             if need_ab:
@@ -175,8 +197,11 @@ class QLoRALinearFunction(torch.autograd.Function):
                     )
                 )
         dxo = dx.reshape(x_shape) if need_dx else None
-        return dxo, None, None, None, da, db, None, None, None, None, None
+        return dxo, None, None, None, da, db, None, None, None, None, None, None
 
 
-def qlora_linear(x, packed, absmax, bias, lora_a, lora_b, scale, out_features, in_features, blocksize=64, qdtype=torch.bfloat16):
-    return QLoRALinearFunction.apply(x, packed, absmax, bias, lora_a, lora_b, scale, out_features, in_features, blocksize, qdtype)
+def qlora_linear(x, packed, absmax, bias, lora_a, lora_b, scale, out_features, in_features, blocksize=64,
+                 qdtype=torch.bfloat16, tiled=None):
+    """``tiled``: optional (codes_t, absmax_t) from :func:`nf4_tile_weight` for the same weight."""
+    return QLoRALinearFunction.apply(x, packed, absmax, bias, lora_a, lora_b, scale, out_features, in_features,
+                                     blocksize, qdtype, tiled)
