@@ -38,18 +38,38 @@ def main():
         "dA/dB          ": lambda i: L.vft_lora_bwd_dab(gs[i % NSET].data_ptr(), xs[i % NSET].data_ptr(), ts.data_ptr(), dts.data_ptr(), T, N, K, r, 2, 1.0 / r, dA.data_ptr(), dB.data_ptr(), ws.data_ptr(), wsb, st),
     }
     tot = {}
+    REP = 20
     for name, fn in calls.items():
-        for i in range(5): _cabi.check(fn(i))
+        for i in range(3): _cabi.check(fn(i))
         torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            sst = side.cuda_stream
+            # the lambdas read `st` from the enclosing scope at call time
+            st_saved = st
+            st = sst
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(REP): _cabi.check(fn(i))
+            st = st_saved
+        graph.replay(); torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for i in range(40): _cabi.check(fn(i))
+        for _ in range(5): graph.replay()
         b.record(); torch.cuda.synchronize()
-        tot[name] = a.elapsed_time(b) / 40 * 1e3
+        tot[name] = a.elapsed_time(b) / (5 * REP) * 1e3
         print(f"  {name}: {tot[name]:7.1f} us")
+    if int(os.environ.get("VFT_TC_DEBUG", "0")) & 16:
+        import ctypes
+        names = ["entry", "setup done", "first full", "last full", "acc in regs", "after cluster sync", "stored", "exit"]
+        for nm in ("dt only        ", "dA/dB          "):
+            _cabi.check(calls[nm](0)); torch.cuda.synchronize()
+            buf = (ctypes.c_ulonglong * 16)()
+            L.vft_debug_side_timeline(buf, 16)
+            print(f"  side-kernel timeline [{nm.strip()}] (ns since entry): " + ", ".join(f"{n} {buf[i]-buf[0]}" for i, n in enumerate(names)))
     step = tot["fwd  (+LoRA)   "] + tot["bwd  (+LoRA)   "] + tot["dA/dB          "]
     fl = 4 * T * N * K + 6 * T * r * (N + K)
-    print(f"T={T} N={N} K={K} r={r}: step (3 calls back to back, no graph) {step:.1f} us -> {fl / step / 1e6:.0f} TF/s; "
+    print(f"T={T} N={N} K={K} r={r}: step (3 calls, CUDA-graph replay) {step:.1f} us -> {fl / step / 1e6:.0f} TF/s; "
           f"adapter side kernels {step - tot['fwd  (NF4 only)'] - tot['bwd  (NF4 only)']:.1f} us")
 
 main()

@@ -1,6 +1,7 @@
 // extern "C" entry points of libvft_b200.so (declared in include/vft_b200.h) and the
 // dispatcher between the tcgen05 family (qlora_tc.cu) and the generic family (qlora_simt.cu).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -48,6 +49,12 @@ static bool use_tc(const LayerArgs& a, bool backward, int* status) {
   }
   if (forced == VFT_PATH_SIMT) return false;
   return ok;
+}
+
+// triage switch: VFT_SIDE_MMA=1 keeps the mma.sync adapter kernels (lora_mma.cu) instead of lora_tc.cu
+static bool side_mma() {
+  const char* e = getenv("VFT_SIDE_MMA");
+  return e && e[0] == '1';
 }
 
 }  // namespace vft
@@ -150,7 +157,8 @@ int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (r > 0) {
     rc = (forced_path() == VFT_PATH_SIMT) ? simt_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st)
-                                          : mma_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st);
+                                          : side_mma() ? mma_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st)
+                                                       : tc_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st);
     if (rc != VFT_OK) return rc;
   }
   const bool tc = use_tc(a, false, &rc);
@@ -173,7 +181,8 @@ int vft_qlora_bwd_dx(const void* dy, int64_t T, const uint8_t* packed, const flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (r > 0) {
     rc = (forced_path() == VFT_PATH_SIMT) ? simt_lora_dt(dy, lora_b, T, N, r, scale, act_dtype, dt_save, st)
-                                          : mma_lora_dt(dy, lora_b, T, N, r, scale, act_dtype, dt_save, st);
+                                          : side_mma() ? mma_lora_dt(dy, lora_b, T, N, r, scale, act_dtype, dt_save, st)
+                                                       : tc_lora_dt(dy, lora_b, T, N, r, scale, act_dtype, dt_save, st);
     if (rc != VFT_OK) return rc;
   }
   if (dx == nullptr) {
@@ -201,8 +210,11 @@ int vft_lora_bwd_dab(const void* dy, const void* x, const void* t_save, const vo
   if (forced_path() == VFT_PATH_SIMT)
     return simt_dab(dy, x, t_save, dt_save, T, N, K, r, act_dtype, scale, dA, dB, static_cast<float*>(ws),
                     static_cast<cudaStream_t>(stream));
-  return mma_dab(dy, x, t_save, dt_save, T, N, K, r, act_dtype, scale, dA, dB, static_cast<float*>(ws),
-                 static_cast<cudaStream_t>(stream));
+  if (side_mma())
+    return mma_dab(dy, x, t_save, dt_save, T, N, K, r, act_dtype, scale, dA, dB, static_cast<float*>(ws),
+                   static_cast<cudaStream_t>(stream));
+  return tc_dab(dy, x, t_save, dt_save, T, N, K, r, act_dtype, scale, dA, dB, static_cast<float*>(ws),
+                static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -130,6 +130,14 @@ int mma_lora_dt(const void* dy, const void* b, int64_t T, int64_t N, int r, floa
 int mma_dab(const void* dy, const void* x, const void* t_save, const void* dt_save, int64_t T, int64_t N, int64_t K,
             int r, int act_dtype, float scale, void* dA, void* dB, float* ws, cudaStream_t st);
 
+// tcgen05 + TMA form of the same three products (lora_tc.cu); falls back to mma_* when unsupported
+int tc_lora_down(const void* x, const void* a, int64_t T, int64_t K, int r, int act_dtype, void* t_save,
+                 cudaStream_t st);
+int tc_lora_dt(const void* dy, const void* b, int64_t T, int64_t N, int r, float scale, int act_dtype, void* dt_save,
+               cudaStream_t st);
+int tc_dab(const void* dy, const void* x, const void* t_save, const void* dt_save, int64_t T, int64_t N, int64_t K,
+           int r, int act_dtype, float scale, void* dA, void* dB, float* ws, cudaStream_t st);
+
 // tcgen05 family
 bool tc_supported(const LayerArgs& a, bool backward);
 int tc_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st);
