@@ -386,9 +386,14 @@ def run_gpu_arm(args):
         flops_launch = 2 * T * N_FEAT * K_FEAT
         achieved = 2 * flops_launch / ((t_f + t_b) * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": UNIT,
-                "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"] + ", burst",
-                "kernel": "qlora_tc_kernel (fwd + bwd launches)", "fwd_us": t_f * 1e3, "bwd_us": t_b * 1e3,
-                "flops_per_launch": flops_launch}
+                "frac": achieved / peaks["bf16_tflops"],
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
+                # kernel (profiles/r01_ncu_pair_kernel_*.txt: 30.5 MB read + 0.4 MB written; the 25 MB of output
+                # stay in the 126 MB L2 past the end of the launch).  Algorithmic minimum x + y + packed W: 55.9 MB.
+                "traffic": 30.9e6, "traffic_source": "ncu dram bytes per launch, profiles/r01_ncu_pair_kernel_before_tiling.txt",
+                "peak_source": peaks["source"] + ", burst",
+                "kernel": "qlora_tc2_kernel (persistent CTA-pair tcgen05 GEMM; forward + backward launches)",
+                "fwd_us": t_f * 1e3, "bwd_us": t_b * 1e3, "flops_per_launch": flops_launch}
 
     # ---- secondary figures of merit (same run, rank 0): quantize/pack GB/s, small-T weight-stream GB/s
     extra = {}
@@ -417,7 +422,7 @@ def run_gpu_arm(args):
             r = time_cpu(256, 3, 1)
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                    "sample": f"256 of {TOKENS} tokens, 1 warm-up + 3 runs of the oracle port (dequant + F.linear + LoRA, autograd)"}
-        kernels_per_step = 7  # lora_down, tc_fwd | lora_dt, tc_bwd, colsum x2, finalize
+        kernels_per_step = 5  # lora_side<x.A^T>, qlora_tc2<fwd> | lora_side<dy.B>, qlora_tc2<bwd>, lora_side<dA,dB>
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
