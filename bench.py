@@ -203,7 +203,9 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     peaks = measured_peaks()
     model = build_layer(dev)
     layer = model.linear
@@ -257,7 +259,7 @@ def run_gpu_arm(args):
     comm = torch.cuda.Stream() if world > 1 else None
     comm_events = [None] * n_sets
 
-    def run_step(i):
+    def run_step(i, exchange=True):
         s = i % n_sets
         if comm is not None and comm_events[s] is not None:
             torch.cuda.current_stream().wait_event(comm_events[s])  # the set's gradients are about to be overwritten
@@ -267,7 +269,7 @@ def run_gpu_arm(args):
         else:
             step(i)
             flat = torch.cat([p.grad.reshape(-1) for p in params])
-        if comm is not None:
+        if comm is not None and exchange:
             ev = torch.cuda.Event()
             ev.record()
             with torch.cuda.stream(comm):
@@ -299,7 +301,7 @@ def run_gpu_arm(args):
     # keep the GPU under the same load a little longer if the region was too short to sample clocks
     t_end = time.time() + 0.25
     while len(sampler.samples) < 8 and time.time() < t_end:
-        run_step(0)
+        run_step(0, exchange=False)  # rank-local padding: the number of iterations differs per rank, so no collective
     torch.cuda.synchronize()
     clocks = sampler.stop()
     if world > 1:
