@@ -400,23 +400,38 @@ def run_gpu_arm(args):
     # ---- secondary figures of merit (same run, rank 0): quantize/pack GB/s, small-T weight-stream GB/s
     extra = {}
     if rank == 0:
-        wq = (torch.randn(8192, 3072, device=dev) * 0.02).to(torch.bfloat16)
-        wq2 = [(torch.randn(8192, 3072, device=dev) * 0.02).to(torch.bfloat16) for _ in range(3)]
-        for t in wq2:
-            ops.nf4_quantize(t)
+        # NF4 quantize/pack (BASELINE configs[1] building block): the largest AuraFlow DiT weight [18432, 3072] bf16,
+        # device-resident, outputs preallocated, C-ABI calls replayed from a CUDA graph (host overhead off the timeline)
+        qn, qk = 18432, 3072
+        wq2 = [(torch.randn(qn, qk, device=dev) * 0.02).to(torch.bfloat16) for _ in range(3)]
+        n = qn * qk
+        q_packed = torch.empty(n // 2, dtype=torch.uint8, device=dev)
+        q_absmax = torch.empty(n // 64, dtype=torch.float32, device=dev)
+        qside = torch.cuda.Stream()
+        qgraph = torch.cuda.CUDAGraph()
+        q_reps = 9
+        with torch.cuda.stream(qside):
+            qst = qside.cuda_stream
+            for t in wq2:
+                _cabi.check(_cabi.lib.vft_nf4_quantize(t.data_ptr(), _cabi.BF16, n, 64, q_packed.data_ptr(), q_absmax.data_ptr(), qst))
+            qside.synchronize()
+            with torch.cuda.graph(qgraph, stream=qside):
+                for i in range(q_reps):
+                    _cabi.check(_cabi.lib.vft_nf4_quantize(wq2[i % 3].data_ptr(), _cabi.BF16, n, 64, q_packed.data_ptr(),
+                                                           q_absmax.data_ptr(), qst))
+        qgraph.replay()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        iters = 30
-        for i in range(iters):
-            ops.nf4_quantize(wq2[i % 3])
+        for _ in range(5):
+            qgraph.replay()
         b.record()
         torch.cuda.synchronize()
-        n = wq.numel()
-        q_ms = a.elapsed_time(b) / iters
+        q_ms = a.elapsed_time(b) / (5 * q_reps)
         gbs = (2 * n + n / 2 + n / 16) / (q_ms * 1e-3) / 1e9
         extra["nf4_quantize_pack"] = {"GB/s": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"], "elements": n,
-                                      "bytes_per_element": 2.5625, "note": "includes torch.empty of outputs per call"}
+                                      "bytes_per_element": 2.5625, "us_per_tensor": q_ms * 1e3,
+                                      "note": "bf16 [18432, 3072], device-resident, CUDA-graph replay; whole AuraFlow set: tools/quant_probe.py"}
 
     if rank == 0:
         cpu = None

@@ -23,50 +23,37 @@
 
 namespace vft {
 
-constexpr int kCells = 36;
-constexpr float kCellMagic = 8388625.0f;  // 2^23 + 17
+// Cell table.  y = fma(x, 16, 2^15 + 17) has ulp 2^-8 for x in [-1, 1], so mantissa bits [8, 14) of y hold
+// k = floor(16 x + 17) (x rounded to a 2^-12 grid first): cell k covers x in [(k - 17) / 16, (k - 16) / 16).  Cells
+// are 1/16 wide and NF4 thresholds are >= 0.0805 apart, so a cell holds at most one threshold, and
+//     code(x) = base[k] + (x > thr[k])        base[k] = number of thresholds below the cell
+// is exact PROVIDED no threshold sits within the rounding distance below a cell boundary (checked when the table
+// is built: a value there could be pushed into the next cell and skip its compare).  64 cells are allocated so
+// that the NaN of an all-zero block (0 * inf) still indexes inside the table; its word is forced to 0 afterwards.
+constexpr int kCells = 64;
+constexpr float kCellMagic = 32768.0f + 17.0f;
 
 struct CellTable {
   float thr[kCells];
-  float base[kCells];  // small integers stored as float bit patterns of uint32 (see below)
+  float base[kCells];  // number of thresholds below the cell, as a float (codes are accumulated in fp32)
 };
-
-static inline unsigned host_cell(float x) {
-  float y = fmaf(x, 16.0f, kCellMagic);
-  uint32_t u;
-  memcpy(&u, &y, 4);
-  return u & 63u;
-}
 
 static CellTable make_cell_table() {
   const float thr[15] = VFT_NF4_THRESHOLDS;
   CellTable t;
-  int owner[kCells];
-  for (int g = 0; g < kCells; ++g) owner[g] = -1;
-  for (int i = 0; i < 15; ++i) {
-    unsigned g = host_cell(thr[i]);
-    // by construction every threshold owns a distinct cell; checked in tests through bit-exactness
-    if (g < (unsigned)kCells && owner[g] < 0) owner[g] = i;
-  }
-  int below = 0;
-  for (int g = 0; g < kCells; ++g) {
-    uint32_t b = (uint32_t)below;
-    memcpy(&t.base[g], &b, 4);
-    if (owner[g] >= 0) {
-      t.thr[g] = thr[owner[g]];
-      ++below;
-    } else {
-      t.thr[g] = INFINITY;
+  for (int k = 0; k < kCells; ++k) {
+    const double lo = (k - 17) / 16.0, hi = (k - 16) / 16.0;
+    int below = 0, owner = -1;
+    for (int i = 0; i < 15; ++i) {
+      if ((double)thr[i] < lo) ++below;
+      else if ((double)thr[i] < hi) owner = i;  // at most one (spacing > cell width)
     }
+    t.base[k] = (float)below;
+    t.thr[k] = owner >= 0 ? thr[owner] : INFINITY;
+    // a threshold within 2^-8 / 16 (+ slack) below the upper boundary would break exactness: none of the 15 is
+    if (owner >= 0 && hi - (double)thr[owner] < 2.0 / 4096.0) t.thr[k] = NAN;  // poison: tests fail loudly
   }
   return t;
-}
-
-__device__ __forceinline__ unsigned encode_cell(float x, const float2* __restrict__ tab /* [cell][32] + lane */) {
-  const float y = __fmaf_rn(x, 16.0f, kCellMagic);
-  const unsigned g = __float_as_uint(y) & 63u;
-  const float2 e = tab[g * 32];
-  return __float_as_uint(e.y) + (x > e.x ? 1u : 0u);
 }
 
 template <typename T>
@@ -117,26 +104,45 @@ constexpr int kWarpElems = 32 * 8;                      // elements per warp per
 constexpr int kChunkElems = kWarpElems * kQuantUnroll;  // 1024
 
 // Fast path: blocksize == 64, n_main a multiple of 1024, w 16-byte aligned.
+// The kernel is bound by instruction issue, not by memory (ncu of the first version: 18 instructions per element,
+// 82 % issue-active at 62 % of HBM speed), so the per-element sequence is kept to
+//     unpack, FMUL (x = w * s), FFMA (cell), LOP3 (table address), LDS.64, FSET (x > thr -> 1.0/0.0), FADD, FFMA
+// with the 4-bit codes accumulated as fp32 (two 16-bit halves per 8 elements, exact) so that the packing runs on
+// the FMA pipe, and the table address is a single LOP3: the table is 16 KB-aligned in shared memory, replicated per
+// lane ([cell][lane], 8 bytes each: conflict-free), and the cell index sits at bits [8, 14) of the FFMA result.
+constexpr int kTabBytes = kCells * 32 * 8;  // 16 KB
+
 template <typename T>
 __global__ void __launch_bounds__(kQuantThreads)
 nf4_quantize64_kernel(const T* __restrict__ w, int64_t n_chunks, uint32_t* __restrict__ packed_words,
                       float* __restrict__ absmax, const CellTable table) {
-  __shared__ float2 s_tab[kCells * 32];
+  extern __shared__ uint8_t q_smem[];
+  const uint32_t raw = static_cast<uint32_t>(__cvta_generic_to_shared(q_smem));
+  const uint32_t tab_base = (raw + (uint32_t)kTabBytes - 1u) & ~((uint32_t)kTabBytes - 1u);
+  float2* s_tab = reinterpret_cast<float2*>(q_smem + (tab_base - raw));
   for (int i = threadIdx.x; i < kCells * 32; i += kQuantThreads) {
     const int g = i >> 5;
     s_tab[i] = make_float2(table.thr[g], table.base[g]);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const float2* tab = s_tab + lane;
+  const uint32_t lane_addr = tab_base + (uint32_t)lane * 8u;
   const int64_t warp_global = (int64_t)blockIdx.x * (kQuantThreads / 32) + (threadIdx.x >> 5);
   const int64_t warp_stride = (int64_t)gridDim.x * (kQuantThreads / 32);
 
+  // register double buffering: the loads of the warp's NEXT chunk are in flight while this one is encoded
+  Vec8<T> v[kQuantUnroll], nxt[kQuantUnroll];
+  if (warp_global < n_chunks) {
+#pragma unroll
+    for (int u = 0; u < kQuantUnroll; ++u) v[u].load(w + warp_global * kChunkElems + lane * 8 + u * kWarpElems);
+  }
   for (int64_t chunk = warp_global; chunk < n_chunks; chunk += warp_stride) {
     const int64_t base = chunk * kChunkElems + lane * 8;
-    Vec8<T> v[kQuantUnroll];
+    if (chunk + warp_stride < n_chunks) {
 #pragma unroll
-    for (int u = 0; u < kQuantUnroll; ++u) v[u].load(w + base + u * kWarpElems);
+      for (int u = 0; u < kQuantUnroll; ++u)
+        nxt[u].load(w + (chunk + warp_stride) * kChunkElems + lane * 8 + u * kWarpElems);
+    }
 #pragma unroll
     for (int u = 0; u < kQuantUnroll; ++u) {
       float f[8];
@@ -147,19 +153,29 @@ nf4_quantize64_kernel(const T* __restrict__ w, int64_t n_chunks, uint32_t* __res
       am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
       am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
       am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 4));
-      const float s = __fdiv_rn(1.0f, am);  // IEEE reciprocal; +inf for an all-zero block
-      uint32_t word = 0;
+      const float s = __frcp_rn(am);  // correctly rounded 1.0f / am (same value as IEEE division); +inf for am = 0
+      // element 2j goes to the HIGH nibble of byte j: weights 16, 1, 4096, 256 inside each 16-bit half
+      float half_acc[2] = {0.0f, 0.0f};
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const unsigned c = encode_cell(__fmul_rn(f[i], s), tab);
-        // element e=2j in the high nibble of byte j; bytes little-endian inside the word
-        word |= c << (8 * (i >> 1) + ((i & 1) ? 0 : 4));
+        const float x = __fmul_rn(f[i], s);
+        const float y = __fmaf_rn(x, 16.0f, kCellMagic);
+        uint32_t addr;  // (bits(y) & 0x3F00) | lane_addr as ONE LOP3 (the compiler otherwise emits AND + ADD)
+        asm("lop3.b32 %0, %1, 0x3F00, %2, 0xEA;" : "=r"(addr) : "r"(__float_as_uint(y)), "r"(lane_addr));
+        float2 e;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e.x), "=f"(e.y) : "r"(addr));
+        const float code = e.y + (x > e.x ? 1.0f : 0.0f);
+        const float wgt = (float)(1u << (8 * ((i & 3) >> 1) + ((i & 1) ? 0 : 4)));
+        half_acc[i >> 2] = __fmaf_rn(code, wgt, half_acc[i >> 2]);
       }
+      uint32_t word = __float2uint_rz(half_acc[0]) | (__float2uint_rz(half_acc[1]) << 16);
       if (am == 0.0f) word = 0;  // 0 * inf = NaN -> every '>' false -> code 0
       const int64_t e0 = base + u * kWarpElems;
       packed_words[e0 >> 3] = word;
       if ((lane & 7) == 0) absmax[e0 >> 6] = am;
     }
+#pragma unroll
+    for (int u = 0; u < kQuantUnroll; ++u) v[u] = nxt[u];
   }
 }
 
@@ -203,9 +219,9 @@ static int quantize_typed(const T* w, int64_t n, int blocksize, uint8_t* packed,
     const int64_t n_chunks = n_main / kChunkElems;
     const int warps_per_block = kQuantThreads / 32;
     int64_t blocks = ceil_div64(n_chunks, warps_per_block);
-    const int64_t max_blocks = 148 * 8;  // 8 resident CTAs of 256 threads per SM
+    const int64_t max_blocks = 148 * 6;  // 6 resident CTAs of 256 threads per SM (32 KB of shared memory each)
     if (blocks > max_blocks) blocks = max_blocks;
-    nf4_quantize64_kernel<T><<<(unsigned)blocks, kQuantThreads, 0, st>>>(
+    nf4_quantize64_kernel<T><<<(unsigned)blocks, kQuantThreads, 2 * kTabBytes, st>>>(
         w, n_chunks, reinterpret_cast<uint32_t*>(packed), absmax, table);
     VFT_CUDA_OK(cudaGetLastError());
   }
