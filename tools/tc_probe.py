@@ -19,10 +19,13 @@ def main():
     y = torch.empty(T, N, device=dev, dtype=torch.bfloat16)
     dx = torch.empty(T, K, device=dev, dtype=torch.bfloat16)
     st = torch.cuda.current_stream().cuda_stream
+    WFB = _cabi.lib.vft_workspace_bytes(0, T, N, K, 0); WBB = _cabi.lib.vft_workspace_bytes(1, T, N, K, 0)
+    wf_t = torch.empty(max(WFB, 4), dtype=torch.uint8, device=dev); wb_t = torch.empty(max(WBB, 4), dtype=torch.uint8, device=dev)
+    WF = wf_t.data_ptr() if WFB else None; WB = wb_t.data_ptr() if WBB else None
     def fwd(i):
-        _cabi.check(_cabi.lib.vft_qlora_fwd(xs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, None, 0, 0.0, y.data_ptr(), None, None, 0, TC, TA, st))
+        _cabi.check(_cabi.lib.vft_qlora_fwd(xs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, None, 0, 0.0, y.data_ptr(), None, WF, WFB, TC, TA, st))
     def bwd(i):
-        _cabi.check(_cabi.lib.vft_qlora_bwd_dx(gs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, 0, 0.0, dx.data_ptr(), None, None, 0, TC, TA, st))
+        _cabi.check(_cabi.lib.vft_qlora_bwd_dx(gs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, 0, 0.0, dx.data_ptr(), None, WB, WBB, TC, TA, st))
     res = {}
     for name, fn in (("fwd", fwd), ("bwd", bwd)):
         for i in range(5): fn(i)
@@ -32,7 +35,7 @@ def main():
         for i in range(40): fn(i)
         b.record(); torch.cuda.synchronize()
         res[name] = a.elapsed_time(b) / 40 * 1e3
-    if int(os.environ.get("VFT_TC_DEBUG", "0")) & 16 and T < 512:
+    if False:
         import ctypes
         fwd(0); torch.cuda.synchronize()
         buf = (ctypes.c_ulonglong * 512)()
@@ -41,7 +44,7 @@ def main():
         c0, n0 = buf[0], buf[1]
         for i, nm in enumerate(names):
             print(f"   {nm:18s} +{buf[2*i]-c0:8d} cyc  +{(buf[2*i+1]-n0)/1e3:8.2f} us")
-    if int(os.environ.get("VFT_TC_DEBUG", "0")) & 16 and hasattr(_cabi.lib, "vft_debug_tc2_timeline") and T >= 512:
+    if int(os.environ.get("VFT_TC_DEBUG", "0")) & 16 and hasattr(_cabi.lib, "vft_debug_tc2_timeline"):
         import ctypes
         for nm, fn in (("fwd", fwd), ("bwd", bwd)):
             fn(0); torch.cuda.synchronize()
@@ -53,7 +56,7 @@ def main():
             def rel(v): return (v - t0) if v else -1
             print(f"  [{nm}] pair-kernel timeline (cycles since first producer wait), leader CTA of pair 0")
             print("   step: mma_full_seen  mma_commit   | prod_empty_seen")
-            for g in list(range(0, 12)) + list(range(40, 56)) + list(range(88, 100)):
+            for g in list(range(0, 12)) + list(range(40, 56)):
                 print(f"   {g:4d}: {rel(rows[0][g]):10d} {rel(rows[1][g]):10d}   | {rel(rows[5][g]):10d}")
             print("   decode group0 (steps 0,4,8..): empty_seen, stores issued, arrived")
             for i in list(range(0, 6)) + list(range(10, 14)):

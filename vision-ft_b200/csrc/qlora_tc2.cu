@@ -90,6 +90,11 @@ struct Tc2Params {
   int stage_bytes;  // (backward: kATileBytes +) n_acc * b_bytes
   int n_fblk;       // feature blocks of 256
   int n_tiles;      // n_fblk * token blocks
+  // split-K (small problems: fewer tiles than SM pairs): a work item is (tile, split); split i reduces ring steps
+  // [i * k_per, (i + 1) * k_per) of the contraction (the adapter step belongs to the last split) and ADDS its fp32
+  // partial tile into `partial` [T, OUT] (zeroed by the host; converted by qlora_tc2_finalize_kernel afterwards)
+  int n_split, k_per;
+  float* partial;
   int debug;        // VFT_TC_DEBUG triage mask (results are garbage when non-zero): 1 = no decode stores,
                     // 2 = no MMAs, 4 = no epilogue stores, 8 = no TMA loads
 };
@@ -126,7 +131,6 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   const int64_t OUT = kBackward ? p.K : p.N;  // feature dimension of this GEMM
   const int64_t RED = kBackward ? p.N : p.K;  // contraction dimension
   const int n_main = (int)((RED + kBK - 1) / kBK);
-  const int n_blocks = n_main + (p.r > 0 ? 1 : 0);
   const int KB = (int)(p.K / kBK);  // absmax entries per weight row
   const int S = p.stages;
   const int n_pairs = (int)(gridDim.x >> 1);
@@ -148,6 +152,16 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   auto accs_of = [&](int64_t t0) -> int {
     const int64_t left = p.T - t0;
     return left >= tok_tile ? p.n_acc : (int)((left + p.N_acc - 1) / p.N_acc);
+  };
+
+  // work items: item -> (tile, split) -> ring steps [b0, b1) of that tile (step n_main = the adapter step)
+  const int n_items = p.n_tiles * p.n_split;
+  auto item_tile = [&](int item) { return item / p.n_split; };
+  auto item_b0 = [&](int item) { return (item % p.n_split) * p.k_per; };
+  auto item_b1 = [&](int item) {
+    const int sp = item % p.n_split;
+    const int e = min(n_main, (sp + 1) * p.k_per);
+    return sp == p.n_split - 1 ? e + (p.r > 0 ? 1 : 0) : e;
   };
 
   if (warp == kTmaWarp && ptx::elect_one()) {
@@ -182,10 +196,12 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     if (ptx::elect_one()) {
       int g = 0, s = 0;
       uint32_t empty_par = 1;
-      for (int tile = pair; tile < p.n_tiles; tile += n_pairs) {
+      for (int item = pair; item < n_items; item += n_pairs) {
+        const int tile = item_tile(item);
         const int64_t t0 = (int64_t)(tile / p.n_fblk) * tok_tile;
         const int na = accs_of(t0);
-        for (int b = 0; b < n_blocks; ++b, ++g) {
+        const int b1 = item_b1(item);
+        for (int b = item_b0(item); b < b1; ++b, ++g) {
           ptx::mbar_wait(bar_empty(s), empty_par);
           tl_mark(p, 5, g);
           if (p.debug & 8) {
@@ -226,12 +242,14 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       const bool do_mma = !(p.debug & 2);
       int g = 0, s = 0;
       uint32_t full_par = 0, acc_par = 1;
-      for (int tile = pair; tile < p.n_tiles; tile += n_pairs) {
+      for (int item = pair; item < n_items; item += n_pairs) {
+        const int tile = item_tile(item);
         const int64_t t0 = (int64_t)(tile / p.n_fblk) * tok_tile;
         const int na = accs_of(t0);
-        for (int b = 0; b < n_blocks; ++b, ++g) {
+        const int b0 = item_b0(item), b1 = item_b1(item);
+        for (int b = b0; b < b1; ++b, ++g) {
           ptx::mbar_wait(bar_full(s), full_par);
-          if (b == 0) {  // the epilogue must have drained the accumulators of the previous tile
+          if (b == b0) {  // the epilogue must have drained the accumulators of the previous work item
             for (int a = 0; a < na; ++a) ptx::mbar_wait(bar_acc_empty(a), acc_par);
           }
           ptx::tc_fence_after();
@@ -242,7 +260,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
                                             : ptx::make_smem_desc_sw128(stage_a(s), 16, 1024);
           const uint64_t b_desc0 = ptx::make_smem_desc_sw128(stage_b(s, 0), 16, 1024);
           const uint64_t b_desc1 = ptx::make_smem_desc_sw128(stage_b(s, 1), 16, 1024);
-          const uint32_t acc0 = b > 0 ? 1u : 0u;
+          const uint32_t acc0 = b > b0 ? 1u : 0u;
           // forward: A = TMEM stage s, 8 columns (16 packed 16-bit values per lane) per MMA
           const uint32_t a_tmem = tmem_d + (uint32_t)(kTmemACol0 + 32 * s);
           auto mma = [&](uint32_t d, int k, uint64_t b_desc, uint32_t accumulate) {
@@ -259,14 +277,14 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
                   for (int k = 0; k < kBK / 16; ++k) mma(tmem_d + kAccCols, k, b_desc1, k > 0 ? 1u : acc0);
                 }
               } else {  // adapter step: ceil(r / 16) MMAs per accumulator
-                for (int k = 0; k < k_lora; ++k) mma(tmem_d, k, b_desc0, (b | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < k_lora; ++k) mma(tmem_d, k, b_desc0, k > 0 ? 1u : acc0);
                 if (na > 1) {
-                  for (int k = 0; k < k_lora; ++k) mma(tmem_d + kAccCols, k, b_desc1, (b | k) != 0 ? 1u : 0u);
+                  for (int k = 0; k < k_lora; ++k) mma(tmem_d + kAccCols, k, b_desc1, k > 0 ? 1u : acc0);
                 }
               }
             }
             ptx::umma_commit_pair(bar_empty(s));  // the stage is reusable in both CTAs once these MMAs have read it
-            if (b == n_blocks - 1) ptx::umma_commit_pair(bar_acc_full);  // tile complete -> epilogue warps, both CTAs
+            if (b == b1 - 1) ptx::umma_commit_pair(bar_acc_full);  // item complete -> epilogue warps, both CTAs
           }
           __syncwarp();
           tl_mark(p, 1, g);
@@ -292,7 +310,8 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     const uint32_t lane_base = tmem_d + ((uint32_t)(quad * 32) << 16);
     const uint32_t epi_smem = bar_base - (uint32_t)kEpiBytes + (uint32_t)(quad * 32 + lane) * 2u;
     uint32_t it = 0, chunk = 0;
-    for (int tile = pair; tile < p.n_tiles; tile += n_pairs, ++it) {
+    for (int item = pair; item < n_items; item += n_pairs, ++it) {
+      const int tile = item_tile(item);
       const int64_t t0 = (int64_t)(tile / p.n_fblk) * tok_tile;
       const int na = accs_of(t0);
       const int64_t feat0 = (int64_t)(tile % p.n_fblk) * (2 * kBM) + (int64_t)rank * kBM;
@@ -318,6 +337,16 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar_acc_empty(a), 0));
           }
           if (!live) continue;
+          if (p.n_split > 1) {  // split-K: add the fp32 partial tile to the workspace (32 consecutive floats per token)
+            if (feat < OUT && !(p.debug & 4)) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int64_t t = ta + c0 + j;
+                if (c0 + j < p.N_acc && t < p.T) atomicAdd(p.partial + t * OUT + feat, __uint_as_float(v[j]));
+              }
+            }
+            continue;
+          }
           const uint32_t buf = epi_smem + (chunk & 1u) * (uint32_t)(kEpiBytes / 2);
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
@@ -361,13 +390,14 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     const uint32_t a_xor = (uint32_t)(row & 7) << 4;
 
     struct Pos {
-      int b;     // pipeline step within the tile
-      int tile;  // global tile index
+      int b;     // ring step of the tile's contraction (n_main = the adapter step)
+      int item;  // work item (tile, split)
     };
-    auto normalize = [&](Pos& q) {
-      while (q.b >= n_blocks) {
-        q.b -= n_blocks;
-        q.tile += n_pairs;
+    auto normalize = [&](Pos& q) {  // carry an overflow past the item's last step into the pair's next item(s)
+      while (q.item < n_items && q.b >= item_b1(q.item)) {
+        const int over = q.b - item_b1(q.item);
+        q.item += n_pairs;
+        q.b = (q.item < n_items ? item_b0(q.item) : 0) + over;
       }
     };
     // first feature of this CTA's half of the tile (forward: out-feature n; backward: in-feature k)
@@ -378,8 +408,8 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     auto prefetch = [&](const Pos& q) {
       q0 = q1 = make_uint4(0, 0, 0, 0);
       am = 0.0f;
-      if (q.tile >= p.n_tiles || q.b >= n_main) return;
-      const int64_t f0 = f0_of(q.tile);
+      if (q.item >= n_items || q.b >= n_main) return;
+      const int64_t f0 = f0_of(item_tile(q.item));
       int64_t wrow, wcol;  // element coordinates of this thread's quantization block in W [N, K]
       if (kBackward) {
         wrow = (int64_t)q.b * kBK + row;
@@ -405,16 +435,16 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       }
     };
 
-    Pos cur{group, pair};
+    Pos cur{(pair < n_items ? item_b0(pair) : 0) + group, pair};
     normalize(cur);
     prefetch(cur);
     // forward: this thread's lane of the TMEM weight ring (warp % 4 = lane quadrant the warp may access)
     const uint32_t a_tmem_lane = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)kTmemACol0;
     int s = group;  // S >= kGroups: at most one ring wrap per step of kGroups
     uint32_t empty_parity = 1;
-    for (int g = group; cur.tile < p.n_tiles; g += kGroups) {
+    for (int g = group; cur.item < n_items; g += kGroups) {
       const uint32_t a_tile = stage_a(s) + a_row_off;
-      Pos nxt{cur.b + kGroups, cur.tile};
+      Pos nxt{cur.b + kGroups, cur.item};
       normalize(nxt);
       uint32_t v[8][4];  // this thread's 64 decoded 16-bit values, in contraction order
       if (cur.b < n_main) {
@@ -429,7 +459,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       } else {
         // adapter step: forward row n of scale*B (r values), backward row j of A (64 in-features)
         const ActT* lw = static_cast<const ActT*>(p.lora_w);
-        const int64_t f0 = f0_of(cur.tile);
+        const int64_t f0 = f0_of(item_tile(cur.item));
         prefetch(nxt);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -497,6 +527,29 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   }
 }
 
+// split-K epilogue: out[t, f] = ActT(partial[t, f] + bias[f]); 8 outputs per thread (OUT % 8 == 0)
+template <typename ActT>
+__global__ void qlora_tc2_finalize_kernel(const float* __restrict__ partial, const ActT* __restrict__ bias, int64_t total8,
+                                          int64_t OUT, ActT* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int64_t e = i * 8;
+  const int64_t f = e % OUT;
+  const float4 a = __ldcs(reinterpret_cast<const float4*>(partial + e));
+  const float4 b = __ldcs(reinterpret_cast<const float4*>(partial + e) + 1);
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  if (bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += to_f32<ActT>(bias[f + j]);
+  }
+  uint4 q;
+  q.x = pack2<ActT>(v[0], v[1]);
+  q.y = pack2<ActT>(v[2], v[3]);
+  q.z = pack2<ActT>(v[4], v[5]);
+  q.w = pack2<ActT>(v[6], v[7]);
+  *reinterpret_cast<uint4*>(out + e) = q;
+}
+
 // ---------------------------------------------------------------------------
 // host side: tile shape selection + launch
 // ---------------------------------------------------------------------------
@@ -523,40 +576,83 @@ static bool config_ok(bool tmem_a, int n_acc, int N_acc) {
   return max_stages(tmem_a, n_acc, N_acc) >= kGroups;  // a decode group may run at most one ring phase ahead
 }
 
-static Tc2Config choose_config(int64_t T, int64_t OUT, int n_blocks, int n_pairs, bool tmem_a) {
-  Tc2Config best{0, 0, 0, 1e300};
+// Split-K plan: with fewer tiles than half the SM pairs, the contraction of every tile is divided over n_split work
+// items so that about one item per pair exists; their fp32 partial tiles are summed in a caller-provided workspace.
+struct Tc2Plan {
+  Tc2Config cfg;
+  int n_tiles, n_split, k_per;
+  int64_t ws_bytes;  // 0 when no split is used
+};
+
+// Tile shape and split are chosen together from a cycle model of one CTA: per ring step the tensor pipe needs
+// 2*N_acc cycles per accumulator (M = 256 over the pair, K = 64), decode ~620 ALU-pipe cycles per 128 x 64 weight
+// tile, shared memory 128 B/clk over the activation boxes (TMA write + MMA read) and -- backward only -- the decoded
+// tile (written once, read once per accumulator); per work item ~2500 cycles of fill + ~20 cycles per token of
+// epilogue (128 per token when the partial tile leaves through fp32 atomics); a split adds a memset and a finalize
+// launch (~6000 cycles).  In practice the split wins only for a few tokens (adaLN / modulation layers, T = batch).
+static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a, int n_pairs, bool allow_split = true) {
+  Tc2Plan best = {};
+  double best_cost = 1e300;
+  const int n_main = (int)ceil_div64(RED, kBK);
   const int64_t n_f = ceil_div64(OUT, 2 * kBM);
+  const int64_t ws = T * OUT * (int64_t)sizeof(float);
   for (int n_acc = 1; n_acc <= kMaxAcc; ++n_acc) {
     for (int N_acc = 32; N_acc <= 256; N_acc += 16) {
       if (!config_ok(tmem_a, n_acc, N_acc)) continue;
       const int b_bytes = (N_acc / 2) * 128;
       const int64_t tok = (int64_t)n_acc * N_acc;
       const int64_t tiles = n_f * ceil_div64(T, tok);
-      const double waves = (double)ceil_div64(tiles, n_pairs);
       const double mma = 2.0 * N_acc * n_acc;
       const double smem = ((tmem_a ? 0.0 : kATileBytes * (1.0 + n_acc)) + 2.0 * n_acc * b_bytes) / 128.0;
       double step = mma > smem ? mma : smem;
-      if (step < 620.0) step = 620.0;  // decode: ~600 ALU-pipe cycles per 128 x 64 weight tile
-      const double cost = waves * (n_blocks * step + 2500.0 + 6.0 * tok);
-      if (cost < best.cost * 0.999 || (cost < best.cost * 1.001 && N_acc > best.N_acc))
-        best = {n_acc, N_acc, max_stages(tmem_a, n_acc, N_acc), cost};
+      if (step < 620.0) step = 620.0;
+      int split = 1, k_per = n_main;
+      if (allow_split && tiles * 2 <= n_pairs && n_main >= 4 && ws <= (64ll << 20)) {
+        int want = (int)(n_pairs / tiles);
+        if (want > n_main / 2) want = n_main / 2;  // at least two ring steps per item
+        if (want > 1) {
+          k_per = (n_main + want - 1) / want;
+          split = (n_main + k_per - 1) / k_per;
+          if (split <= 1) { split = 1; k_per = n_main; }
+        }
+      }
+      const double waves = (double)ceil_div64(tiles * split, n_pairs);
+      // split epilogue: one fp32 atomic per (feature lane, token), ~1 cycle per lane-atomic on the SM's path to L2
+      const double tok_live = (double)(tok < T ? tok : T);
+      const double epi = split > 1 ? 128.0 * tok_live : 20.0 * tok;
+      const double cost = waves * ((k_per + (r > 0 ? 1 : 0)) * step + 2500.0 + epi) + (split > 1 ? 6000.0 : 0.0);
+      if (cost < best_cost * 0.999 || (cost < best_cost * 1.001 && N_acc > best.cfg.N_acc)) {
+        best_cost = cost;
+        best.cfg = {n_acc, N_acc, max_stages(tmem_a, n_acc, N_acc), cost};
+        best.n_tiles = (int)tiles;
+        best.n_split = split;
+        best.k_per = k_per;
+        best.ws_bytes = split > 1 ? ws : 0;
+      }
     }
   }
   return best;
+}
+
+static int device_pairs() {
+  int dev = 0, n_sm = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  else cudaGetLastError();
+  return n_sm / 2 > 0 ? n_sm / 2 : 1;
 }
 
 template <typename ActT, bool kBackward>
 static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void* lora_act, cudaStream_t st) {
   const int64_t OUT = kBackward ? a.K : a.N;
   const int64_t RED = kBackward ? a.N : a.K;
-  int dev = 0, n_sm = 0;
-  VFT_CUDA_OK(cudaGetDevice(&dev));
-  VFT_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  int n_pairs = n_sm / 2;
-  if (n_pairs < 1) n_pairs = 1;
-  const int n_blocks = (int)ceil_div64(RED, kBK) + (a.r > 0 ? 1 : 0);
+  const int n_pairs = device_pairs();
   constexpr bool kTmemA = !kBackward;
-  Tc2Config cfg = choose_config(a.T, OUT, n_blocks, n_pairs, kTmemA);
+  const char* nosplit = getenv("VFT_TC2_NOSPLIT");
+  Tc2Plan plan = plan_tc2(a.T, OUT, RED, a.r, kTmemA, n_pairs);
+  if (plan.n_split > 1 && (a.ws == nullptr || a.ws_bytes < plan.ws_bytes || (nosplit && nosplit[0] == '1')))
+    plan = plan_tc2(a.T, OUT, RED, a.r, kTmemA, n_pairs, /*allow_split=*/false);  // no workspace: unsplit shape
+  Tc2Config cfg = plan.cfg;
+  bool forced_cfg = false;
   if (const char* e = getenv("VFT_TC2_NACC")) {  // triage override: "<n_acc>x<N_acc>" (clamped to what the path allows)
     int na = 0, nn = 0;
     if (sscanf(e, "%dx%d", &na, &nn) == 2) {
@@ -565,6 +661,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
         cfg.n_acc = na;
         cfg.N_acc = nn;
         cfg.stages = max_stages(kTmemA, na, nn);
+        forced_cfg = true;
       }
     }
   }
@@ -588,6 +685,15 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
   p.stage_bytes = (kTmemA ? 0 : kATileBytes) + cfg.n_acc * p.b_bytes;
   p.n_fblk = (int)ceil_div64(OUT, 2 * kBM);
   p.n_tiles = p.n_fblk * (int)ceil_div64(a.T, (int64_t)cfg.n_acc * cfg.N_acc);
+  p.n_split = 1;
+  p.k_per = (int)ceil_div64(RED, kBK);
+  p.partial = nullptr;
+  if (!forced_cfg && plan.n_split > 1) {
+    p.n_split = plan.n_split;
+    p.k_per = plan.k_per;
+    p.partial = static_cast<float*>(a.ws);
+    VFT_CUDA_OK(cudaMemsetAsync(a.ws, 0, (size_t)plan.ws_bytes, st));
+  }
   const char* dbg = getenv("VFT_TC_DEBUG");
   p.debug = dbg ? atoi(dbg) : 0;
 
@@ -614,8 +720,9 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
   // the fewest pairs that still finish in the same number of waves (T = 4096, 3072 features: 144 tiles -> 72 pairs
   // of 2 tiles instead of 74): identical run time, and the SMs left over stay free for a concurrent NCCL all-reduce
   // of the LoRA gradients, which otherwise delays the launch of the last cluster until it has drained
-  const int waves = (p.n_tiles + n_pairs - 1) / n_pairs;
-  const int pairs = (p.n_tiles + waves - 1) / waves;
+  const int n_items = p.n_tiles * p.n_split;
+  const int waves = (n_items + n_pairs - 1) / n_pairs;
+  const int pairs = (n_items + waves - 1) / waves;
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)(2 * pairs));
   lc.blockDim = dim3(kThreads);
@@ -630,6 +737,12 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
   lc.numAttrs = 1;
   VFT_CUDA_OK(cudaLaunchKernelEx(&lc, kern, map_act, map_lora, map_out, p));
   VFT_CUDA_OK(cudaGetLastError());
+  if (p.n_split > 1) {
+    const int64_t total8 = a.T * OUT / 8;
+    qlora_tc2_finalize_kernel<ActT><<<(unsigned)ceil_div64(total8, 256), 256, 0, st>>>(
+        p.partial, static_cast<const ActT*>(p.bias), total8, OUT, static_cast<ActT*>(out));
+    VFT_CUDA_OK(cudaGetLastError());
+  }
   return VFT_OK;
 }
 
@@ -649,8 +762,15 @@ namespace vft {
 bool tc2_preferred(const LayerArgs& a, bool backward) {
   const int64_t OUT = backward ? a.K : a.N;
   if (OUT % 8 != 0) return false;  // row stride of the output must be a multiple of 16 bytes (TMA store)
-  if (const char* e = getenv("VFT_TC2")) return e[0] != '0' && OUT >= kBM + 1 && a.T >= 32;
-  return a.T >= 512 && OUT >= 2 * kBM;
+  if (const char* e = getenv("VFT_TC2")) return e[0] != '0' && OUT >= kBM + 1 && a.T >= 1;
+  return OUT >= 2 * kBM;  // every token count: small problems are split along the contraction
+}
+
+// fp32 workspace the split-K form wants for this call (0: none); the call still works without it, unsplit
+int64_t tc2_workspace_bytes(int64_t T, int64_t N, int64_t K, int r, bool backward) {
+  const int64_t OUT = backward ? K : N, RED = backward ? N : K;
+  if (T <= 0 || OUT % 8 != 0 || OUT < 2 * kBM || K % 64 != 0) return 0;
+  return plan_tc2(T, OUT, RED, r, !backward, device_pairs()).ws_bytes;
 }
 
 int tc2_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st) {

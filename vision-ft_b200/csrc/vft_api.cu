@@ -138,8 +138,9 @@ int vft_nf4_tile_weight(const uint8_t* packed, const float* absmax, int64_t N, i
 }
 
 int64_t vft_workspace_bytes(int op, int64_t T, int64_t N, int64_t K, int r) {
-  (void)T;
   if (op == VFT_OP_BWD_DAB) return (int64_t)sizeof(float) * (N + K) * (r > 0 ? r : 0);
+  if (op == VFT_OP_FWD) return tc2_workspace_bytes(T, N, K, r, false);
+  if (op == VFT_OP_BWD_DX) return tc2_workspace_bytes(T, N, K, r, true);
   return 0;
 }
 
@@ -147,10 +148,9 @@ int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* 
                   int blocksize, int act_dtype, int qdtype, const void* bias, const void* lora_a, const void* lora_b,
                   int r, float scale, void* y, void* t_save, void* ws, int64_t ws_bytes, const uint8_t* codes_t,
                   const float* absmax_t, void* stream) {
-  (void)ws;
-  (void)ws_bytes;
   VFT_REQUIRE((codes_t == nullptr) == (absmax_t == nullptr), "codes_t / absmax_t must be given together");
-  LayerArgs a{T, N, K, blocksize, act_dtype, qdtype, r, scale, packed, absmax, bias, lora_a, lora_b, codes_t, absmax_t};
+  LayerArgs a{T, N, K, blocksize, act_dtype, qdtype, r, scale, packed, absmax, bias, lora_a, lora_b, codes_t, absmax_t,
+              ws, ws_bytes};
   int rc = check_layer(a, x, y);
   if (rc != VFT_OK) return rc;
   VFT_REQUIRE(r == 0 || t_save != nullptr, "t_save is required when r > 0");
@@ -171,10 +171,9 @@ int vft_qlora_bwd_dx(const void* dy, int64_t T, const uint8_t* packed, const flo
                      int blocksize, int act_dtype, int qdtype, const void* lora_a, const void* lora_b, int r,
                      float scale, void* dx, void* dt_save, void* ws, int64_t ws_bytes, const uint8_t* codes_t,
                      const float* absmax_t, void* stream) {
-  (void)ws;
-  (void)ws_bytes;
   VFT_REQUIRE((codes_t == nullptr) == (absmax_t == nullptr), "codes_t / absmax_t must be given together");
-  LayerArgs a{T, N, K, blocksize, act_dtype, qdtype, r, scale, packed, absmax, nullptr, lora_a, lora_b, codes_t, absmax_t};
+  LayerArgs a{T, N, K, blocksize, act_dtype, qdtype, r, scale, packed, absmax, nullptr, lora_a, lora_b, codes_t, absmax_t,
+              ws, ws_bytes};
   int rc = check_layer(a, dy, dx, /*out_optional=*/true);  // dx == NULL: only dt_save is wanted
   if (rc != VFT_OK) return rc;
   VFT_REQUIRE(r == 0 || dt_save != nullptr, "dt_save is required when r > 0");

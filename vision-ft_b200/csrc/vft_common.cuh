@@ -110,6 +110,8 @@ struct LayerArgs {
   const void* lora_b;
   const uint8_t* codes_t = nullptr;  // optional micro-tiled copy (vft_nf4_tile_weight); both or neither
   const float* absmax_t = nullptr;
+  void* ws = nullptr;  // optional workspace (vft_workspace_bytes) for the split-K form of small problems
+  int64_t ws_bytes = 0;
 };
 
 // generic CUDA-core family
@@ -144,6 +146,7 @@ int tc_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaS
 int tc_bwd_dx(const LayerArgs& a, const void* dy, void* dx, const void* dt_save, cudaStream_t st);
 // persistent CTA-pair form (qlora_tc2.cu); same contract, used by tc_fwd / tc_bwd_dx for large token counts
 bool tc2_preferred(const LayerArgs& a, bool backward);
+int64_t tc2_workspace_bytes(int64_t T, int64_t N, int64_t K, int r, bool backward);
 int tc2_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st);
 int tc2_bwd_dx(const LayerArgs& a, const void* dy, void* dx, const void* dt_save, cudaStream_t st);
 

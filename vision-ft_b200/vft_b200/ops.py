@@ -114,6 +114,14 @@ def nf4_tile_weight(packed: torch.Tensor, absmax: torch.Tensor, out_features: in
     return codes_t, absmax_t
 
 
+def _workspace(op: int, T: int, N: int, K: int, r: int, dev) -> tuple[torch.Tensor | None, int]:
+    """Scratch the C side asks for (split-K partial sums of small problems); allocated from torch's caching allocator."""
+    n = lib.vft_workspace_bytes(op, T, N, K, r)
+    if n <= 0:
+        return None, 0
+    return torch.empty((n,), dtype=torch.uint8, device=dev), n
+
+
 # ----------------------------------------------------------------------------- fused layer
 class QLoRALinearFunction(torch.autograd.Function):
     """y = x . W~^T (+bias) + scale * (x . A^T) . B^T with W~ decoded from NF4 inside the GEMM.
@@ -146,11 +154,12 @@ class QLoRALinearFunction(torch.autograd.Function):
             bias = bias.to(x.dtype).contiguous()
         y = torch.empty((T, N), dtype=x.dtype, device=dev)
         t_save = torch.empty((T, LORA_LD), dtype=x.dtype, device=dev) if r else None
+        ws, ws_bytes = _workspace(_cabi.OP_FWD, T, N, K, r, dev)
         with torch.cuda.device(dev):
             check(
                 lib.vft_qlora_fwd(
                     x2.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, blocksize, act, dtype_code(qdtype),
-                    _ptr(bias), _ptr(lora_a), _ptr(lora_b), r, float(scale), y.data_ptr(), _ptr(t_save), None, 0,
+                    _ptr(bias), _ptr(lora_a), _ptr(lora_b), r, float(scale), y.data_ptr(), _ptr(t_save), _ptr(ws), ws_bytes,
                     _ptr(codes_t), _ptr(absmax_t), _stream(),
                 )
             )
@@ -178,10 +187,11 @@ class QLoRALinearFunction(torch.autograd.Function):
         da = db = None
         with torch.cuda.device(dev):
             if need_dx or need_ab:
+                ws, ws_bytes = _workspace(_cabi.OP_BWD_DX, T, N, K, r, dev) if need_dx else (None, 0)
                 check(
                     lib.vft_qlora_bwd_dx(
                         dy2.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, blocksize, act, qd,
-                        _ptr(lora_a), _ptr(lora_b), r, scale, _ptr(dx), _ptr(dt_save), None, 0,
+                        _ptr(lora_a), _ptr(lora_b), r, scale, _ptr(dx), _ptr(dt_save), _ptr(ws), ws_bytes,
                         _ptr(codes_t), _ptr(absmax_t), _stream(),
                     )
                 )
