@@ -142,6 +142,8 @@ lora_side_kernel(const __grid_constant__ CUtensorMap map_m0, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem_d = *tmem_slot_gen;
   if (threadIdx.x == 0) side_mark(pp.debug, 1);
+  ptx::griddep_launch_dependents();  // programmatic dependent launch: see qlora_tc2.cu
+  ptx::griddep_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
@@ -329,13 +331,15 @@ static int launch_side(const CUtensorMap& m0, const CUtensorMap& v0, const CUten
   lc.blockDim = dim3(kSideThreads);
   lc.dynamicSmemBytes = kSideDyn;
   lc.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = (unsigned)split;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
-  lc.numAttrs = 1;
+  lc.numAttrs = pdl_enabled() ? 2 : 1;
   VFT_CUDA_OK(cudaLaunchKernelEx(&lc, kern, m0, v0, m1, v1, pp));
   VFT_CUDA_OK(cudaGetLastError());
   return VFT_OK;

@@ -290,6 +290,13 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// launch_dependents: the next kernel in the stream (launched with programmaticStreamSerialization) may start its
+// prologue as soon as this grid's CTAs free their resources; wait: block until the previous grid has completed and
+// its memory is visible.  Everything before the wait must not touch data the previous kernel produces.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ register re-allocation between warpgroups
 template <int kRegs>
 __device__ __forceinline__ void setmaxnreg_inc() {

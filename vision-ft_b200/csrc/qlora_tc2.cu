@@ -183,6 +183,10 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   ptx::cluster_sync();  // barrier inits of both CTAs visible before any remote arrive / multicast commit
   ptx::tc_fence_after();
   const uint32_t tmem_d = *tmem_slot_gen;
+  // programmatic dependent launch: everything above (barriers, TMEM, tensor-map fetch) overlapped the tail of the
+  // previous kernel; from here on activations / saved adapter products of that kernel are read and outputs written
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
 
   // Register budget: 768 threads start with 80 registers each.  The control warpgroup (warps 20-23) gives most of
   // its share back so that the four decode warpgroups can hold a fully decoded block (32 registers) while they
@@ -728,13 +732,15 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
   lc.blockDim = dim3(kThreads);
   lc.dynamicSmemBytes = (size_t)dyn_bytes;
   lc.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
-  lc.numAttrs = 1;
+  lc.numAttrs = pdl_enabled() ? 2 : 1;
   VFT_CUDA_OK(cudaLaunchKernelEx(&lc, kern, map_act, map_lora, map_out, p));
   VFT_CUDA_OK(cudaGetLastError());
   if (p.n_split > 1) {

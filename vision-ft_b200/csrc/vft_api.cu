@@ -51,6 +51,11 @@ static bool use_tc(const LayerArgs& a, bool backward, int* status) {
   return ok;
 }
 
+bool pdl_enabled() {
+  const char* e = getenv("VFT_PDL");
+  return !(e && e[0] == '0');
+}
+
 // triage switch: VFT_SIDE_MMA=1 keeps the mma.sync adapter kernels (lora_mma.cu) instead of lora_tc.cu
 static bool side_mma() {
   const char* e = getenv("VFT_SIDE_MMA");

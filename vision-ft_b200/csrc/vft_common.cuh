@@ -89,6 +89,9 @@ __device__ __forceinline__ float round_through(float v, int qdtype) {
 
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// programmatic dependent launch of the fused kernels (VFT_PDL=0 switches it off for triage)
+bool pdl_enabled();
+
 // ---------------------------------------------------------------------------
 // launchers implemented across the .cu files (all return vft_status)
 // ---------------------------------------------------------------------------
