@@ -49,6 +49,7 @@ constexpr int kDecWarp0 = 0;                    // warps 0..15: decode
 constexpr int kEpiWarp0 = 4 * kGroups;          // warps 16..19: epilogue (warp % 4 = TMEM lane quadrant)
 constexpr int kTmaWarp = kEpiWarp0 + 4;         // warp 20: TMA producer
 constexpr int kAllocWarp = kEpiWarp0 + 5;       // warp 21: TMEM allocation
+constexpr int kStoreWarp = kEpiWarp0 + 6;       // warp 22: issues the TMA stores of the staged output tiles
 constexpr int kMmaWarp = kEpiWarp0 + 7;         // warp 23: MMA issuer
 constexpr int kThreads = (kEpiWarp0 + 8) * 32;  // 768
 // registers per thread after the role split (launch: 80 x 768): 4 x 128 x (88 - 80) <= 128 x (80 - 40) + 128 x (80 - 72)
@@ -70,8 +71,10 @@ struct AccLayout {
 };
 constexpr int kTmemCols = 512;
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kBarBytes = (2 * kMaxStages + 1 + kMaxAcc) * 8 + 16;
-constexpr int kEpiBytes = 2 * 32 * kBM * 2;  // two staging tiles [32 tokens][128 features] of 16-bit outputs
+constexpr int kMaxStg = 16;  // output staging tiles
+constexpr int kBarBytes = (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg) * 8 + 16;
+constexpr int kStgBytes = 32 * kBM * 2;  // one staging tile [32 tokens][128 features] of 16-bit outputs (8 KB)
+constexpr int kEpiBytes = 2 * kStgBytes;  // the minimum: two tiles
 
 struct Tc2Params {
   int64_t T, N, K;
@@ -86,6 +89,8 @@ struct Tc2Params {
   void* out;           // forward: Y [T, N]; backward: dX [T, K]
   int n_acc, N_acc;    // accumulators per tile, tokens per accumulator (multiple of 16, <= 256)
   int stages;
+  int n_stg;        // output staging tiles (2..16): as many as fit, so that the accumulators drain at the epilogue
+                    // warps' speed while the TMA stores trickle out under the next tile's main loop
   int b_bytes;      // bytes of one accumulator's activation box in one CTA: (N_acc / 2) * 128
   int stage_bytes;  // (backward: kATileBytes +) n_acc * b_bytes
   int n_fblk;       // feature blocks of 256
@@ -138,14 +143,18 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   const int tok_tile = p.n_acc * p.N_acc;
 
   // shared memory: [S stages: decoded weight tile | n_acc activation boxes][epilogue staging][barriers, TMEM slot]
-  const uint32_t bar_base = smem_base + (uint32_t)(S * p.stage_bytes + kEpiBytes);
+  const int epi_bytes = p.n_stg * kStgBytes;
+  const uint32_t bar_base = smem_base + (uint32_t)(S * p.stage_bytes + epi_bytes);
   auto bar_full = [&](int s) { return bar_base + 8u * s; };
   auto bar_empty = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   const uint32_t bar_acc_full = bar_base + 8u * (2 * kMaxStages);
   auto bar_acc_empty = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 1 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc);
-  volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + S * p.stage_bytes + kEpiBytes + 8 * (2 * kMaxStages + 1 + kMaxAcc));
+  // output staging tiles: full[b] (the four epilogue warps have written tile b) / empty[b] (its TMA store has read it)
+  auto bar_stg_full = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc + b); };
+  auto bar_stg_empty = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc + kMaxStg + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + S * p.stage_bytes + epi_bytes + 8 * (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg));
   auto stage_a = [&](int s) { return smem_base + (uint32_t)(s * p.stage_bytes); };
   auto stage_b = [&](int s, int a) { return smem_base + (uint32_t)(s * p.stage_bytes + kAOff + a * p.b_bytes); };
   // accumulators of a tile that hold at least one real token (all roles derive it the same way)
@@ -176,6 +185,10 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     }
     ptx::mbar_init(bar_acc_full, 1);
     for (int a = 0; a < kMaxAcc; ++a) ptx::mbar_init(bar_acc_empty(a), 2 * 4);  // epilogue warps of both CTAs
+    for (int b = 0; b < p.n_stg; ++b) {
+      ptx::mbar_init(bar_stg_full(b), 4);   // one arrive per epilogue warp
+      ptx::mbar_init(bar_stg_empty(b), 1);  // the store-issuing thread
+    }
     ptx::fence_mbar_init();
   }
   if (warp == kAllocWarp) ptx::tmem_alloc_pair<kTmemCols>(tmem_slot);
@@ -300,6 +313,43 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         acc_par ^= 1u;
       }
     }
+  } else if (warp == kStoreWarp) {
+    // ------------------------------------------------------------- output store issuer
+    // Issuing a TMA store costs one thread ~350 cycles; done by an epilogue thread it sat on the critical path of
+    // every 32-token chunk.  This warp mirrors the epilogue's chunk sequence and does nothing but wait for a staged
+    // tile, hand it to the TMA engine and release it once the engine has read it.
+    if (p.n_split == 1 && ptx::elect_one()) {
+      const uint32_t stg = bar_base - (uint32_t)epi_bytes;
+      uint32_t chunk = 0, sb = 0, sphase = 0;  // staging tile of this chunk and its use parity
+      for (int item = pair; item < n_items; item += n_pairs) {
+        const int tile = item_tile(item);
+        const int64_t t0 = (int64_t)(tile / p.n_fblk) * tok_tile;
+        const int na = accs_of(t0);
+        const int64_t feat0 = (int64_t)(tile % p.n_fblk) * (2 * kBM) + (int64_t)rank * kBM;
+        for (int a = 0; a < na; ++a) {
+          const int64_t ta = t0 + (int64_t)a * p.N_acc;
+          for (int c0 = 0; c0 < p.N_acc && ta + c0 < p.T; c0 += 32, ++chunk) {
+            const uint32_t b = sb;
+            ptx::mbar_wait(bar_stg_full(b), sphase);
+            if (feat0 < OUT && !(p.debug & 4)) {
+              const uint32_t src = stg + b * (uint32_t)kStgBytes;
+              ptx::tma_store_2d(&map_out, src, (int)feat0, (int)(ta + c0));
+              if (c0 + 16 < p.N_acc) ptx::tma_store_2d(&map_out, src + 16u * 256u, (int)feat0, (int)(ta + c0 + 16));
+            }
+            ptx::bulk_commit_group();
+            if (chunk >= 1) {  // the group committed one chunk ago has finished reading ITS tile
+              ptx::bulk_wait_group_read<1>();
+              ptx::mbar_arrive(bar_stg_empty(b == 0 ? (uint32_t)p.n_stg - 1u : b - 1u));
+            }
+            if (++sb == (uint32_t)p.n_stg) {
+              sb = 0;
+              sphase ^= 1u;
+            }
+          }
+        }
+      }
+      ptx::bulk_wait_group<0>();  // all output rows written before the CTA retires
+    }
   }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------- epilogue warps
@@ -312,8 +362,8 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int et = (warp - kEpiWarp0) * 32 + lane;
     const uint32_t lane_base = tmem_d + ((uint32_t)(quad * 32) << 16);
-    const uint32_t epi_smem = bar_base - (uint32_t)kEpiBytes + (uint32_t)(quad * 32 + lane) * 2u;
-    uint32_t it = 0, chunk = 0;
+    const uint32_t epi_smem = bar_base - (uint32_t)epi_bytes + (uint32_t)(quad * 32 + lane) * 2u;
+    uint32_t it = 0, sb = 0, sphase = 1;  // staging tile of the next live chunk; parity of its "empty" wait
     for (int item = pair; item < n_items; item += n_pairs, ++it) {
       const int tile = item_tile(item);
       const int64_t t0 = (int64_t)(tile / p.n_fblk) * tok_tile;
@@ -351,7 +401,8 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             }
             continue;
           }
-          const uint32_t buf = epi_smem + (chunk & 1u) * (uint32_t)(kEpiBytes / 2);
+          const uint32_t buf = epi_smem + sb * (uint32_t)kStgBytes;
+          ptx::mbar_wait(bar_stg_empty(sb), sphase);  // the tile's previous store has read it
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             const uint32_t pk = pack2<ActT>(__uint_as_float(v[j]) + bias_v, __uint_as_float(v[j + 1]) + bias_v);
@@ -359,17 +410,12 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             ptx::sts16(buf + (uint32_t)(j + 1) * 256u, pk >> 16);
           }
           ptx::fence_proxy_async_smem();
-          // the store issued one chunk ago (other staging tile) has finished READING by the time this thread
-          // reaches the barrier, so after the barrier everyone may overwrite that tile for chunk c + 1
-          if (et == 0) ptx::bulk_wait_group_read<0>();
-          ptx::named_bar_sync(1, 128);
-          if (et == 0 && feat0 < OUT && !(p.debug & 4)) {
-            const uint32_t src = buf - (uint32_t)(quad * 32 + lane) * 2u;
-            ptx::tma_store_2d(&map_out, src, (int)feat0, (int)(ta + c0));
-            if (c0 + 16 < p.N_acc) ptx::tma_store_2d(&map_out, src + 16u * 256u, (int)feat0, (int)(ta + c0 + 16));
-            ptx::bulk_commit_group();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_stg_full(sb));  // the store warp takes it from here
+          if (++sb == (uint32_t)p.n_stg) {  // live chunks walk round the staging tiles
+            sb = 0;
+            sphase ^= 1u;
           }
-          ++chunk;  // live chunks alternate between the two staging tiles
         }
       }
       if (et == 0) tl_mark(p, 4, 2 * (int)it + 1);
@@ -377,7 +423,6 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar_acc_empty(a), 0));
       }
     }
-    if (et == 0) ptx::bulk_wait_group<0>();  // all output rows written before the CTA retires
   } else {
     // ------------------------------------------------------------- decode warps
     ptx::setmaxnreg_inc<kDecRegs>();
@@ -571,6 +616,14 @@ static int max_stages(bool tmem_a, int n_acc, int N_acc) {
   int stages = (kSmemLimit - kBarBytes - kEpiBytes - 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (tmem_a && stages > kTmemAStages) stages = kTmemAStages;  // the weight ring in tensor memory has 4 slots
+  // four stages (one per decode group) keep the tensor pipe fed; shared memory beyond that is worth more as output
+  // staging (see n_stg), which shortens the accumulator drain at tile boundaries
+  if (const char* e = getenv("VFT_TC2_MAXSTAGES")) {
+    const int v = atoi(e);
+    if (v >= kGroups && stages > v) stages = v;
+  } else if (stages > kGroups) {
+    stages = kGroups;
+  }
   return stages;
 }
 
@@ -718,7 +771,14 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
     map_lora = map_act;
   }
 
-  const int dyn_bytes = cfg.stages * p.stage_bytes + kEpiBytes + kBarBytes + 1024;  // + slack to align the base to 1024 B
+  // output staging tiles from what the ring leaves over (a whole tile of 2 x 176 tokens is 11 of them)
+  p.n_stg = (kSmemLimit - kBarBytes - 1024 - cfg.stages * p.stage_bytes) / kStgBytes;
+  if (p.n_stg > kMaxStg) p.n_stg = kMaxStg;
+  if (const char* e = getenv("VFT_TC2_NSTG")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= p.n_stg) p.n_stg = v;
+  }
+  const int dyn_bytes = cfg.stages * p.stage_bytes + p.n_stg * kStgBytes + kBarBytes + 1024;  // + 1024-B alignment slack
   auto kern = qlora_tc2_kernel<ActT, kBackward>;
   VFT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_bytes));
   // the fewest pairs that still finish in the same number of waves (T = 4096, 3072 features: 144 tiles -> 72 pairs
