@@ -122,7 +122,8 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
 template <typename ActT, bool kBackward>
 __global__ void __launch_bounds__(kThreads, 1)
 qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_lora,
-                 const __grid_constant__ CUtensorMap map_out, const Tc2Params p) {
+                 const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out16,
+                 const Tc2Params p) {
   constexpr bool kTmemA = !kBackward;  // forward: decoded weights go to tensor memory, backward: shared memory
   constexpr int kAccCols = AccLayout<kTmemA>::pitch;
   constexpr int kAOff = kTmemA ? 0 : kATileBytes;  // offset of the activation boxes inside a stage
@@ -177,6 +178,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     ptx::tma_prefetch_desc(&map_act);
     if (p.r > 0) ptx::tma_prefetch_desc(&map_lora);
     ptx::tma_prefetch_desc(&map_out);
+    ptx::tma_prefetch_desc(&map_out16);
   }
   if (warp == kMmaWarp && ptx::elect_one()) {
     for (int s = 0; s < S; ++s) {
@@ -332,9 +334,12 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             const uint32_t b = sb;
             ptx::mbar_wait(bar_stg_full(b), sphase);
             if (feat0 < OUT && !(p.debug & 4)) {
+              // the staged tile is two halves [32 tokens][64 features] (128-byte rows, SWIZZLE_128B); a chunk cut
+              // short by N_acc (a multiple of 16) leaves through the 16-token boxes
               const uint32_t src = stg + b * (uint32_t)kStgBytes;
-              ptx::tma_store_2d(&map_out, src, (int)feat0, (int)(ta + c0));
-              if (c0 + 16 < p.N_acc) ptx::tma_store_2d(&map_out, src + 16u * 256u, (int)feat0, (int)(ta + c0 + 16));
+              const CUtensorMap* m = (c0 + 32 <= p.N_acc) ? &map_out : &map_out16;
+              ptx::tma_store_2d(m, src, (int)feat0, (int)(ta + c0));
+              if (feat0 + 64 < OUT) ptx::tma_store_2d(m, src + 4096u, (int)feat0 + 64, (int)(ta + c0));
             }
             ptx::bulk_commit_group();
             if (chunk >= 1) {  // the group committed one chunk ago has finished reading ITS tile
@@ -362,16 +367,27 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int et = (warp - kEpiWarp0) * 32 + lane;
     const uint32_t lane_base = tmem_d + ((uint32_t)(quad * 32) << 16);
-    const uint32_t epi_smem = bar_base - (uint32_t)epi_bytes + (uint32_t)(quad * 32 + lane) * 2u;
+    // stmatrix row address of this thread inside a staging tile: matrix k = lane / 8 (features 8k..8k+7 of the
+    // quadrant's 32), row i = lane % 8 (token 8q + i); half (quad / 2), 16-byte chunk (quad % 2) * 4 + k of the
+    // 128-byte row, XOR-swizzled with the token (SWIZZLE_128B, matching the store's tensor map)
+    const int sm_k = lane >> 3, sm_i = lane & 7;
+    const uint32_t st_off = (uint32_t)((quad >> 1) * 4096 + sm_i * 128 + ((((quad & 1) * 4 + sm_k) ^ sm_i) << 4));
+    const uint32_t epi_smem = bar_base - (uint32_t)epi_bytes + st_off;
     uint32_t it = 0, sb = 0, sphase = 1;  // staging tile of the next live chunk; parity of its "empty" wait
     for (int item = pair; item < n_items; item += n_pairs, ++it) {
       const int tile = item_tile(item);
       const int64_t t0 = (int64_t)(tile / p.n_fblk) * tok_tile;
       const int na = accs_of(t0);
       const int64_t feat0 = (int64_t)(tile % p.n_fblk) * (2 * kBM) + (int64_t)rank * kBM;
-      const int64_t feat = feat0 + quad * 32 + lane;
-      float bias_v = 0.0f;
-      if (!kBackward && p.bias != nullptr && feat < OUT) bias_v = to_f32<ActT>(static_cast<const ActT*>(p.bias)[feat]);
+      // bias of the four feature rows this thread holds fragments of: quadrant base + lane / 4 + {0, 8, 16, 24}
+      float bias_v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if (!kBackward && p.bias != nullptr) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t f = feat0 + quad * 32 + (lane >> 2) + 8 * u;
+          if (f < OUT) bias_v[u] = to_f32<ActT>(static_cast<const ActT*>(p.bias)[f]);
+        }
+      }
       ptx::mbar_wait(bar_acc_full, it & 1u);
       ptx::tc_fence_after();
       if (et == 0) tl_mark(p, 4, 2 * (int)it);
@@ -380,9 +396,11 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
 #pragma unroll 1
         for (int c0 = 0; c0 < p.N_acc; c0 += 32) {
           const bool live = ta + c0 < p.T;  // warp-uniform; dead chunks still release the accumulator below
-          uint32_t v[32];
+          // 16x256b: mma-style fragments -- r[4q], r[4q+1] = (lane t/4, tokens 8q + 2(t%4), +1); r[4q+2], r[4q+3] = lane + 8
+          uint32_t v0[16], v1[16];  // lanes 0..15 / 16..31 of the quadrant, 32 token columns
           if (live) {
-            ptx::tmem_ld_32x32b_x32(lane_base + (uint32_t)(a * kAccCols + c0), v);
+            ptx::tmem_ld_16x256b_x4(lane_base + (uint32_t)(a * kAccCols + c0), v0);
+            ptx::tmem_ld_16x256b_x4(lane_base + (16u << 16) + (uint32_t)(a * kAccCols + c0), v1);
             ptx::tmem_ld_wait();
           }
           if (c0 + 32 >= p.N_acc) {  // accumulator a is in registers / not needed: the issuer may overwrite it
@@ -391,12 +409,20 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar_acc_empty(a), 0));
           }
           if (!live) continue;
-          if (p.n_split > 1) {  // split-K: add the fp32 partial tile to the workspace (32 consecutive floats per token)
-            if (feat < OUT && !(p.debug & 4)) {
+          if (p.n_split > 1) {  // split-K: add the fp32 partial tile to the workspace
+            if (!(p.debug & 4)) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int64_t t = ta + c0 + j;
-                if (c0 + j < p.N_acc && t < p.T) atomicAdd(p.partial + t * OUT + feat, __uint_as_float(v[j]));
+              for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int64_t t = ta + c0 + 8 * q + 2 * (lane & 3) + (e & 1);
+                  const int col = c0 + 8 * q + 2 * (lane & 3) + (e & 1);
+                  const int64_t f_lo = feat0 + quad * 32 + (lane >> 2) + ((e >> 1) ? 8 : 0);
+                  if (col < p.N_acc && t < p.T) {
+                    if (f_lo < OUT) atomicAdd(p.partial + t * OUT + f_lo, __uint_as_float(v0[4 * q + e]));
+                    if (f_lo + 16 < OUT) atomicAdd(p.partial + t * OUT + f_lo + 16, __uint_as_float(v1[4 * q + e]));
+                  }
+                }
               }
             }
             continue;
@@ -404,10 +430,12 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
           const uint32_t buf = epi_smem + sb * (uint32_t)kStgBytes;
           ptx::mbar_wait(bar_stg_empty(sb), sphase);  // the tile's previous store has read it
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const uint32_t pk = pack2<ActT>(__uint_as_float(v[j]) + bias_v, __uint_as_float(v[j + 1]) + bias_v);
-            ptx::sts16(buf + (uint32_t)j * 256u, pk);
-            ptx::sts16(buf + (uint32_t)(j + 1) * 256u, pk >> 16);
+          for (int q = 0; q < 4; ++q) {  // tokens 8q..8q+7: four 8x8 matrices = feature groups 0-7, 8-15, 16-23, 24-31
+            const uint32_t m0 = pack2<ActT>(__uint_as_float(v0[4 * q]) + bias_v[0], __uint_as_float(v0[4 * q + 1]) + bias_v[0]);
+            const uint32_t m1 = pack2<ActT>(__uint_as_float(v0[4 * q + 2]) + bias_v[1], __uint_as_float(v0[4 * q + 3]) + bias_v[1]);
+            const uint32_t m2 = pack2<ActT>(__uint_as_float(v1[4 * q]) + bias_v[2], __uint_as_float(v1[4 * q + 1]) + bias_v[2]);
+            const uint32_t m3 = pack2<ActT>(__uint_as_float(v1[4 * q + 2]) + bias_v[3], __uint_as_float(v1[4 * q + 3]) + bias_v[3]);
+            ptx::stmatrix_x4_trans(buf + (uint32_t)(q * 1024), m0, m1, m2, m3);
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
@@ -756,12 +784,14 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
 
   const CUtensorMapDataType dt =
       std::is_same<ActT, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  CUtensorMap map_act, map_lora, map_out;
+  CUtensorMap map_act, map_lora, map_out, map_out16;
   int rc = make_map_2d(&map_act, dt, act, (uint64_t)RED, (uint64_t)a.T, (uint64_t)RED * 2, kBK, cfg.N_acc / 2,
                        CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != VFT_OK) return rc;
-  // output rows leave through TMA stores of [16 tokens x 128 features] boxes (clipped at T / OUT)
-  rc = make_map_2d(&map_out, dt, out, (uint64_t)OUT, (uint64_t)a.T, (uint64_t)OUT * 2, kBM, 16, CU_TENSOR_MAP_SWIZZLE_NONE);
+  // output rows leave through TMA stores of [32 (or 16) tokens x 64 features] boxes, clipped at T / OUT
+  rc = make_map_2d(&map_out, dt, out, (uint64_t)OUT, (uint64_t)a.T, (uint64_t)OUT * 2, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != VFT_OK) return rc;
+  rc = make_map_2d(&map_out16, dt, out, (uint64_t)OUT, (uint64_t)a.T, (uint64_t)OUT * 2, 64, 16, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != VFT_OK) return rc;
   if (a.r > 0) {
     rc = make_map_2d(&map_lora, dt, lora_act, VFT_LORA_LD, (uint64_t)a.T, VFT_LORA_LD * 2, kBK, cfg.N_acc / 2,
@@ -801,7 +831,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
   lc.numAttrs = pdl_enabled() ? 2 : 1;
-  VFT_CUDA_OK(cudaLaunchKernelEx(&lc, kern, map_act, map_lora, map_out, p));
+  VFT_CUDA_OK(cudaLaunchKernelEx(&lc, kern, map_act, map_lora, map_out, map_out16, p));
   VFT_CUDA_OK(cudaGetLastError());
   if (p.n_split > 1) {
     const int64_t total8 = a.T * OUT / 8;
