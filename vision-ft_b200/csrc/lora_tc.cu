@@ -300,19 +300,44 @@ lora_side_kernel(const __grid_constant__ CUtensorMap map_m0, const __grid_consta
 // ---------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------
-// Cluster size along the contraction: the largest of 4 / 2 / 1 whose clusters all fit in ONE wave (1 CTA per SM:
-// 197 KB of shared memory).  Measured cluster capacity on B200: size 2 packs all 74 SM pairs, size 4 places 33
-// clusters (GPC sizes strand 16 SMs), size 8 only 15, size 3 fewer than 48; the rank-0 reduction is also serial in
-// the cluster size.
-static int pick_split(int64_t tiles, int64_t n_steps, int n_sm) {
+// Cluster size along the contraction: the largest S <= 4 whose clusters all fit in ONE wave (1 CTA per SM: 197 KB
+// of shared memory), asked from the occupancy API once per kernel and size (size 2 packs all 74 SM pairs of a B200,
+// size 4 places 33 clusters -- GPC sizes strand 16 SMs --, size 8 only 15); the rank-0 reduction is serial in S.
+template <typename Kern>
+static int max_active_clusters(Kern kern, int split) {
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(1, (unsigned)split);
+  lc.blockDim = dim3(kSideThreads);
+  lc.dynamicSmemBytes = kSideDyn;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = (unsigned)split;
+  attr[0].val.clusterDim.z = 1;
+  lc.attrs = attr;
+  lc.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &lc) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+template <typename Kern>
+static int pick_split(Kern kern, int64_t tiles, int64_t n_steps, int n_sm) {
   if (const char* e = getenv("VFT_SIDE_SPLIT")) {  // triage override
     const int s = atoi(e);
     if (s >= 1 && s <= kMaxSplit) return s <= n_steps ? s : 1;
   }
-  int split = 1;
-  if (tiles * 2 <= n_sm && n_steps >= 2) split = 2;
-  if (tiles * 4 <= (n_sm * 33 * 4) / 148 && n_steps >= 4) split = 4;
-  return split;
+  static int cap[5] = {0, -1, -1, -1, -1};  // per kernel instantiation: clusters of size S that fit at once
+  for (int s = 4; s >= 2; --s) {
+    if (s > n_steps) continue;
+    if (cap[s] < 0) cap[s] = max_active_clusters(kern, s);
+    if (tiles <= cap[s]) return s;
+  }
+  (void)n_sm;
+  return 1;
 }
 
 static int sm_count() {
@@ -323,9 +348,10 @@ static int sm_count() {
 
 template <typename ActT, int kMode, int RP>
 static int launch_side(const CUtensorMap& m0, const CUtensorMap& v0, const CUtensorMap& m1, const CUtensorMap& v1,
-                       const SidePair& pp, int64_t tiles, int split, cudaStream_t st) {
+                       const SidePair& pp, int64_t tiles, int64_t n_steps, cudaStream_t st) {
   auto kern = lora_side_kernel<ActT, kMode, RP>;
   VFT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSideDyn));
+  const int split = pick_split(kern, tiles, n_steps, sm_count());
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)tiles, (unsigned)split);
   lc.blockDim = dim3(kSideThreads);
@@ -352,10 +378,10 @@ static CUtensorMapDataType tm_dtype() {
 
 template <typename ActT, int kMode>
 static int launch_side_rank(const CUtensorMap& m0, const CUtensorMap& v0, const CUtensorMap& m1, const CUtensorMap& v1,
-                            const SidePair& pp, int64_t tiles, int split, int r, cudaStream_t st) {
-  if (r <= 16) return launch_side<ActT, kMode, 16>(m0, v0, m1, v1, pp, tiles, split, st);
-  if (r <= 32) return launch_side<ActT, kMode, 32>(m0, v0, m1, v1, pp, tiles, split, st);
-  return launch_side<ActT, kMode, 64>(m0, v0, m1, v1, pp, tiles, split, st);
+                            const SidePair& pp, int64_t tiles, int64_t n_steps, int r, cudaStream_t st) {
+  if (r <= 16) return launch_side<ActT, kMode, 16>(m0, v0, m1, v1, pp, tiles, n_steps, st);
+  if (r <= 32) return launch_side<ActT, kMode, 32>(m0, v0, m1, v1, pp, tiles, n_steps, st);
+  return launch_side<ActT, kMode, 64>(m0, v0, m1, v1, pp, tiles, n_steps, st);
 }
 
 template <typename ActT, int kMode>
@@ -378,8 +404,7 @@ static int rowproj_tc(const void* M, const void* V, int64_t T, int64_t C, int r,
   pp.tiles_first = 0x7fffffff;
   pp.debug = getenv("VFT_TC_DEBUG") ? atoi(getenv("VFT_TC_DEBUG")) : 0;
   const int64_t tiles = ceil_div64(T, kTile);
-  return launch_side_rank<ActT, kMode>(mm, mv, mm, mv, pp, tiles, pick_split(tiles, ceil_div64(C, kStep), sm_count()),
-                                       r, st);
+  return launch_side_rank<ActT, kMode>(mm, mv, mm, mv, pp, tiles, ceil_div64(C, kStep), r, st);
 }
 
 template <typename ActT>
@@ -404,8 +429,7 @@ static int dab_tc(const void* dy, const void* x, const void* t_save, const void*
   pp.tiles_first = (int)ceil_div64(K, kTile);
   pp.debug = getenv("VFT_TC_DEBUG") ? atoi(getenv("VFT_TC_DEBUG")) : 0;
   const int64_t tiles = ceil_div64(K, kTile) + ceil_div64(N, kTile);
-  return launch_side_rank<ActT, kCol>(mx, mdt, mdy, mt, pp, tiles, pick_split(tiles, ceil_div64(T, kStep), sm_count()),
-                                      r, st);
+  return launch_side_rank<ActT, kCol>(mx, mdt, mdy, mt, pp, tiles, ceil_div64(T, kStep), r, st);
 }
 
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
