@@ -199,9 +199,10 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   ptx::tc_fence_after();
   const uint32_t tmem_d = *tmem_slot_gen;
   // programmatic dependent launch: everything above (barriers, TMEM, tensor-map fetch) overlapped the tail of the
-  // previous kernel; from here on activations / saved adapter products of that kernel are read and outputs written
+  // previous kernel.  Each role waits for that kernel itself, as late as it can: the decode warps first put the
+  // loads of their first weight block in flight (frozen weights: no dependency), the MMA issuer touches no global
+  // memory at all.
   ptx::griddep_launch_dependents();
-  ptx::griddep_wait();
 
   // Register budget: 768 threads start with 80 registers each.  The control warpgroup (warps 20-23) gives most of
   // its share back so that the four decode warpgroups can hold a fully decoded block (32 registers) while they
@@ -213,6 +214,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------- TMA producer (activations)
     if (ptx::elect_one()) {
+      ptx::griddep_wait();  // activations / saved adapter products come from the previous kernels
       int g = 0, s = 0;
       uint32_t empty_par = 1;
       for (int item = pair; item < n_items; item += n_pairs) {
@@ -321,6 +323,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     // every 32-token chunk.  This warp mirrors the epilogue's chunk sequence and does nothing but wait for a staged
     // tile, hand it to the TMA engine and release it once the engine has read it.
     if (p.n_split == 1 && ptx::elect_one()) {
+      ptx::griddep_wait();  // the output buffer may still be read by the previous kernel
       const uint32_t stg = bar_base - (uint32_t)epi_bytes;
       uint32_t chunk = 0, sb = 0, sphase = 0;  // staging tile of this chunk and its use parity
       for (int item = pair; item < n_items; item += n_pairs) {
@@ -374,6 +377,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     const uint32_t st_off = (uint32_t)((quad >> 1) * 4096 + sm_i * 128 + ((((quad & 1) * 4 + sm_k) ^ sm_i) << 4));
     const uint32_t epi_smem = bar_base - (uint32_t)epi_bytes + st_off;
     uint32_t it = 0, sb = 0, sphase = 1;  // staging tile of the next live chunk; parity of its "empty" wait
+    ptx::griddep_wait();  // bias / split-K workspace (zeroed by a memset node) / output ordering
     for (int item = pair; item < n_items; item += n_pairs, ++it) {
       const int tile = item_tile(item);
       const int64_t t0 = (int64_t)(tile / p.n_fblk) * tok_tile;
@@ -515,6 +519,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     Pos cur{(pair < n_items ? item_b0(pair) : 0) + group, pair};
     normalize(cur);
     prefetch(cur);
+    ptx::griddep_wait();  // the adapter weights read in the adapter step are written by the optimizer's kernels
     // forward: this thread's lane of the TMEM weight ring (warp % 4 = lane quadrant the warp may access)
     const uint32_t a_tmem_lane = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)kTmemACol0;
     int s = group;  // S >= kGroups: at most one ring wrap per step of kGroups
