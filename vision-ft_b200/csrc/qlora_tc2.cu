@@ -470,53 +470,67 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
                                          : (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
     const uint32_t a_xor = (uint32_t)(row & 7) << 4;
 
+    // Position in this pair's step sequence, with the per-item part of the weight addresses cached: the integer
+    // divisions (item -> tile -> feature block) run once per work item instead of once per 64-element block.
     struct Pos {
-      int b;     // ring step of the tile's contraction (n_main = the adapter step)
-      int item;  // work item (tile, split)
+      int b;             // ring step of the tile's contraction (n_main = the adapter step)
+      int item;          // work item (tile, split)
+      int b1;            // end of the item's step range
+      int64_t f0;        // first feature of this CTA's half of the tile (forward: out-feature n; backward: in-feature k)
+      const uint8_t* c;  // codes of this thread's block at step 0 (nullptr: outside the weight)
+      const float* a;    // its absmax
+    };
+    // per-step strides of the two pointers and the offset of the second 16 bytes of a 32-byte block
+    const int64_t c_step = p.tiled ? (kBackward ? (int64_t)KB * 2048 : 2048) : (kBackward ? 32 * p.K : 32);
+    const int64_t a_step = p.tiled ? (kBackward ? (int64_t)KB * 64 : 64) : (kBackward ? (int64_t)kBK * KB : 1);
+    const int c_second = p.tiled ? 1024 : 16;
+    auto enter_item = [&](Pos& q) {
+      q.b1 = 0;
+      q.c = nullptr;
+      q.a = nullptr;
+      q.f0 = 0;
+      if (q.item >= n_items) return;
+      q.b1 = item_b1(q.item);
+      q.f0 = (int64_t)(item_tile(q.item) % p.n_fblk) * (2 * kBM) + (int64_t)rank * kBM;
+      // element coordinates of this thread's quantization block at step 0 in W [N, K]
+      const int64_t wrow = kBackward ? row : q.f0 + row;
+      const int64_t wcol = kBackward ? q.f0 + half * 64 : 0;
+      if (kBackward ? (wcol >= p.K) : (wrow >= p.N)) return;
+      if (p.tiled) {  // 64 x 64 micro-tiles: the warp's 32 rows are contiguous (512 B per load, one line of absmax)
+        const int64_t mt = (wrow >> 6) * KB + (wcol >> 6);
+        q.c = p.packed + mt * 2048 + (wrow & 63) * 16;
+        q.a = p.absmax + mt * 64 + (wrow & 63);
+      } else {
+        q.c = p.packed + ((wrow * p.K + wcol) >> 1);
+        q.a = p.absmax + wrow * KB + (wcol >> 6);
+      }
     };
     auto normalize = [&](Pos& q) {  // carry an overflow past the item's last step into the pair's next item(s)
-      while (q.item < n_items && q.b >= item_b1(q.item)) {
-        const int over = q.b - item_b1(q.item);
+      while (q.item < n_items && q.b >= q.b1) {
+        const int over = q.b - q.b1;
         q.item += n_pairs;
+        enter_item(q);
         q.b = (q.item < n_items ? item_b0(q.item) : 0) + over;
       }
     };
-    // first feature of this CTA's half of the tile (forward: out-feature n; backward: in-feature k)
-    auto f0_of = [&](int tile) -> int64_t { return (int64_t)(tile % p.n_fblk) * (2 * kBM) + (int64_t)rank * kBM; };
 
     uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
     float am = 0.0f;
     auto prefetch = [&](const Pos& q) {
       q0 = q1 = make_uint4(0, 0, 0, 0);
       am = 0.0f;
-      if (q.item >= n_items || q.b >= n_main) return;
-      const int64_t f0 = f0_of(item_tile(q.item));
-      int64_t wrow, wcol;  // element coordinates of this thread's quantization block in W [N, K]
-      if (kBackward) {
-        wrow = (int64_t)q.b * kBK + row;
-        wcol = f0 + half * 64;
-        if (wrow >= p.N || wcol >= p.K) return;
-      } else {
-        wrow = f0 + row;
-        wcol = (int64_t)q.b * kBK;
-        if (wrow >= p.N) return;
-      }
-      if (p.tiled) {  // 64 x 64 micro-tiles: the warp's 32 rows are contiguous (512 B per load, one line of absmax)
-        const int64_t mt = (wrow >> 6) * KB + (wcol >> 6);
-        const int r = (int)(wrow & 63);
-        const uint8_t* c = p.packed + mt * 2048 + r * 16;
-        q0 = ldg_stream_u4(c);
-        q1 = ldg_stream_u4(c + 1024);
-        am = __ldg(p.absmax + mt * 64 + r);
-      } else {
-        const uint8_t* c = p.packed + ((wrow * p.K + wcol) >> 1);
-        q0 = ldg_stream_u4(c);
-        q1 = ldg_stream_u4(c + 16);
-        am = __ldg(p.absmax + wrow * KB + (wcol >> 6));
-      }
+      if (q.c == nullptr || q.b >= n_main) return;
+      if (kBackward && (int64_t)q.b * kBK + row >= p.N) return;
+      const uint8_t* c = q.c + q.b * c_step;
+      q0 = ldg_stream_u4(c);
+      q1 = ldg_stream_u4(c + c_second);
+      am = __ldg(q.a + q.b * a_step);
     };
 
-    Pos cur{(pair < n_items ? item_b0(pair) : 0) + group, pair};
+    Pos cur;
+    cur.item = pair;
+    enter_item(cur);
+    cur.b = (pair < n_items ? item_b0(pair) : 0) + group;
     normalize(cur);
     prefetch(cur);
     ptx::griddep_wait();  // the adapter weights read in the adapter step are written by the optimizer's kernels
@@ -526,7 +540,8 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     uint32_t empty_parity = 1;
     for (int g = group; cur.item < n_items; g += kGroups) {
       const uint32_t a_tile = stage_a(s) + a_row_off;
-      Pos nxt{cur.b + kGroups, cur.item};
+      Pos nxt = cur;
+      nxt.b += kGroups;
       normalize(nxt);
       uint32_t v[8][4];  // this thread's 64 decoded 16-bit values, in contraction order
       if (cur.b < n_main) {
@@ -541,7 +556,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       } else {
         // adapter step: forward row n of scale*B (r values), backward row j of A (64 in-features)
         const ActT* lw = static_cast<const ActT*>(p.lora_w);
-        const int64_t f0 = f0_of(item_tile(cur.item));
+        const int64_t f0 = cur.f0;
         prefetch(nxt);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
