@@ -166,6 +166,8 @@ CASES = [
     (1, 640, 640, 16, False, None),     # single token
     (528, 640, 5120, 16, True, None),   # SDXL ff.net.0.proj, C=640, ragged bucket
     (264, 3072, 384, 0, False, None),   # NF4-only (AuraFlow double-layer w1*, mlpC)
+    (2, 1024, 2048, 0, True, None),     # modulation-style layer, T = batch: split-K work items + fp32 workspace
+    (5, 1024, 2048, 8, True, None),     # the same with an adapter (its step belongs to the last split)
 ]
 
 
@@ -227,15 +229,16 @@ def test_fp16_checkpoint_bf16_activations(ops):
         _check(out, ref, truth, ("y", "dx", "da", "db"), f"fp16ckpt-p{path}")
 
 
-def test_fp16_activations(ops):
-    w, x, dy, a, b, bv = _make_case(130, 192, 128, 8, seed=11, dt=torch.float16)
+@pytest.mark.parametrize("T,K,N,r", [(130, 192, 128, 8), (600, 256, 512, 16)])  # one-tile kernel / pair kernel
+def test_fp16_activations(ops, T, K, N, r):
+    w, x, dy, a, b, bv = _make_case(T, K, N, r, seed=11, dt=torch.float16)
     x, dy = x * 0.5, dy * 0.5
     p, am = nf4_oracle.nf4_quantize(w)
-    w_deq = qlora_oracle.dequant_weight(p, am, (128, 192), "float16")
+    w_deq = qlora_oracle.dequant_weight(p, am, (N, K), "float16")
     truth = qlora_oracle.qlora_linear_truth(x, w_deq, None, a, b, 1.0, dy)
     for path in (TC, SIMT):
-        out, used = _run_cuda(ops, torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), x, dy, a, b, None, 1.0, 128,
-                              192, torch.float16, path)
+        out, used = _run_cuda(ops, torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), x, dy, a, b, None, 1.0, N,
+                              K, torch.float16, path, tiled=(path == TC))
         assert used == path
         for k in ("y", "dx", "da", "db"):
             assert qlora_oracle.rel_l2(out[k], truth[k]) <= 2e-3, (path, k)
