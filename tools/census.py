@@ -91,6 +91,23 @@ def time_layer(N, K, T, lora, bias, dev):
         out[name] = a.elapsed_time(b) / (3 * reps) * 1e3
     return out["fwd"], out["bwd"], L.vft_last_path()
 
+def model_step(layers, dev, verbose=None):
+    """Sum of (2 x forward + backward) over the NF4(+LoRA) Linear layers of one training step."""
+    tot_us = tot_fl = 0.0
+    cache, rows = {}, []
+    for nm, N, K, T, lora, bias, count in layers:
+        key = (N, K, T, lora, bias)
+        if key not in cache:
+            cache[key] = time_layer(N, K, T, lora, bias, dev)
+        f, b, _ = cache[key]
+        fl_f = 2 * T * N * K + (2 * T * R * (N + K) if lora else 0)
+        fl_b = 2 * T * N * K + (4 * T * R * (N + K) if lora else 0)
+        tot_us += (2 * f + b) * count
+        tot_fl += (2 * fl_f + fl_b) * count
+        rows.append((nm, N, K, T, lora, count, f, b, fl_f, fl_b))
+    return tot_us / 1e3, tot_fl / tot_us / 1e6, rows
+
+
 def main():
     dev = torch.device("cuda")
     models = {"auraflow_6.8B_B2_1024": auraflow(2), "lumina2_2.6B_B1_1024": lumina2(1), "sdxl_unet_B2_1024": sdxl(2)}
@@ -116,4 +133,5 @@ def main():
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(report, open(os.path.join(ROOT, "gpurun_out", "census.json"), "w"), indent=1)
 
-main()
+if __name__ == "__main__":
+    main()
