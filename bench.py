@@ -389,15 +389,16 @@ def run_gpu_arm(args):
         yk = torch.empty(T, N_FEAT, device=dev, dtype=torch.bfloat16)
         dxk = torch.empty(T, K_FEAT, device=dev, dtype=torch.bfloat16)
         st = torch.cuda.current_stream().cuda_stream
-        tiles = ops.nf4_tile_weight(w.data, qs.absmax, N_FEAT, K_FEAT)  # same derived copy the module path uses
+        absmax = qs.absmax_f32()
+        tiles = ops.nf4_tile_weight(w.data, absmax, N_FEAT, K_FEAT)  # same derived copy the module path uses
         tc_ptr, ta_ptr = (tiles[0].data_ptr(), tiles[1].data_ptr()) if tiles else (None, None)
 
         def k_fwd(i):
-            _cabi.check(_cabi.lib.vft_qlora_fwd(xk[i % n_sets].data_ptr(), T, w.data_ptr(), qs.absmax.data_ptr(), N_FEAT, K_FEAT, 64,
+            _cabi.check(_cabi.lib.vft_qlora_fwd(xk[i % n_sets].data_ptr(), T, w.data_ptr(), absmax.data_ptr(), N_FEAT, K_FEAT, 64,
                                                 _cabi.BF16, _cabi.BF16, None, None, None, 0, 0.0, yk.data_ptr(), None, None, 0, tc_ptr, ta_ptr, st))
 
         def k_bwd(i):
-            _cabi.check(_cabi.lib.vft_qlora_bwd_dx(gk[i % n_sets].data_ptr(), T, w.data_ptr(), qs.absmax.data_ptr(), N_FEAT, K_FEAT, 64,
+            _cabi.check(_cabi.lib.vft_qlora_bwd_dx(gk[i % n_sets].data_ptr(), T, w.data_ptr(), absmax.data_ptr(), N_FEAT, K_FEAT, 64,
                                                    _cabi.BF16, _cabi.BF16, None, None, 0, 0.0, dxk.data_ptr(), None, None, 0, tc_ptr, ta_ptr, st))
 
         def time_kernel(fn, iters=50):

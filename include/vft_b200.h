@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define VFT_ABI_VERSION 2
+#define VFT_ABI_VERSION 3
 #define VFT_LORA_LD 64 /* leading dimension (elements) of the saved LoRA activations t_save / dt_save */
 
 enum vft_dtype { VFT_F32 = 0, VFT_F16 = 1, VFT_BF16 = 2 };
@@ -55,7 +55,7 @@ enum vft_path {
   VFT_PATH_SIMT = 2     /* generic CUDA-core kernels: shapes the tensor path does not take */
 };
 
-enum vft_op { VFT_OP_FWD = 0, VFT_OP_BWD_DX = 1, VFT_OP_BWD_DAB = 2 };
+enum vft_op { VFT_OP_FWD = 0, VFT_OP_BWD_DX = 1, VFT_OP_BWD_DAB = 2, VFT_OP_ABSMAX_NEST = 3 };
 
 int vft_abi_version(void);
 const char* vft_last_error(void);
@@ -91,6 +91,25 @@ int vft_nf4_quantize_host(const void* w_host, int dtype, int64_t n, int blocksiz
 int64_t vft_nf4_tiled_bytes(int64_t N, int64_t K, int which);
 int vft_nf4_tile_weight(const uint8_t* packed, const float* absmax, int64_t N, int64_t K, int blocksize,
                         uint8_t* codes_t, float* absmax_t, void* stream);
+
+/* Nested ("double quant") block statistics.  Replaces the tail of bitsandbytes.functional.quantize_4bit(
+ * compress_statistics=True) -- offset = absmax.mean(); quantize_blockwise(absmax - offset, blocksize=256) with the
+ * 8-bit "dynamic" map -- which is the path Params4bit.cuda() takes under BnbLinear4bit's default
+ * (/root/reference/src/modules/quant/bnb.py:44,122-129; /root/reference/tools/quantize_model.py:33-54).
+ *   absmax   [nblocks] device fp32 in (16-byte aligned)      code256  [256] device fp32, ascending (the dynamic map)
+ *   absmax8  [nblocks] device uint8 out                      absmax2  [ceil(nblocks/256)] device fp32 out
+ *   offset   device fp32 scalar out = fp32(sum_fp64(absmax) / nblocks)
+ *   ws       vft_workspace_bytes(VFT_OP_ABSMAX_NEST, ...) bytes
+ * Bit-exact contract: v = absmax - offset (fp32); absmax2 = max|v| per 256; index = bitsandbytes' dQuantize
+ * bisection of v * (1.0f/absmax2) over code256 (nearest entry; a value exactly on a midpoint keeps the pivot). */
+int vft_absmax_nest(const float* absmax, int64_t nblocks, int blocksize2, const float* code256, uint8_t* absmax8,
+                    float* absmax2, float* offset, void* ws, int64_t ws_bytes, void* stream);
+
+/* Decode side: absmax_out[i] = code256[absmax8[i]] * absmax2[i / blocksize2] + offset (two fp32 roundings), i.e.
+ * bitsandbytes.functional.dequantize_blockwise(absmax8, state2) + offset -- what every dequantize_4bit of a nested
+ * checkpoint starts with (prequantized branch, /root/reference/src/modules/quant/bnb.py:91-107). */
+int vft_absmax_denest(const uint8_t* absmax8, const float* absmax2, const float* code256, float offset,
+                      int64_t nblocks, int blocksize2, float* absmax_out, void* stream);
 
 /* Scratch the caller must provide for an op (bytes; 0 is possible). */
 int64_t vft_workspace_bytes(int op, int64_t T, int64_t N, int64_t K, int r);

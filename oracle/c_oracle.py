@@ -25,7 +25,34 @@ def _lib():
     lib.nf4_quantize_ref.restype = ctypes.c_int
     lib.nf4_dequantize_ref.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
     lib.nf4_dequantize_ref.restype = ctypes.c_int
+    lib.absmax_nest_ref.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.absmax_nest_ref.restype = ctypes.c_int
+    lib.absmax_denest_ref.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
+    lib.absmax_denest_ref.restype = ctypes.c_int
     return lib
+
+
+def absmax_nest(absmax, code, blocksize2: int = 256):
+    """fp32 absmax -> (absmax8, absmax2, offset) through the C restatement."""
+    a = np.ascontiguousarray(absmax, dtype=np.float32).reshape(-1)
+    c = np.ascontiguousarray(code, dtype=np.float32)
+    n = a.size
+    q = np.zeros(n, np.uint8)
+    a2 = np.zeros((n + blocksize2 - 1) // blocksize2, np.float32)
+    off = np.zeros(1, np.float32)
+    rc = _lib().absmax_nest_ref(a.ctypes.data, n, blocksize2, c.ctypes.data, q.ctypes.data, a2.ctypes.data, off.ctypes.data)
+    assert rc == 0
+    return q, a2, off[0]
+
+
+def absmax_denest(q, absmax2, offset, code, blocksize2: int = 256):
+    q = np.ascontiguousarray(q, dtype=np.uint8).reshape(-1)
+    a2 = np.ascontiguousarray(absmax2, dtype=np.float32)
+    c = np.ascontiguousarray(code, dtype=np.float32)
+    out = np.zeros(q.size, np.float32)
+    rc = _lib().absmax_denest_ref(q.ctypes.data, a2.ctypes.data, c.ctypes.data, float(offset), q.size, blocksize2, out.ctypes.data)
+    assert rc == 0
+    return out
 
 
 def quantize(w_torch, blocksize: int = 64):

@@ -170,3 +170,148 @@ def unpack_quant_state_blob(blob) -> dict:
     if hasattr(blob, "detach"):
         blob = blob.detach().cpu().numpy()
     return json.loads(bytes(np.asarray(blob, dtype=np.uint8)).decode("utf-8"))
+
+
+# ---------------------------------------------------------------------------
+# Nested ("double quant") block statistics -- PARITY UNPINNED like the rest of this file.
+# bitsandbytes.functional.quantize_4bit(compress_statistics=True), the path Params4bit.cuda() takes under the
+# reference's default (/root/reference/src/modules/quant/bnb.py:44,122-129; tools/quantize_model.py:33-54):
+#     offset = absmax.mean(); absmax -= offset
+#     qabsmax, state2 = quantize_blockwise(absmax, blocksize=256)     # 8-bit "dynamic" map, kQuantizeBlockwise
+# and on the way back  absmax = dequantize_blockwise(qabsmax, state2) + offset.
+# ---------------------------------------------------------------------------
+NESTED_BLOCKSIZE = 256
+
+
+def dynamic_map(signed: bool = True, max_exponent_bits: int = 7, total_bits: int = 8) -> np.ndarray:
+    """bitsandbytes.functional.create_dynamic_map restated: the 256-entry ascending 8-bit code of the nested
+    statistics (``nested_quant_map`` in a checkpoint).  torch.linspace in fp32, like the original."""
+    import torch
+
+    data: list[float] = []
+    non_sign_bits = total_bits - 1
+    additional_items = 2 ** (non_sign_bits - max_exponent_bits) - 1
+    i = 0
+    for i in range(max_exponent_bits):
+        fraction_items = int(
+            2 ** (i + non_sign_bits - max_exponent_bits) + 1 if signed else 2 ** (i + non_sign_bits - max_exponent_bits + 1) + 1
+        )
+        boundaries = torch.linspace(0.1, 1, fraction_items, dtype=torch.float32)
+        means = (boundaries[:-1] + boundaries[1:]) / 2.0
+        data += ((10 ** (-(max_exponent_bits - 1) + i)) * means).tolist()
+        if signed:
+            data += (-(10 ** (-(max_exponent_bits - 1) + i)) * means).tolist()
+    if additional_items > 0:
+        boundaries = torch.linspace(0.1, 1, additional_items + 1, dtype=torch.float32)
+        means = (boundaries[:-1] + boundaries[1:]) / 2.0
+        data += ((10 ** (-(max_exponent_bits - 1) + i)) * means).tolist()
+        if signed:
+            data += (-(10 ** (-(max_exponent_bits - 1) + i)) * means).tolist()
+    data.append(0)
+    data.append(1.0)
+    assert len(data) == 2**total_bits
+    data.sort()
+    return torch.tensor(data, dtype=torch.float32).numpy()
+
+
+def _dquantize8(code: np.ndarray, x: np.float32) -> int:
+    """bitsandbytes' ``dQuantize<0>`` (kernels.cu), scalar restatement: seven-step bisection from pivot 127, then the
+    nearer of the pivot and the neighbour on x's side, all comparisons strict, fp32 midpoints."""
+    pivot, upper_pivot, lower_pivot = 127, 255, 0
+    lower, upper = np.float32(-1.0), np.float32(1.0)
+    val = code[pivot]
+    i = 64
+    while i > 0:
+        if x > val:
+            lower_pivot, lower = pivot, val
+            pivot += i
+        else:
+            upper_pivot, upper = pivot, val
+            pivot -= i
+        val = code[pivot]
+        i >>= 1
+    if upper_pivot == 255:
+        upper = code[upper_pivot]
+    if lower_pivot == 0:
+        lower = code[lower_pivot]
+    if x > val:
+        mid = np.float32(np.float32(upper + val) * np.float32(0.5))
+        return upper_pivot if x > mid else pivot
+    mid = np.float32(np.float32(lower + val) * np.float32(0.5))
+    return lower_pivot if x < mid else pivot
+
+
+def dquantize8(code: np.ndarray, x: np.ndarray) -> np.ndarray:
+    """Vectorised form of :func:`_dquantize8` (same decisions; checked against the scalar loop in tests)."""
+    code = np.asarray(code, np.float32)
+    x = np.asarray(x, np.float32).reshape(-1)
+    n = x.size
+    pivot = np.full(n, 127, np.int64)
+    upper_pivot = np.full(n, 255, np.int64)
+    lower_pivot = np.zeros(n, np.int64)
+    lower = np.full(n, -1.0, np.float32)
+    upper = np.full(n, 1.0, np.float32)
+    val = code[pivot]
+    i = 64
+    with np.errstate(invalid="ignore"):
+        while i > 0:
+            gt = x > val
+            lower_pivot = np.where(gt, pivot, lower_pivot)
+            lower = np.where(gt, val, lower)
+            upper_pivot = np.where(gt, upper_pivot, pivot)
+            upper = np.where(gt, upper, val)
+            pivot = np.where(gt, pivot + i, pivot - i)
+            val = code[pivot]
+            i >>= 1
+        upper = np.where(upper_pivot == 255, code[255], upper).astype(np.float32)
+        lower = np.where(lower_pivot == 0, code[0], lower).astype(np.float32)
+        gt = x > val
+        mid_hi = ((upper + val).astype(np.float32) * np.float32(0.5)).astype(np.float32)
+        mid_lo = ((lower + val).astype(np.float32) * np.float32(0.5)).astype(np.float32)
+        out = np.where(gt, np.where(x > mid_hi, upper_pivot, pivot), np.where(x < mid_lo, lower_pivot, pivot))
+    return out.astype(np.uint8)
+
+
+def absmax_nest(absmax, code: np.ndarray | None = None, blocksize2: int = NESTED_BLOCKSIZE):
+    """fp32 absmax -> (absmax8 uint8[n], absmax2 fp32[ceil(n/256)], offset fp32, code fp32[256]).
+
+    ``offset`` is the correctly rounded fp32 mean (float64 accumulation).  bitsandbytes takes torch's fp32
+    ``absmax.mean()`` whose summation order depends on the device and the torch build; the float64 mean is the value
+    all of those approximate, and is what the CUDA kernel computes (csrc/absmax_nest.cu)."""
+    a = np.ascontiguousarray(np.asarray(absmax, np.float32).reshape(-1))
+    code = dynamic_map() if code is None else np.asarray(code, np.float32)
+    n = a.size
+    offset = np.float32(a.astype(np.float64).sum() / n)
+    v = (a - offset).astype(np.float32)
+    nb = (n + blocksize2 - 1) // blocksize2
+    pad = nb * blocksize2 - n
+    vp = np.concatenate([v, np.zeros(pad, np.float32)]) if pad else v
+    blocks = vp.reshape(nb, blocksize2)
+    absmax2 = np.abs(blocks).max(axis=1).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = (np.float32(1.0) / absmax2).astype(np.float32)
+        scaled = (blocks * inv[:, None]).astype(np.float32)
+    q = dquantize8(code, scaled.reshape(-1))[:n]
+    return q, absmax2, offset, code
+
+
+def absmax_denest(absmax8, absmax2, offset, code: np.ndarray, blocksize2: int = NESTED_BLOCKSIZE) -> np.ndarray:
+    """``dequantize_blockwise(absmax8, state2) + offset``: code[q] * absmax2[i // 256] rounded to fp32, then + offset
+    rounded to fp32 (formula corroborated by vllm's bitsandbytes loader)."""
+    q = np.asarray(absmax8, np.uint8).reshape(-1)
+    s = np.asarray(absmax2, np.float32).reshape(-1)
+    code = np.asarray(code, np.float32)
+    idx = np.arange(q.size) // blocksize2
+    prod = (code[q] * s[idx]).astype(np.float32)
+    return (prod + np.float32(offset)).astype(np.float32)
+
+
+def quant_state_absmax_f32(quant_state) -> np.ndarray:
+    """fp32 block statistics a (possibly nested) module-level quant state decodes to -- checker-side restatement of
+    what Linear4bit feeds the kernels.  ``quant_state``: the product's QuantState (read-only: tensors -> numpy)."""
+    a = quant_state.absmax.detach().cpu().numpy()
+    if not getattr(quant_state, "nested", False):
+        return a.astype(np.float32)
+    s2 = quant_state.state2
+    return absmax_denest(a, s2.absmax.detach().cpu().numpy(), np.float32(float(quant_state.offset)),
+                         s2.code.detach().cpu().numpy(), int(s2.blocksize))

@@ -100,3 +100,58 @@ int nf4_dequantize_ref(const uint8_t* packed, const float* absmax, int64_t n, in
   }
   return 0;
 }
+
+/* ---- nested ("double quant") block statistics: quantize_blockwise(absmax - mean, 256) with the 8-bit dynamic map.
+ * Same status (parity unpinned) and same semantics as oracle/nf4_oracle.py absmax_nest / absmax_denest. */
+static unsigned dquantize8(const float* code, float x) { /* bitsandbytes dQuantize<0> */
+  int pivot = 127, upper_pivot = 255, lower_pivot = 0;
+  float lower = -1.0f, upper = 1.0f, val = code[pivot];
+  for (int i = 64; i > 0; i >>= 1) {
+    if (x > val) { lower_pivot = pivot; lower = val; pivot += i; }
+    else { upper_pivot = pivot; upper = val; pivot -= i; }
+    val = code[pivot];
+  }
+  if (upper_pivot == 255) upper = code[upper_pivot];
+  if (lower_pivot == 0) lower = code[lower_pivot];
+  if (x > val) {
+    const float mid = (upper + val) * 0.5f;
+    return (unsigned)(x > mid ? upper_pivot : pivot);
+  }
+  const float mid = (lower + val) * 0.5f;
+  return (unsigned)(x < mid ? lower_pivot : pivot);
+}
+
+int absmax_nest_ref(const float* absmax, int64_t n, int blocksize2, const float* code, uint8_t* q, float* absmax2,
+                    float* offset_out) {
+  if (n <= 0 || blocksize2 <= 0) return -1;
+  double s = 0.0;
+  for (int64_t i = 0; i < n; ++i) s += (double)absmax[i];
+  const float off = (float)(s / (double)n);
+  *offset_out = off;
+  const int64_t nb = (n + blocksize2 - 1) / blocksize2;
+#pragma omp parallel for schedule(static)
+  for (int64_t b = 0; b < nb; ++b) {
+    const int64_t lo = b * blocksize2, hi = lo + blocksize2 < n ? lo + blocksize2 : n;
+    float m = 0.0f;
+    for (int64_t i = lo; i < hi; ++i) {
+      const float a = fabsf(absmax[i] - off);
+      m = a > m ? a : m;
+    }
+    absmax2[b] = m;
+    const volatile float one = 1.0f;
+    const float inv = one / m;
+    for (int64_t i = lo; i < hi; ++i) q[i] = (uint8_t)dquantize8(code, (absmax[i] - off) * inv);
+  }
+  return 0;
+}
+
+int absmax_denest_ref(const uint8_t* q, const float* absmax2, const float* code, float offset, int64_t n,
+                      int blocksize2, float* out) {
+  if (blocksize2 <= 0) return -1;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    const volatile float prod = code[q[i]] * absmax2[i / blocksize2];
+    out[i] = prod + offset;
+  }
+  return 0;
+}

@@ -82,6 +82,13 @@ def nf4_hashes() -> dict:
         w = (torch.randn(3072, 3072, generator=g) * 0.02).to(dt)
         packed, absmax = nf4_oracle.nf4_quantize(w)
         res[dt_name] = {"packed_sha256": sha(packed), "absmax_sha256": sha(absmax), "seed": 0, "std": 0.02, "shape": [3072, 3072]}
+        # nested ("double quant") statistics of the same weight
+        q, a2, off, code = nf4_oracle.absmax_nest(absmax)
+        res[dt_name].update({
+            "nested_absmax8_sha256": sha(q), "nested_absmax2_sha256": sha(a2), "nested_offset": float(off),
+            "denested_absmax_sha256": sha(nf4_oracle.absmax_denest(q, a2, off, code)),
+        })
+    res["dynamic_map_sha256"] = sha(nf4_oracle.dynamic_map())
     return res
 
 

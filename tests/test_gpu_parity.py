@@ -344,3 +344,60 @@ def test_auto_dispatch_reports_path(ops):
     ops.qlora_linear(xf, torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), None, None, None, 0.0, 128, 64, 64,
                      torch.bfloat16)
     assert ops.last_path() == SIMT
+
+
+# ----------------------------------------------------------------------------- nested ("double quant") statistics
+@pytest.mark.parametrize("n", [1, 7, 255, 256, 257, 1000, 4099, 3072 * 3072 // 64, 18432 * 3072 // 64])
+def test_absmax_nest_bit_exact(ops, n):
+    from vft_b200.nn import create_dynamic_map
+
+    rng = np.random.default_rng(n)
+    a = (np.abs(rng.normal(0, 0.02, n)) * 3 + 0.05).astype(np.float32)
+    if n > 600:
+        a[256:512] = a[300]  # a constant statistics block: (a - offset) identical, still a valid block
+    code = create_dynamic_map()
+    assert np.array_equal(code.numpy(), nf4_oracle.dynamic_map())
+    q, a2, off = ops.absmax_nest(torch.from_numpy(a).cuda(), code.cuda())
+    qo, a2o, offo, _ = nf4_oracle.absmax_nest(a)
+    assert float(off) == float(offo)
+    assert np.array_equal(a2.cpu().numpy(), a2o) and np.array_equal(q.cpu().numpy(), qo)
+    d = ops.absmax_denest(q, a2, code.cuda(), float(off))
+    assert np.array_equal(d.cpu().numpy(), nf4_oracle.absmax_denest(qo, a2o, offo, code.numpy()))
+
+
+def test_absmax_nest_all_equal_block(ops):
+    """Every statistic equal -> (a - mean) == 0 -> 0 * inf = NaN -> every comparison false: index 0 (oracle agrees)."""
+    from vft_b200.nn import create_dynamic_map
+
+    a = np.full(512, 0.125, np.float32)
+    code = create_dynamic_map()
+    q, a2, off = ops.absmax_nest(torch.from_numpy(a).cuda(), code.cuda())
+    qo, a2o, offo, _ = nf4_oracle.absmax_nest(a)
+    assert float(off) == 0.125 == float(offo) and np.array_equal(q.cpu().numpy(), qo) and (qo == 0).all()
+    assert np.array_equal(a2.cpu().numpy(), a2o) and (a2o == 0).all()
+
+
+@pytest.mark.parametrize("dt_name,dt", [("bfloat16", torch.bfloat16), ("float16", torch.float16)])
+def test_quantize_4bit_nested_seeded_hashes(golden_dir, dt_name, dt):
+    """quantize_4bit(compress_statistics=True) -- Params4bit.cuda()'s path -- against the committed hashes, and the
+    as_dict(packed=True) checkpoint entries it emits."""
+    from vft_b200.nn import dequantize_4bit, quantize_4bit
+
+    ref = json.load(open(os.path.join(golden_dir, "nf4_hashes.json")))[dt_name]
+    g = torch.Generator().manual_seed(ref["seed"])
+    w = (torch.randn(*ref["shape"], generator=g) * ref["std"]).to(dt)
+    packed, qs = quantize_4bit(w.cuda(), compress_statistics=True)
+    assert qs.nested and qs.absmax.dtype == torch.uint8
+    assert _sha(packed.cpu().numpy()) == ref["packed_sha256"]
+    assert _sha(qs.absmax.cpu().numpy()) == ref["nested_absmax8_sha256"]
+    assert _sha(qs.state2.absmax.cpu().numpy()) == ref["nested_absmax2_sha256"]
+    assert float(qs.offset) == ref["nested_offset"]
+    assert _sha(qs.absmax_f32().cpu().numpy()) == ref["denested_absmax_sha256"]
+    d = qs.as_dict(packed=True)
+    assert set(d) == {"absmax", "quant_map", "nested_absmax", "nested_quant_map", "quant_state.bitsandbytes__nf4"}
+    meta = nf4_oracle.unpack_quant_state_blob(d["quant_state.bitsandbytes__nf4"])
+    assert meta == {"quant_type": "nf4", "blocksize": 64, "dtype": dt_name, "shape": ref["shape"],
+                    "nested_blocksize": 256, "nested_dtype": "float32", "nested_offset": ref["nested_offset"]}
+    # dequantize with the de-nested statistics == oracle decode of the same pieces
+    want = nf4_oracle.nf4_dequantize(packed.cpu().numpy(), nf4_oracle.quant_state_absmax_f32(qs), ref["shape"], dt_name)
+    assert torch.equal(dequantize_4bit(packed, qs).cpu(), want)

@@ -120,32 +120,77 @@ def test_prequantized_checkpoint_loads_on_cpu():
     )
 
 
-@torch.no_grad()
-def test_nested_absmax_checkpoint_is_denested_on_load():
-    """compress_statistics=True checkpoints (tools/quantize_model.py output): absmax uint8 + nested_* keys."""
+def _nested_stats(n_out=128, n_in=256, seed=0):
+    """A compress_statistics=True checkpoint entry built by the oracle (tools/quantize_model.py output format)."""
     import json
 
-    absmax = torch.rand(512) * 0.1 + 0.01
-    offset = absmax.mean()
-    code = torch.linspace(-1, 1, 256)
-    centered = (absmax - offset).reshape(2, 256)
-    am2 = centered.abs().amax(dim=1)
-    idx = ((centered / am2[:, None])[:, :, None] - code[None, None, :]).abs().argmin(dim=2).to(torch.uint8)
-    want = (code[idx.long()] * am2[:, None]).reshape(-1) + offset
-    meta = {"quant_type": "nf4", "blocksize": 64, "dtype": "bfloat16", "shape": [128, 256],
-            "nested_blocksize": 256, "nested_dtype": "float32", "nested_offset": float(offset)}
+    import numpy as np
+
+    from oracle import nf4_oracle
+
+    w = torch.randn(n_out, n_in, generator=torch.Generator().manual_seed(seed)).to(torch.bfloat16)
+    p, a = nf4_oracle.nf4_quantize(w)
+    q8, a2, off, code2 = nf4_oracle.absmax_nest(a)
+    meta = {"quant_type": "nf4", "blocksize": 64, "dtype": "bfloat16", "shape": [n_out, n_in],
+            "nested_blocksize": 256, "nested_dtype": "float32", "nested_offset": float(off)}
     stats = {
-        "absmax": idx.reshape(-1),
-        "quant_map": torch.zeros(16),
-        "nested_absmax": am2,
-        "nested_quant_map": code,
+        "absmax": torch.from_numpy(q8),
+        "quant_map": torch.from_numpy(nf4_oracle.NF4_CODEBOOK.copy()),
+        "nested_absmax": torch.from_numpy(a2),
+        "nested_quant_map": torch.from_numpy(np.array(code2)),
         "quant_state.bitsandbytes__nf4": torch.tensor(list(json.dumps(meta).encode()), dtype=torch.uint8),
     }
+    return w, torch.from_numpy(p), stats, nf4_oracle.absmax_denest(q8, a2, off, code2)
+
+
+@torch.no_grad()
+def test_nested_absmax_checkpoint_stays_nested_on_cpu():
+    """compress_statistics=True checkpoints: absmax uint8 + nested_* keys survive load -> state_dict unchanged (the
+    fp32 statistics are derived on the device, never stored)."""
     from vft_b200.nn import Params4bit
 
-    w = Params4bit.from_prequantized(torch.zeros(128 * 256 // 2, 1, dtype=torch.uint8), stats, device="cpu")
-    assert w.quant_state.absmax.dtype == torch.float32 and not w.quant_state.nested
-    assert torch.allclose(w.quant_state.absmax, want, atol=1e-7)
+    _, packed, stats, _ = _nested_stats()
+    w = Params4bit.from_prequantized(packed, stats, device="cpu")
+    qs = w.quant_state
+    assert qs.nested and qs.absmax.dtype == torch.uint8 and qs.state2.blocksize == 256
+    out = qs.as_dict(packed=True)
+    assert set(out) == set(stats)
+    for k in ("absmax", "nested_absmax", "nested_quant_map", "quant_map"):
+        assert torch.equal(out[k], stats[k]), k
+    import json
+
+    blob = lambda t: json.loads(bytes(t.tolist()).decode())
+    assert blob(out["quant_state.bitsandbytes__nf4"]) == blob(stats["quant_state.bitsandbytes__nf4"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        qs.absmax_f32()
+
+
+@pytest.mark.gpu
+@torch.no_grad()
+def test_nested_absmax_checkpoint_forward_matches_oracle():
+    """Prequantized nested checkpoint -> module -> forward with the de-nested statistics (bit-exact vs the oracle)."""
+    from oracle import qlora_oracle
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.linear = nn.Linear(256, 128, bias=False)
+
+    w, packed, stats, absmax_eff = _nested_stats()
+    sd = {"linear.weight": packed, **{f"linear.weight.{k}": v for k, v in stats.items()}}
+    model = M()
+    replace_by_prequantized_weights(model, sd)
+    model.load_state_dict(sd)
+    model.cuda()
+    qs = model.linear.weight.quant_state
+    assert qs.nested and torch.equal(qs.absmax_f32().cpu(), torch.from_numpy(absmax_eff))
+    out = model.state_dict()
+    for k, v in sd.items():
+        assert torch.equal(out[k].cpu(), v), k
+    x = torch.randn(70, 256, dtype=torch.bfloat16)
+    y = model.linear(x.cuda())
+    ref = qlora_oracle.qlora_linear_ref(x, qlora_oracle.dequant_weight(packed.numpy(), absmax_eff, (128, 256)), None, None, None, 1.0)["y"]
+    assert qlora_oracle.rel_l2(y.cpu(), ref) < 6e-3
 
 
 # ----------------------------------------------------------------------------- GPU: the reference's numeric tests
@@ -218,7 +263,16 @@ def test_quantized_module_matches_oracle_and_moves_between_devices():
     model.cuda()
     p, a = nf4_oracle.nf4_quantize(w)
     assert torch.equal(model.linear.weight.data.cpu(), torch.from_numpy(p))
-    assert torch.equal(model.linear.weight.quant_state.absmax.cpu(), torch.from_numpy(a))
+    # module default compress_statistics=True (bnb.py:44): nested statistics, each piece bit-exact vs the oracle
+    qs = model.linear.weight.quant_state
+    q8, a2, off, code2 = nf4_oracle.absmax_nest(a)
+    assert qs.nested and torch.equal(qs.absmax.cpu(), torch.from_numpy(q8))
+    assert torch.equal(qs.state2.absmax.cpu(), torch.from_numpy(a2)) and float(qs.offset) == float(off)
+    assert torch.equal(qs.state2.code.cpu(), torch.from_numpy(code2))
+    a = nf4_oracle.absmax_denest(q8, a2, off, code2)
+    assert torch.equal(qs.absmax_f32().cpu(), torch.from_numpy(a))
+    sd = model.state_dict()
+    assert sd["linear.weight.absmax"].dtype == torch.uint8 and "linear.weight.nested_absmax" in sd and "linear.weight.nested_quant_map" in sd
     x = torch.randn(3, 50, 128, dtype=torch.bfloat16)
     y = model.linear(x.cuda())
     ref = qlora_oracle.qlora_linear_ref(x, qlora_oracle.dequant_weight(p, a, (256, 128)), b, None, None, 1.0)["y"]

@@ -132,3 +132,53 @@ def test_quant_state_blob_roundtrip():
     blob = nf4_oracle.pack_quant_state_blob((32, 16), "float16")
     meta = nf4_oracle.unpack_quant_state_blob(blob)
     assert meta == {"quant_type": "nf4", "blocksize": 64, "dtype": "float16", "shape": [32, 16]}
+
+
+# ----------------------------------------------------------------------------- nested ("double quant") statistics
+def test_dynamic_map_shape_and_hash(golden_dir):
+    m = nf4_oracle.dynamic_map()
+    assert m.dtype == np.float32 and m.shape == (256,) and (np.diff(m) > 0).all()
+    assert m[0] == np.float32(-0.99296874) and m[127] == 0.0 and m[255] == 1.0  # 127 negatives, 0, 128 positives
+    assert np.isclose(m[128], 5.5e-7) and np.isclose(m[1], -0.9789063)
+    with open(os.path.join(golden_dir, "nf4_hashes.json")) as f:
+        assert _sha(m) == json.load(f)["dynamic_map_sha256"]
+
+
+def test_dquantize8_is_nearest_entry():
+    m = nf4_oracle.dynamic_map()
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-1, 1, 4000), rng.normal(0, 1e-4, 2000), m, [-1.0, 1.0, 0.0]]).astype(np.float32)
+    got = nf4_oracle.dquantize8(m, x)
+    scalar = np.array([nf4_oracle._dquantize8(m, v) for v in x[:1500]])
+    assert np.array_equal(got[:1500], scalar)
+    d = np.abs(x[:, None].astype(np.float64) - m[None, :].astype(np.float64))
+    assert np.array_equal(d[np.arange(x.size), got], d.min(axis=1))  # a nearest entry (ties: either side)
+    assert np.array_equal(nf4_oracle.dquantize8(m, m), np.arange(256))  # every code value maps to itself
+
+
+@pytest.mark.parametrize("n", [1, 5, 255, 256, 257, 1000, 3072 * 3072 // 64])
+def test_absmax_nest_numpy_and_c(n):
+    rng = np.random.default_rng(n)
+    a = (np.abs(rng.normal(0, 0.02, n)) * 3 + 0.05).astype(np.float32)
+    q, a2, off, code = nf4_oracle.absmax_nest(a)
+    qc, a2c, offc = c_oracle.absmax_nest(a, code)
+    assert np.array_equal(q, qc) and np.array_equal(a2, a2c) and off == offc
+    d = nf4_oracle.absmax_denest(q, a2, off, code)
+    assert np.array_equal(d, c_oracle.absmax_denest(q, a2, off, code))
+    if n > 1:  # the 8-bit map resolves (absmax - mean) / absmax2 to ~1.5 % of full scale near +-1
+        assert np.abs(d - a).max() <= 0.016 * np.abs(a - off).max() + 1e-9
+    # idempotence of the decoded statistics under re-encoding with the same offset/scale grid
+    assert q.dtype == np.uint8 and a2.shape == ((n + 255) // 256,)
+
+
+@pytest.mark.parametrize("dt_name,dt", [("bfloat16", torch.bfloat16), ("float16", torch.float16)])
+def test_nested_seeded_3072_hashes(golden_dir, dt_name, dt):
+    with open(os.path.join(golden_dir, "nf4_hashes.json")) as f:
+        ref = json.load(f)[dt_name]
+    g = torch.Generator().manual_seed(ref["seed"])
+    w = (torch.randn(*ref["shape"], generator=g) * ref["std"]).to(dt)
+    _, a = c_oracle.quantize(w)
+    q, a2, off, code = nf4_oracle.absmax_nest(a)
+    assert _sha(q) == ref["nested_absmax8_sha256"] and _sha(a2) == ref["nested_absmax2_sha256"]
+    assert float(off) == ref["nested_offset"]
+    assert _sha(nf4_oracle.absmax_denest(q, a2, off, code)) == ref["denested_absmax_sha256"]

@@ -106,7 +106,7 @@ def test_one_training_step_matches_the_oracle():
         if base is None or (not hasattr(mod, "lora_up") and name.endswith(".linear")):
             continue
         packed = base.weight.data.cpu().numpy()
-        absmax = base.weight.quant_state.absmax.cpu().numpy()
+        absmax = nf4_oracle.quant_state_absmax_f32(base.weight.quant_state)
         n_out, n_in = base.out_features, base.in_features
         w_deq = qlora_oracle.dequant_weight(packed, absmax, (n_out, n_in), "bfloat16")
         bias = None if base.bias is None else base.bias.detach().cpu()

@@ -142,7 +142,23 @@ int vft_nf4_tile_weight(const uint8_t* packed, const float* absmax, int64_t N, i
   return launch_tile_weight(packed, absmax, N, K, blocksize, codes_t, absmax_t, static_cast<cudaStream_t>(stream));
 }
 
+int vft_absmax_nest(const float* absmax, int64_t nblocks, int blocksize2, const float* code256, uint8_t* absmax8,
+                    float* absmax2, float* offset, void* ws, int64_t ws_bytes, void* stream) {
+  VFT_REQUIRE(absmax && code256 && absmax8 && absmax2 && offset, "null pointer");
+  return launch_absmax_nest(absmax, nblocks, blocksize2, code256, absmax8, absmax2, offset, ws, ws_bytes,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int vft_absmax_denest(const uint8_t* absmax8, const float* absmax2, const float* code256, float offset,
+                      int64_t nblocks, int blocksize2, float* absmax_out, void* stream) {
+  VFT_REQUIRE(nblocks >= 0, "nblocks must be >= 0");
+  VFT_REQUIRE(nblocks == 0 || (absmax8 && absmax2 && code256 && absmax_out), "null pointer");
+  return launch_absmax_denest(absmax8, absmax2, code256, offset, nblocks, blocksize2, absmax_out,
+                              static_cast<cudaStream_t>(stream));
+}
+
 int64_t vft_workspace_bytes(int op, int64_t T, int64_t N, int64_t K, int r) {
+  if (op == VFT_OP_ABSMAX_NEST) return absmax_nest_workspace_bytes();
   if (op == VFT_OP_BWD_DAB) return (int64_t)sizeof(float) * (N + K) * (r > 0 ? r : 0);
   if (op == VFT_OP_FWD) return tc2_workspace_bytes(T, N, K, r, false);
   if (op == VFT_OP_BWD_DX) return tc2_workspace_bytes(T, N, K, r, true);

@@ -102,6 +102,13 @@ int launch_dequantize(const uint8_t* packed, const float* absmax, int64_t n, int
 int launch_tile_weight(const uint8_t* packed, const float* absmax, int64_t N, int64_t K, int blocksize,
                        uint8_t* codes_t, float* absmax_t, cudaStream_t st);
 
+// nested block statistics (absmax_nest.cu)
+int64_t absmax_nest_workspace_bytes();
+int launch_absmax_nest(const float* absmax, int64_t n, int blocksize2, const float* code256, uint8_t* absmax8,
+                       float* absmax2, float* offset_out, void* ws, int64_t ws_bytes, cudaStream_t st);
+int launch_absmax_denest(const uint8_t* absmax8, const float* absmax2, const float* code256, float offset, int64_t n,
+                         int blocksize2, float* out, cudaStream_t st);
+
 struct LayerArgs {
   int64_t T, N, K;
   int blocksize, act_dtype, qdtype, r;

@@ -12,11 +12,11 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvft_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 LORA_LD = 64
 F32, F16, BF16 = 0, 1, 2
 PATH_NONE, PATH_TCGEN05, PATH_SIMT = 0, 1, 2
-OP_FWD, OP_BWD_DX, OP_BWD_DAB = 0, 1, 2
+OP_FWD, OP_BWD_DX, OP_BWD_DAB, OP_ABSMAX_NEST = 0, 1, 2, 3
 
 # every symbol include/vft_b200.h declares: (restype, argtypes)
 _c = ctypes
@@ -31,6 +31,8 @@ SYMBOLS = {
     "vft_nf4_quantize_host": (_i, [_p, _i, _i64, _i, _p, _p]),
     "vft_nf4_tiled_bytes": (_i64, [_i64, _i64, _i]),
     "vft_nf4_tile_weight": (_i, [_p, _p, _i64, _i64, _i, _p, _p, _p]),
+    "vft_absmax_nest": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p, _i64, _p]),
+    "vft_absmax_denest": (_i, [_p, _p, _p, _f, _i64, _i, _p, _p]),
     "vft_workspace_bytes": (_i64, [_i, _i64, _i64, _i64, _i]),
     "vft_qlora_fwd": (_i, [_p, _i64, _p, _p, _i64, _i64, _i, _i, _i, _p, _p, _p, _i, _f, _p, _p, _p, _i64, _p, _p, _p]),
     "vft_qlora_bwd_dx": (_i, [_p, _i64, _p, _p, _i64, _i64, _i, _i, _i, _p, _p, _i, _f, _p, _p, _p, _i64, _p, _p, _p]),

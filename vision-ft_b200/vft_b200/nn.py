@@ -24,12 +24,52 @@ NF4_QUANT_MAP = (
     0.07958029955625534, 0.16093020141124725, 0.24611230194568634, 0.33791524171829224,
     0.44070982933044434, 0.5626170039176941, 0.7229568362236023, 1.0,
 )
+NESTED_BLOCKSIZE = 256
 _DTYPE_BY_NAME = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}
 _PACKED_KEY = "quant_state.bitsandbytes__"
 
 
 def _dtype_name(dt: torch.dtype) -> str:
     return str(dt).replace("torch.", "")
+
+
+_DYNAMIC_MAP: torch.Tensor | None = None
+
+
+def create_dynamic_map(signed: bool = True, max_exponent_bits: int = 7, total_bits: int = 8) -> torch.Tensor:
+    """The 256-entry ascending 8-bit "dynamic" code of the nested statistics (``nested_quant_map`` in a checkpoint;
+    stands where bitsandbytes.functional.create_dynamic_map stands).  Exponent-like layout: 10^-6 .. 10^0 decades,
+    each with linearly spaced fraction means, mirrored in sign, plus 0 and 1.  Host-side table construction."""
+    global _DYNAMIC_MAP
+    if (signed, max_exponent_bits, total_bits) == (True, 7, 8) and _DYNAMIC_MAP is not None:
+        return _DYNAMIC_MAP.clone()
+    non_sign_bits = total_bits - 1
+    extra = 2 ** (non_sign_bits - max_exponent_bits) - 1
+    values: list[float] = []
+
+    def decade(exponent: int, n_items: int) -> None:
+        edges = torch.linspace(0.1, 1, n_items, dtype=torch.float32)
+        means = (edges[:-1] + edges[1:]) / 2.0
+        mag = ((10 ** exponent) * means).tolist()
+        values.extend(mag)
+        if signed:
+            values.extend((-(10 ** exponent) * means).tolist())
+
+    e = -(max_exponent_bits - 1)
+    for i in range(max_exponent_bits):
+        e = -(max_exponent_bits - 1) + i
+        decade(e, int(2 ** (i + non_sign_bits - max_exponent_bits) + 1 if signed
+                      else 2 ** (i + non_sign_bits - max_exponent_bits + 1) + 1))
+    if extra > 0:
+        decade(e, extra + 1)
+    values += [0.0, 1.0]
+    if len(values) != 2 ** total_bits:
+        raise ValueError("dynamic map does not fill the code space")
+    table = torch.tensor(sorted(values), dtype=torch.float32)
+    if (signed, max_exponent_bits, total_bits) == (True, 7, 8):
+        _DYNAMIC_MAP = table
+        return table.clone()
+    return table
 
 
 class QuantState:
@@ -46,23 +86,23 @@ class QuantState:
         self.state2 = state2
         self.nested = state2 is not None
 
-    # ---- nested ("double quant") statistics: decode only; see DESIGN.md for the encode status
-    def denest(self) -> None:
-        """absmax(uint8) -> fp32: nested_quant_map[absmax] * nested_absmax[i // bs2] + offset (bitsandbytes
-        dequantize_blockwise + offset; formula corroborated by vllm's bitsandbytes loader)."""
+    # ---- nested ("double quant") statistics: absmax is uint8 indices into state2.code, scaled per 256 by
+    # state2.absmax, shifted by offset.  The checkpoint form is kept as loaded / as encoded; the fused kernels read
+    # the fp32 vector below, decoded ONCE per weight on the device (bitsandbytes decodes it in every forward).
+    def absmax_f32(self) -> torch.Tensor:
         if not self.nested:
-            return
-        s2 = self.state2
-        idx = self.absmax.to(torch.long).reshape(-1)
-        vals = s2.code.to(idx.device)[idx]
-        scale = s2.absmax.to(idx.device).float().repeat_interleave(s2.blocksize)[: idx.numel()]
-        off = self.offset if torch.is_tensor(self.offset) else torch.tensor(float(self.offset))
-        self.absmax = (vals * scale + off.to(idx.device).float()).float()
-        self.state2, self.offset, self.nested = None, None, False
+            return self.absmax
+        cached = self.__dict__.get("_absmax_f32")
+        if cached is None or cached.device != self.absmax.device:
+            s2 = self.state2
+            cached = ops.absmax_denest(self.absmax, s2.absmax, s2.code, float(self.offset), s2.blocksize)
+            self.__dict__["_absmax_f32"] = cached
+        return cached
 
     def to(self, device) -> "QuantState":
         self.absmax = self.absmax.to(device)
         self.code = self.code.to(device)
+        self.__dict__.pop("_absmax_f32", None)
         if self.nested:
             self.offset = self.offset.to(device) if torch.is_tensor(self.offset) else self.offset
             self.state2.absmax = self.state2.absmax.to(device)
@@ -142,13 +182,19 @@ def quantize_4bit(w: torch.Tensor, blocksize: int = 64, compress_statistics: boo
     if w.dtype not in _DTYPE_BY_NAME.values():
         raise ValueError(f"cannot quantize dtype {w.dtype}")
     packed, absmax = ops.nf4_quantize(w, blocksize)
-    # compress_statistics (nested absmax) is accepted; statistics stay fp32 in this round ("next").
-    return packed, QuantState(absmax=absmax, shape=w.shape, dtype=w.dtype, blocksize=blocksize, quant_type="nf4")
+    if not compress_statistics:
+        return packed, QuantState(absmax=absmax, shape=w.shape, dtype=w.dtype, blocksize=blocksize, quant_type="nf4")
+    # nested statistics: offset = mean(absmax); 8-bit dynamic-map blockwise code of (absmax - offset), blocksize 256
+    code2 = create_dynamic_map().to(absmax.device)
+    absmax8, absmax2, offset = ops.absmax_nest(absmax, code2, NESTED_BLOCKSIZE)
+    state2 = QuantState(absmax=absmax2, shape=absmax.shape, dtype=torch.float32, blocksize=NESTED_BLOCKSIZE,
+                        quant_type="dynamic8", code=code2)
+    return packed, QuantState(absmax=absmax8, shape=w.shape, dtype=w.dtype, blocksize=blocksize, quant_type="nf4",
+                              offset=offset, state2=state2)
 
 
 def dequantize_4bit(packed: torch.Tensor, quant_state: QuantState) -> torch.Tensor:
-    quant_state.denest()
-    return ops.nf4_dequantize(packed, quant_state.absmax, quant_state.shape, quant_state.dtype, quant_state.blocksize)
+    return ops.nf4_dequantize(packed, quant_state.absmax_f32(), quant_state.shape, quant_state.dtype, quant_state.blocksize)
 
 
 class Params4bit(torch.nn.Parameter):
@@ -182,9 +228,8 @@ class Params4bit(torch.nn.Parameter):
             device = data.device  # nothing to run on; keep the packed bytes where they are
         self = torch.Tensor._make_subclass(cls, data.to(device), requires_grad)
         self.quant_state = QuantState.from_dict(quantized_stats, device=device)
-        self.quant_state.denest()
         self.blocksize = self.quant_state.blocksize
-        self.compress_statistics = False
+        self.compress_statistics = self.quant_state.nested
         self.quant_type = self.quant_state.quant_type
         self.quant_storage = data.dtype
         self.bnb_quantized = True
@@ -247,16 +292,16 @@ class Linear4bit(nn.Linear):
                 "Linear4bit weight is not quantized yet: move the module to a CUDA device first "
                 "(the NF4 path has no CPU implementation)"
             )
-        qs.denest()
         return w.data, qs
 
     def _tiled(self, packed: torch.Tensor, qs: "QuantState"):
         """Micro-tiled copy of the packed weight for the fused kernels, built once per (storage, device) on first
         use.  Derived data: not a parameter, not a buffer, never in state_dict()."""
-        key = (packed.data_ptr(), qs.absmax.data_ptr(), packed.device)
+        absmax = qs.absmax_f32()
+        key = (packed.data_ptr(), absmax.data_ptr(), packed.device)
         cache = self.__dict__.get("_vft_tiled")
         if cache is None or cache[0] != key:
-            tiles = ops.nf4_tile_weight(packed, qs.absmax, self.out_features, self.in_features, qs.blocksize)
+            tiles = ops.nf4_tile_weight(packed, absmax, self.out_features, self.in_features, qs.blocksize)
             cache = (key, tiles)
             self.__dict__["_vft_tiled"] = cache
         return cache[1]
@@ -272,7 +317,7 @@ class Linear4bit(nn.Linear):
         packed, qs = self._packed()
         inp_dtype = x.dtype
         x = self._cast_input(x)
-        out = ops.qlora_linear(x, packed, qs.absmax, self.bias, None, None, 0.0, self.out_features, self.in_features,
+        out = ops.qlora_linear(x, packed, qs.absmax_f32(), self.bias, None, None, 0.0, self.out_features, self.in_features,
                                qs.blocksize, qs.dtype, self._tiled(packed, qs))
         return out.to(inp_dtype)
 
@@ -281,7 +326,7 @@ class Linear4bit(nn.Linear):
         packed, qs = self._packed()
         inp_dtype = x.dtype
         x = self._cast_input(x)
-        out = ops.qlora_linear(x, packed, qs.absmax, self.bias, lora_a, lora_b, scale, self.out_features,
+        out = ops.qlora_linear(x, packed, qs.absmax_f32(), self.bias, lora_a, lora_b, scale, self.out_features,
                                self.in_features, qs.blocksize, qs.dtype, self._tiled(packed, qs))
         return out.to(inp_dtype)
 

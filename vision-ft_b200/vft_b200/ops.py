@@ -86,6 +86,41 @@ def nf4_dequantize(packed: torch.Tensor, absmax: torch.Tensor, shape, dtype: tor
     return out
 
 
+def absmax_nest(absmax: torch.Tensor, code256: torch.Tensor, blocksize2: int = 256):
+    """Nested statistics encode: fp32 absmax -> (absmax8 uint8 [n], absmax2 fp32 [ceil(n/256)], offset fp32 0-dim)."""
+    dev = _require_cuda(absmax, code256)
+    absmax = absmax.contiguous().float()
+    code256 = code256.contiguous().float()
+    if code256.numel() != 256:
+        raise ValueError("the nested code map must have 256 entries")
+    n = absmax.numel()
+    absmax8 = torch.empty((n,), dtype=torch.uint8, device=dev)
+    absmax2 = torch.empty(((n + blocksize2 - 1) // blocksize2,), dtype=torch.float32, device=dev)
+    offset = torch.empty((), dtype=torch.float32, device=dev)
+    ws_bytes = lib.vft_workspace_bytes(_cabi.OP_ABSMAX_NEST, 0, 0, 0, 0)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.vft_absmax_nest(absmax.data_ptr(), n, blocksize2, code256.data_ptr(), absmax8.data_ptr(),
+                                  absmax2.data_ptr(), offset.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
+    return absmax8, absmax2, offset
+
+
+def absmax_denest(absmax8: torch.Tensor, absmax2: torch.Tensor, code256: torch.Tensor, offset: float,
+                  blocksize2: int = 256) -> torch.Tensor:
+    """Nested statistics decode: code256[absmax8] * absmax2[i // blocksize2] + offset -> fp32 [n]."""
+    dev = _require_cuda(absmax8, absmax2, code256)
+    absmax8 = absmax8.contiguous().reshape(-1)
+    if absmax8.dtype != torch.uint8:
+        raise TypeError(f"nested absmax must be uint8, got {absmax8.dtype}")
+    n = absmax8.numel()
+    out = torch.empty((n,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.vft_absmax_denest(absmax8.data_ptr(), absmax2.contiguous().float().data_ptr(),
+                                    code256.contiguous().float().data_ptr(), float(offset), n, blocksize2,
+                                    out.data_ptr(), _stream()))
+    return out
+
+
 def nf4_quantize_host(w: torch.Tensor, blocksize: int = 64) -> tuple[torch.Tensor, torch.Tensor]:
     """Host-buffer entry (H2D + kernel + D2H inside the C call): what quantize_state_dict amounts to per tensor."""
     if w.is_cuda:
