@@ -248,7 +248,8 @@ def run_gpu_arm(args):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 step(i)
-                flat = torch.cat([p.grad.reshape(-1) for p in params])
+                # the flat bucket exists for the NCCL exchange only: a single rank has nothing to pack
+                flat = torch.cat([p.grad.reshape(-1) for p in params]) if world > 1 else None
             graphs.append(g)
             grad_bufs.append(flat)
         torch.cuda.synchronize()
@@ -269,7 +270,7 @@ def run_gpu_arm(args):
             flat = grad_bufs[s]
         else:
             step(i)
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            flat = torch.cat([p.grad.reshape(-1) for p in params]) if world > 1 else None
         if comm is not None and exchange:
             ev = torch.cuda.Event()
             ev.record()
@@ -463,6 +464,38 @@ def run_gpu_arm(args):
                                       "bytes_per_element": 2.5625, "us_per_tensor": q_ms * 1e3,
                                       "note": "bf16 [18432, 3072], device-resident, CUDA-graph replay; whole AuraFlow set: tools/quant_probe.py"}
 
+    if rank == 0:
+        # few-token forward (T = per-GPU batch 2) of the largest AuraFlow modulation weight [18432, 3072]: achieved
+        # GB/s on the packed-weight stream (0.5625 B/parameter), HBM-cold (9 weight copies in rotation > 2 x L2)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import gemv_probe
+
+            r = gemv_probe.probe(18432, 3072, 2, 0)
+            extra["few_token_weight_stream"] = {
+                "GB/s": r["weight_GBs"], "frac_of_hbm_peak": r["weight_GBs"] / peaks["hbm_gbs"], "us_per_launch": r["us"],
+                "N": 18432, "K": 3072, "T": 2, "path": r["path"], "bytes_per_param": 0.5625,
+                "note": "qlora_gemv.cu (path 3); HBM-cold: weight copies rotate; tools/gemv_probe.py sweeps T and shapes"}
+        except Exception as e:  # pragma: no cover - reported, not hidden
+            extra["few_token_weight_stream"] = {"error": f"{type(e).__name__}: {e}"}
+
+    if not args.no_aura_step:
+        # second half of BASELINE's metric, measured as a job: the AuraFlow-6.8B QLoRA step over the Linear skeleton of
+        # the MMDiT (tools/auraflow_step.py: module API, 322 NF4 Linears, LoRA r=16, checkpointing, fused AdamW,
+        # element-wise glue in torch, attention stand-in), every rank its own batch of 2, LoRA gradients all-reduced
+        # over NCCL from backward hooks.  All ranks take part; timings are the max over ranks.
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import auraflow_step
+
+            res = auraflow_step.measure(B=2, steps=4, warmup=2, attention="stub", world=world, rank=rank)
+            if rank == 0:
+                extra["auraflow_qlora_step_dp"] = res
+        except Exception as e:  # pragma: no cover - reported, not hidden
+            if rank == 0:
+                extra["auraflow_qlora_step_dp"] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
+
     if rank == 0 and world == 1 and not args.no_census:
         # second half of BASELINE's metric: every NF4(+LoRA) Linear of one AuraFlow-6.8B QLoRA training step (per-GPU
         # batch 2 at 1024^2, LoRA r=16 on attention + MLP projections, gradient checkpointing = forward twice), each at
@@ -515,6 +548,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-census", action="store_true")
+    ap.add_argument("--no-aura-step", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -52,7 +52,8 @@ enum vft_status {
 enum vft_path {
   VFT_PATH_NONE = 0,
   VFT_PATH_TCGEN05 = 1, /* fused dequant -> tcgen05.mma (TMEM accumulators), sm_100a */
-  VFT_PATH_SIMT = 2     /* generic CUDA-core kernels: shapes the tensor path does not take */
+  VFT_PATH_SIMT = 2,    /* generic CUDA-core kernels: shapes the tensor path does not take */
+  VFT_PATH_GEMV = 3     /* few-token forward (T <= 8): packed-weight streaming kernel, HBM/decode bound */
 };
 
 enum vft_op { VFT_OP_FWD = 0, VFT_OP_BWD_DX = 1, VFT_OP_BWD_DAB = 2, VFT_OP_ABSMAX_NEST = 3 };

@@ -401,3 +401,103 @@ def test_quantize_4bit_nested_seeded_hashes(golden_dir, dt_name, dt):
     # dequantize with the de-nested statistics == oracle decode of the same pieces
     want = nf4_oracle.nf4_dequantize(packed.cpu().numpy(), nf4_oracle.quant_state_absmax_f32(qs), ref["shape"], dt_name)
     assert torch.equal(dequantize_4bit(packed, qs).cpu(), want)
+
+
+# ----------------------------------------------------------------------------- few-token streaming kernel (qlora_gemv.cu)
+GEMV = 3
+GEMV_CASES = [
+    # T, K, N, r, bias, dt, qdt
+    (2, 3072, 18432, 0, False, torch.bfloat16, torch.bfloat16),   # AuraFlow mod*.1 at per-GPU batch 2
+    (1, 1024, 9216, 0, True, torch.bfloat16, torch.bfloat16),     # Lumina2 adaLN_modulation.1 (bias), batch 1
+    (3, 256, 48, 0, False, torch.bfloat16, torch.bfloat16),       # one group, odd tile count (second tile of the last CTA empty)
+    (4, 768, 1040, 16, True, torch.bfloat16, torch.bfloat16),     # adapter + bias, 3 groups over 4 slices
+    (5, 2304, 272, 8, False, torch.bfloat16, torch.float16),      # fp16 checkpoint, 9 groups (slices uneven)
+    (8, 8192, 160, 4, True, torch.float16, torch.float16),        # widest staged x (TP = 8, K = 8192), fp16 activations
+    (7, 512, 16, 0, False, torch.bfloat16, torch.bfloat16),       # a single row tile
+]
+
+
+@pytest.mark.parametrize("T,K,N,r,bias,dt,qdt", GEMV_CASES)
+def test_gemv_forward_vs_oracle(ops, T, K, N, r, bias, dt, qdt):
+    w, x, dy, a, b, bv = _make_case(T, K, N, r, seed=T + K + N + r, bias=bias, dt=dt, qdt=qdt)
+    if dt == torch.float16:
+        x = x * 0.5
+    p, am = nf4_oracle.nf4_quantize(w)
+    qname = str(qdt).replace("torch.", "")
+    w_deq = qlora_oracle.dequant_weight(p, am, (N, K), qname)
+    truth = qlora_oracle.qlora_linear_truth(x, w_deq.to(dt), bv, a, b, 1.0, None)
+    ops.force_path(0)  # auto: T <= 8 must pick the streaming kernel by itself
+    xc = x.cuda()
+    scale = 1.0 / r if r else 0.0
+    y = ops.qlora_linear(xc, torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), None if bv is None else bv.cuda(),
+                         None if a is None else a.cuda(), None if b is None else b.cuda(), scale, N, K, 64, qdt)
+    assert ops.last_path() == GEMV
+    assert qlora_oracle.rel_l2(y.cpu(), truth["y"]) <= (4e-3 if dt == torch.bfloat16 else 1e-3)
+    if dt == torch.bfloat16 and qdt == torch.bfloat16:
+        ref = qlora_oracle.qlora_linear_ref(x, w_deq, bv, a, b, 1.0, None)
+        _check({"y": y.cpu()}, ref, truth, ("y",), f"gemv-T{T}K{K}N{N}r{r}")
+    if N < 128:
+        return
+    # the tcgen05 family on the same inputs: the two paths share the decode, so they agree to accumulation order
+    ops.force_path(TC)
+    y_tc = ops.qlora_linear(xc, torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), None if bv is None else bv.cuda(),
+                            None if a is None else a.cuda(), None if b is None else b.cuda(), scale, N, K, 64, qdt)
+    assert ops.last_path() == TC
+    ops.force_path(0)
+    assert qlora_oracle.rel_l2(y.cpu(), y_tc.cpu()) <= 5e-3  # two independently bf16-rounded outputs
+
+
+@pytest.mark.parametrize("N,K", [(18432, 3072), (3072, 8192), (9216, 1024)])
+def test_gemv_one_hot_reproduces_weight(ops, N, K):
+    """Size-independent property at full size: x = 8 one-hot rows => y[t, :] is column k_t of the weight the streaming
+    kernel defines, bf16(fp32(bf16(code)) * absmax), BIT FOR BIT (walks all quads, slices, items and both row halves),
+    and that weight sits within one bf16 rounding step of bitsandbytes' bf16(code * absmax)."""
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    w = (torch.randn(N, K, generator=g, device="cuda") * 0.02).to(torch.bfloat16)
+    packed, absmax = ops.nf4_quantize(w)
+    w_deq = ops.nf4_dequantize(packed, absmax, (N, K), torch.bfloat16)
+    codes = nf4_oracle.nf4_unpack(packed.cpu().numpy(), N * K).reshape(N, K)
+    code_bf16 = torch.from_numpy(nf4_oracle.NF4_CODEBOOK.copy()).to(torch.bfloat16).float()
+    am = absmax.cpu().reshape(N, K // 64)
+    ops.force_path(0)
+    ks = torch.randperm(K, generator=torch.Generator().manual_seed(K))[:256].tolist() + [0, 63, 64, 255, 256, K - 1]
+    for i in range(0, len(ks), 8):
+        sel = ks[i:i + 8]
+        x = torch.zeros(len(sel), K, dtype=torch.bfloat16, device="cuda")
+        x[torch.arange(len(sel)), torch.tensor(sel)] = 1.0
+        y = ops.qlora_linear(x, packed, absmax, None, None, None, 0.0, N, K, 64, torch.bfloat16)
+        assert ops.last_path() == GEMV
+        want = torch.stack([(code_bf16[torch.from_numpy(codes[:, k].astype(np.int64))] * am[:, k // 64]).to(torch.bfloat16)
+                            for k in sel])
+        assert torch.equal(y.cpu(), want), sel
+        ref = w_deq[:, sel].t().float().cpu()
+        assert ((y.cpu().float() - ref).abs() <= ref.abs() * 2.0 ** -7 + 1e-30).all(), sel
+
+
+def test_gemv_through_module_with_nested_statistics(ops):
+    """modulation-style layer through BnbLinear4bit (nested absmax by default) at T = batch = 2, with autograd off and
+    on (the backward of a few-token layer stays on the tcgen05 split-K kernel)."""
+    import torch.nn as nn
+
+    from src.modules.quant import quantize_inplace
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mod = nn.Sequential(nn.SiLU(), nn.Linear(512, 3072, bias=False, dtype=torch.bfloat16))
+
+    model = M()
+    w = model.mod[1].weight.detach().clone()
+    quantize_inplace(model, "bnb_nf4", include_keys=["mod.1"])
+    model.cuda()
+    lin = model.mod[1]
+    absmax_eff = nf4_oracle.quant_state_absmax_f32(lin.weight.quant_state)
+    w_deq = qlora_oracle.dequant_weight(lin.weight.data.cpu().numpy(), absmax_eff, (3072, 512), "bfloat16")
+    x = torch.randn(2, 512, dtype=torch.bfloat16)
+    xg = x.cuda().requires_grad_(True)
+    y = lin(xg)
+    assert ops.last_path() == GEMV
+    dy = torch.randn(2, 3072, dtype=torch.bfloat16)
+    y.backward(dy.cuda())
+    ref = qlora_oracle.qlora_linear_ref(x, w_deq, None, None, None, 1.0, dy)
+    assert qlora_oracle.rel_l2(y.detach().cpu(), ref["y"]) < 6e-3 and qlora_oracle.rel_l2(xg.grad.cpu(), ref["dx"]) < 6e-3

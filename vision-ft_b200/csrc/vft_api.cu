@@ -182,6 +182,15 @@ int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* 
                                                        : tc_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st);
     if (rc != VFT_OK) return rc;
   }
+  if ((forced_path() == 0 || forced_path() == VFT_PATH_GEMV) && gemv_supported(a)) {
+    set_path(VFT_PATH_GEMV);  // T <= 8: the launch is a weight stream, not a GEMM
+    return gemv_fwd(a, x, y, t_save, st);
+  }
+  if (forced_path() == VFT_PATH_GEMV) {
+    set_error("streaming path forced but shape/dtype not supported (T=%lld N=%lld K=%lld)", (long long)T, (long long)N,
+              (long long)K);
+    return VFT_ERR_UNSUPPORTED;
+  }
   const bool tc = use_tc(a, false, &rc);
   if (rc != VFT_OK) return rc;
   set_path(tc ? VFT_PATH_TCGEN05 : VFT_PATH_SIMT);

@@ -150,6 +150,10 @@ int tc_lora_dt(const void* dy, const void* b, int64_t T, int64_t N, int r, float
 int tc_dab(const void* dy, const void* x, const void* t_save, const void* dt_save, int64_t T, int64_t N, int64_t K,
            int r, int act_dtype, float scale, void* dA, void* dB, float* ws, cudaStream_t st);
 
+// few-token forward: packed-weight streaming kernel (qlora_gemv.cu)
+bool gemv_supported(const LayerArgs& a);
+int gemv_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st);
+
 // tcgen05 family
 bool tc_supported(const LayerArgs& a, bool backward);
 int tc_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st);

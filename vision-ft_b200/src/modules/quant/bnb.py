@@ -51,8 +51,9 @@ class BnbLinear4bit(Linear4bit):
             raise NotImplementedError(
                 f"BnbLinear4bit(quant_type={quant_type!r}): only 'nf4' is implemented by the B200-native path"
             )
-        super().__init__(input_features, output_features, bias=bias, device=device)
-        # placeholders on 'meta' until a state dict arrives (bnb.py:56-69)
+        # The fp weight nn.Linear would allocate and initialise is replaced two lines below by 'meta' placeholders
+        # (bnb.py:56-69), so it is never materialised: 322 AuraFlow Linears would otherwise cost 27 GB of host RNG.
+        super().__init__(input_features, output_features, bias=bias, device="meta" if device is None else device)
         self.weight = Params4bit(
             torch.empty(output_features, input_features, dtype=compute_dtype, device="meta"),
             requires_grad=False,

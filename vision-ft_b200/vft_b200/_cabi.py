@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libvft_b200.so")
 ABI_VERSION = 3
 LORA_LD = 64
 F32, F16, BF16 = 0, 1, 2
-PATH_NONE, PATH_TCGEN05, PATH_SIMT = 0, 1, 2
+PATH_NONE, PATH_TCGEN05, PATH_SIMT, PATH_GEMV = 0, 1, 2, 3
 OP_FWD, OP_BWD_DX, OP_BWD_DAB, OP_ABSMAX_NEST = 0, 1, 2, 3
 
 # every symbol include/vft_b200.h declares: (restype, argtypes)

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB = os.path.join(HERE, "libvft_b200.so")
-SOURCES = ["vft_api.cu", "nf4_quant.cu", "absmax_nest.cu", "qlora_simt.cu", "lora_mma.cu", "lora_tc.cu", "qlora_tc.cu", "qlora_tc2.cu"]
+SOURCES = ["vft_api.cu", "nf4_quant.cu", "absmax_nest.cu", "qlora_simt.cu", "qlora_gemv.cu", "lora_mma.cu", "lora_tc.cu", "qlora_tc.cu", "qlora_tc2.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
