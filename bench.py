@@ -206,7 +206,20 @@ def run_gpu_arm(args):
     if world > 1:
         import datetime
 
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        # The fused GEMM is a persistent kernel on 72 of the 74 SM pairs.  The LoRA-gradient exchange is small
+        # (196 KB for this layer, 67 MB for a whole AuraFlow step) and latency-bound, so NCCL gets at most 4 CTAs: it
+        # runs on the SMs the GEMM leaves free instead of holding back the next step's cluster launch.
+        pg_opts = None
+        try:
+            pg_opts = dist.ProcessGroupNCCL.Options()
+            pg_opts.config.max_ctas = int(os.environ.get("VFT_NCCL_MAX_CTAS", "4"))
+            pg_opts.config.min_ctas = 1
+        except Exception:  # pragma: no cover - older torch: default channel count
+            pg_opts = None
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120), pg_options=pg_opts)
     peaks = measured_peaks()
     model = build_layer(dev)
     layer = model.linear

@@ -24,7 +24,10 @@
 //     the block (one 8-byte load per row and block, a quad reads the 32 bytes of a block contiguously);
 //   * x is staged once per CTA into shared memory in exactly the fragment order ([block][mma][t][token] x 8 bytes);
 //   * weights are read ONCE, straight from the checkpoint layout (row-major packed codes), three 4-block items in
-//     flight per thread (16 warps per SM: ~110 KB outstanding per SM), evict-first;
+//     flight per thread (16 warps per SM: ~110 KB outstanding per SM), evict-first.  (Requesting the CTA's future
+//     tiles into L2 with cp.async.bulk.prefetch at kernel start was measured and did not help: 16.9 vs 15.8 us --
+//     the kernel is bound by the per-warp dependent issue rate at 16 warps per SM, not by HBM latency; ncu:
+//     issue-active 40 %, no pipe above 36 %, profiles/r01_ncu_gemv_v2_byte_lut.txt);
 //   * a CTA = 4 independent row-tile groups x 4 contraction slices (16 warps); the slices of a tile meet in shared
 //     memory (parity double buffer, one named barrier per group), bias and the rank-r adapter term are added there.
 //
