@@ -199,6 +199,11 @@ def run_gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: everything libraries print while the run lasts (NCCL's version banner
+    # goes to the stdout file descriptor from C) is sent to stderr; the line is written to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the QLoRA hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -207,15 +212,15 @@ def run_gpu_arm(args):
         import datetime
 
         # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         # The fused GEMM is a persistent kernel on 72 of the 74 SM pairs.  The LoRA-gradient exchange is small
-        # (196 KB for this layer, 67 MB for a whole AuraFlow step) and latency-bound, so NCCL gets at most 4 CTAs: it
-        # runs on the SMs the GEMM leaves free instead of holding back the next step's cluster launch.
+        # (196 KB for this layer, 67 MB for a whole AuraFlow step) and latency-bound, so NCCL gets at most 2 CTAs: it
+        # runs on the SMs the GEMM leaves free instead of holding back the next step's cluster launch.  Measured at
+        # 8 GPUs (tools/dp_probe.py, profiles/r01_dp_probe_n8.json), us per step: no exchange 147.9; side stream with
+        # NCCL's default channels 171.2, capped at 4 CTAs 157.2, at 2 CTAs 154.1; in stream order 182-190.
         pg_opts = None
         try:
             pg_opts = dist.ProcessGroupNCCL.Options()
-            pg_opts.config.max_ctas = int(os.environ.get("VFT_NCCL_MAX_CTAS", "4"))
+            pg_opts.config.max_ctas = int(os.environ.get("VFT_NCCL_MAX_CTAS", "2"))
             pg_opts.config.min_ctas = 1
         except Exception:  # pragma: no cover - older torch: default channel count
             pg_opts = None
@@ -271,7 +276,7 @@ def run_gpu_arm(args):
         graphs, launch_mode = [], "eager"
         torch.cuda.synchronize()
 
-    comm = torch.cuda.Stream() if world > 1 else None
+    comm = torch.cuda.Stream() if (world > 1 and args.exchange == "overlap") else None
     comm_events = [None] * n_sets
 
     def run_step(i, exchange=True):
@@ -293,6 +298,8 @@ def run_gpu_arm(args):
                 done = torch.cuda.Event()
                 done.record()
             comm_events[s] = done
+        elif world > 1 and exchange:
+            dist.all_reduce(flat)  # in stream order, right behind the step that produced the gradients
 
     def barrier():
         if world > 1:
@@ -501,7 +508,9 @@ def run_gpu_arm(args):
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import auraflow_step
 
-            res = auraflow_step.measure(B=2, steps=4, warmup=2, attention="stub", world=world, rank=rank)
+            # the 67 MB exchange of a whole step is bandwidth-bound: its own process group, NCCL's default channels
+            aura_group = dist.new_group(pg_options=dist.ProcessGroupNCCL.Options()) if world > 1 else None
+            res = auraflow_step.measure(B=2, steps=4, warmup=2, attention="stub", world=world, rank=rank, group=aura_group)
             if rank == 0:
                 extra["auraflow_qlora_step_dp"] = res
         except Exception as e:  # pragma: no cover - reported, not hidden
@@ -547,7 +556,8 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
             "gpu_launches": kernels_per_step * args.steps, "clocks": clocks, "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -562,6 +572,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-census", action="store_true")
     ap.add_argument("--no-aura-step", action="store_true")
+    ap.add_argument("--exchange", default="overlap", choices=["inorder", "overlap"],
+                    help="N > 1: LoRA-gradient all-reduce in stream order behind each step, or on a side stream")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -58,26 +58,30 @@ def _worker(rank, world, port, out):
     try:
         from vft_b200.dp import LoraGradReducer
 
-        model = _build()
-        trainable = [p for p in model.parameters() if p.requires_grad]
-        reducer = LoraGradReducer(trainable, bucket_bytes=600)  # several small buckets
-        assert len(reducer.buckets) >= 2
-        assert sum(b.numel for b in reducer.buckets) == sum(p.numel() for p in trainable)
-        # accumulation micro-step (no exchange) + final micro-step (exchange)
-        with reducer.no_sync():
-            model(_batch(rank, 0)).pow(2).mean().backward()
-        model(_batch(rank, 1)).pow(2).mean().backward()
-        reducer.wait()
-        want = [sum(gs) / world for gs in zip(*[_local_grads(r, (0, 1)) for r in range(world)])]
-        ok = all(torch.allclose(p.grad, w, rtol=1e-5, atol=1e-7) for p, w in zip(trainable, want))
-        # a second optimizer step reuses the buckets
-        for p in trainable:
-            p.grad = None
-        model(_batch(rank, 2)).pow(2).mean().backward()
-        reducer.wait()
-        want2 = [sum(gs) / world for gs in zip(*[_local_grads(r, (2,)) for r in range(world)])]
-        ok = ok and all(torch.allclose(p.grad, w, rtol=1e-5, atol=1e-7) for p, w in zip(trainable, want2))
-        out[rank] = bool(ok)
+        ok_all = True
+        for overlap in (True, False):  # buckets launched from the backward hooks / all of them from wait()
+            model = _build()
+            trainable = [p for p in model.parameters() if p.requires_grad]
+            reducer = LoraGradReducer(trainable, bucket_bytes=600, overlap=overlap)  # several small buckets
+            assert len(reducer.buckets) >= 2
+            assert sum(b.numel for b in reducer.buckets) == sum(p.numel() for p in trainable)
+            # accumulation micro-step (no exchange) + final micro-step (exchange)
+            with reducer.no_sync():
+                model(_batch(rank, 0)).pow(2).mean().backward()
+            model(_batch(rank, 1)).pow(2).mean().backward()
+            reducer.wait()
+            want = [sum(gs) / world for gs in zip(*[_local_grads(r, (0, 1)) for r in range(world)])]
+            ok = all(torch.allclose(p.grad, w, rtol=1e-5, atol=1e-7) for p, w in zip(trainable, want))
+            # a second optimizer step reuses the buckets
+            for p in trainable:
+                p.grad = None
+            model(_batch(rank, 2)).pow(2).mean().backward()
+            reducer.wait()
+            want2 = [sum(gs) / world for gs in zip(*[_local_grads(r, (2,)) for r in range(world)])]
+            ok = ok and all(torch.allclose(p.grad, w, rtol=1e-5, atol=1e-7) for p, w in zip(trainable, want2))
+            reducer.remove()
+            ok_all = ok_all and ok
+        out[rank] = bool(ok_all)
     finally:
         dist.destroy_process_group()
 

@@ -46,7 +46,11 @@ class _Bucket:
 
 class LoraGradReducer:
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 8 << 20, average: bool = True,
-                 group=None):
+                 group=None, overlap: bool = True):
+        # overlap=False: hooks only count; every bucket is reduced from wait(), after backward.  The fused GEMMs are
+        # persistent kernels sized to the whole GPU: a collective that holds a few SMs while they launch costs them a
+        # wave (measured: 11 ms per AuraFlow step at 2-4 GPUs), far more than the 67 MB all-reduce itself.
+        self.overlap = overlap
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.average = average
@@ -80,7 +84,7 @@ class LoraGradReducer:
             return
         b, _ = self._where[id(p)]
         b.pending -= 1
-        if b.pending == 0:
+        if b.pending == 0 and self.overlap:
             self._launch(b)
 
     def _pack(self, b: _Bucket) -> None:
@@ -117,15 +121,16 @@ class LoraGradReducer:
         """Block the current stream until every bucket is reduced; write the (averaged) sums back into .grad."""
         if self.world == 1:
             return
-        for b in self.buckets:
-            if b.pending != 0:
-                if b.pending != len(b.params):
-                    # parameters that received no gradient this step contribute their current (possibly zero) grads
-                    self._launch(b)
-                else:
-                    continue
-            if b.work is not None:
-                b.work.wait()
+        ready = []
+        for b in self.buckets:  # first pass: everything that has not left yet leaves now
+            if b.pending == len(b.params) and b.work is None:
+                continue  # no gradient reached this bucket in this step
+            if b.work is None:
+                # deferred mode, or a bucket some of whose parameters received no gradient (they count as zero)
+                self._launch(b)
+            ready.append(b)
+        for b in ready:  # second pass: join and write back
+            b.work.wait()
             if self._cuda:
                 torch.cuda.current_stream(b.flat.device).wait_stream(self.stream)
             if self.average and not self._cuda:
