@@ -62,6 +62,18 @@ def test_argument_validation_needs_no_gpu(cabi):
     assert rc == -4 and b"workspace" in lib.vft_last_error()
 
 
+def test_nested_statistics_argument_validation(cabi):
+    lib = cabi.lib
+    assert lib.vft_absmax_nest(None, 256, 256, None, None, None, None, None, 0, None) == -1 and b"null" in lib.vft_last_error()
+    # only bitsandbytes' nested blocksize is implemented; the workspace contract is enforced before any launch
+    assert lib.vft_absmax_nest(16, 256, 128, 16, 16, 16, 16, None, 0, None) == -1 and b"256" in lib.vft_last_error()
+    need = lib.vft_workspace_bytes(cabi.OP_ABSMAX_NEST, 0, 0, 0, 0)
+    assert need == 128 * 8
+    assert lib.vft_absmax_nest(16, 256, 256, 16, 16, 16, 16, None, 0, None) == -4 and b"workspace" in lib.vft_last_error()
+    assert lib.vft_absmax_denest(None, None, None, 0.0, 0, 256, None, None) == 0  # empty vector: no-op
+    assert lib.vft_absmax_denest(None, None, None, 0.0, 5, 256, None, None) == -1
+
+
 def test_cpu_tensors_are_rejected(cabi):
     import torch
     from vft_b200 import ops

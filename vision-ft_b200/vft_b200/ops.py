@@ -187,7 +187,7 @@ class QLoRALinearFunction(torch.autograd.Function):
             lora_b = lora_b.contiguous()
         if bias is not None:
             bias = bias.to(x.dtype).contiguous()
-        y = torch.empty((T, N), dtype=x.dtype, device=dev)
+        y = torch.empty((*x.shape[:-1], N), dtype=x.dtype, device=dev)  # final shape: no view between us and autograd
         t_save = torch.empty((T, LORA_LD), dtype=x.dtype, device=dev) if r else None
         ws, ws_bytes = _workspace(_cabi.OP_FWD, T, N, K, r, dev)
         with torch.cuda.device(dev):
@@ -201,7 +201,7 @@ class QLoRALinearFunction(torch.autograd.Function):
         ctx.meta = (N, K, blocksize, act, dtype_code(qdtype), r, float(scale), x.shape)
         ctx.tiled = (codes_t, absmax_t)  # frozen derived buffers, not autograd-tracked
         ctx.save_for_backward(x2 if r else None, packed, absmax, lora_a, lora_b, t_save)
-        return y.reshape(*x.shape[:-1], N)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
@@ -217,7 +217,8 @@ class QLoRALinearFunction(torch.autograd.Function):
         T = dy2.shape[0]
         need_dx = ctx.needs_input_grad[0]
         need_ab = r > 0 and (ctx.needs_input_grad[4] or ctx.needs_input_grad[5])
-        dx = torch.empty((T, K), dtype=dy2.dtype, device=dev) if need_dx else None
+        # allocated in the input's shape: a reshaped view would make AccumulateGrad clone it (25 MB at config #1)
+        dx = torch.empty(x_shape, dtype=dy2.dtype, device=dev) if need_dx else None
         dt_save = torch.empty((T, LORA_LD), dtype=dy2.dtype, device=dev) if r else None
         da = db = None
         with torch.cuda.device(dev):
@@ -241,8 +242,7 @@ class QLoRALinearFunction(torch.autograd.Function):
                         da.data_ptr(), db.data_ptr(), ws.data_ptr(), ws_bytes, _stream(),
                     )
                 )
-        dxo = dx.reshape(x_shape) if need_dx else None
-        return dxo, None, None, None, da, db, None, None, None, None, None, None
+        return dx, None, None, None, da, db, None, None, None, None, None, None
 
 
 def qlora_linear(x, packed, absmax, bias, lora_a, lora_b, scale, out_features, in_features, blocksize=64,
