@@ -32,9 +32,12 @@
 //     memory (parity double buffer, one named barrier per group), bias and the rank-r adapter term are added there.
 //
 // Algorithmic bytes per launch: N*K*0.5625 (codes + absmax); x, y, bias, B are negligible.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "nf4_lut.cuh"
+#include "ptx_sm100.cuh"
 #include "vft_common.cuh"
 
 namespace vft {
@@ -135,7 +138,12 @@ __global__ void __launch_bounds__(kGemvThreads, 1) qlora_gemv_kernel(const GemvA
     b.am_hi = ok ? __ldcs(q0 + 8 * row_blocks) : 0.0f;
   };
 
-  // ---- the first items leave for HBM before the tables are built
+  // Programmatic dependent launch: the CTAs of this kernel are scheduled under the tail of the previous one and
+  // park here.  Nothing is read before the wait: the packed weight and its statistics may have been written by the
+  // kernel right before this one (first use after quantize / de-nest).
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
+  // ---- the first items leave for HBM before the table is built and x is staged
   Item bufA, bufB, bufC;
   if (n_items > 0) load_item(0, 0, bufA);
   if (n_items > 1) load_item(1 / ipt, 1 % ipt, bufB);
@@ -251,12 +259,24 @@ __global__ void __launch_bounds__(kGemvThreads, 1) qlora_gemv_kernel(const GemvA
 
 template <typename ActT, int TP>
 int launch_gemv_tp(const GemvArgs& g, int n_sm, cudaStream_t st) {
+  // (two instead of three items in flight, or one accumulator per MMA instead of a chain of four, measured the same
+  // 16.2-17.0 us on [18432, 3072]: neither prefetch depth nor the MMA chain is what bounds the kernel)
   auto kern = (g.K % (64 * kKSlices * kItemBlocks) == 0) ? qlora_gemv_kernel<ActT, TP, true> : qlora_gemv_kernel<ActT, TP, false>;
   const size_t smem = (size_t)2 * kLutBytes + sizeof(float) * kRedFloats + (size_t)(g.K / 4) * TP * 8;  // incl. alignment slack
   VFT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_tiles = g.N / 16;
   int grid = n_tiles < n_sm ? n_tiles : n_sm;  // one CTA per SM; tiles go round-robin over CTAs first, groups second
-  kern<<<grid, kGemvThreads, smem, st>>>(g);
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)grid);
+  lc.blockDim = dim3(kGemvThreads);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = pdl_enabled() ? 1 : 0;
+  VFT_CUDA_OK(cudaLaunchKernelEx(&lc, kern, g));
   VFT_CUDA_OK(cudaGetLastError());
   return VFT_OK;
 }
