@@ -501,3 +501,20 @@ def test_gemv_through_module_with_nested_statistics(ops):
     y.backward(dy.cuda())
     ref = qlora_oracle.qlora_linear_ref(x, w_deq, None, None, None, 1.0, dy)
     assert qlora_oracle.rel_l2(y.detach().cpu(), ref["y"]) < 6e-3 and qlora_oracle.rel_l2(xg.grad.cpu(), ref["dx"]) < 6e-3
+
+
+def test_empty_batch(ops):
+    """T = 0 (a rank whose ragged bucket came up empty): empty outputs of the right shape, zero adapter gradients."""
+    N, K, r = 256, 128, 8
+    w, x, dy, a, b, bv = _make_case(4, K, N, r, seed=1)
+    p, am = nf4_oracle.nf4_quantize(w)
+    xc = torch.empty(0, K, dtype=torch.bfloat16, device="cuda", requires_grad=True)
+    ac, bc = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y = ops.qlora_linear(xc, torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), None, ac, bc, 1.0 / r, N, K)
+    assert y.shape == (0, N)
+    y.backward(torch.empty(0, N, dtype=torch.bfloat16, device="cuda"))
+    assert xc.grad.shape == (0, K)
+    assert ac.grad.shape == a.shape and not ac.grad.any() and bc.grad.shape == b.shape and not bc.grad.any()
+    y3 = ops.qlora_linear(torch.empty(2, 0, K, dtype=torch.bfloat16, device="cuda"), torch.from_numpy(p).cuda(),
+                          torch.from_numpy(am).cuda(), None, None, None, 0.0, N, K)
+    assert y3.shape == (2, 0, N)

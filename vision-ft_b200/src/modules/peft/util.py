@@ -1,30 +1,41 @@
-"""Abstract adapter layer (mirror of /root/reference/src/modules/peft/util.py:10-49)."""
+"""The contract an adapter layer fulfils towards the surgery helpers in ``functional.py``.
+
+Interface mirror of /root/reference/src/modules/peft/util.py:10-49 (same class name, attributes and method
+signatures: ``replace_to_peft_layer``, ``get_adapter_parameters``, ``load_peft_weight`` and the enable/disable
+context managers only ever talk to this surface).
+"""
 from __future__ import annotations
 
-from abc import ABC, abstractmethod
+import abc
 
 import torch
-import torch.nn as nn
+from torch import nn
 
 
-class PeftLayer(ABC, nn.Module):
+class PeftLayer(abc.ABC, nn.Module):
+    # names of the sub-modules / parameters that belong to the adapter (what is trained and saved) ...
     adapter_param_names: list[str]
+    # ... and the keys of one layer's entry in an adapter checkpoint
     adapter_weight_names: list[str]
+    # False: forward() is the wrapped layer alone
     enabled: bool
-
-    @abstractmethod
-    def init_weights(self) -> None: ...
 
     def set_enabled(self, enabled: bool) -> None:
         self.enabled = enabled
 
-    @abstractmethod
-    def forward(self, x: torch.Tensor) -> torch.Tensor: ...
+    @abc.abstractmethod
+    def init_weights(self) -> None:
+        """(Re-)initialise the adapter so that the wrapped layer's output is unchanged at step 0."""
+
+    @abc.abstractmethod
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """Wrapped layer + adapter (or the wrapped layer alone when disabled)."""
 
     @classmethod
-    @abstractmethod
-    def from_weights(cls, adapter_weights: dict[str, torch.Tensor], original_layer: nn.Module) -> "PeftLayer": ...
+    @abc.abstractmethod
+    def from_weights(cls, adapter_weights: dict[str, torch.Tensor], original_layer: nn.Module) -> "PeftLayer":
+        """Build the adapter around ``original_layer`` from one layer's checkpoint entries."""
 
-    @abstractmethod
+    @abc.abstractmethod
     def load_weights(self, adapter_weights: dict[str, torch.Tensor | None]) -> None:
-        """Load the adapter tensors named in ``adapter_weight_names`` (missing / None entries are skipped)."""
+        """Overwrite the adapter tensors named in ``adapter_weight_names``; missing / None entries are skipped."""

@@ -191,13 +191,14 @@ class QLoRALinearFunction(torch.autograd.Function):
         t_save = torch.empty((T, LORA_LD), dtype=x.dtype, device=dev) if r else None
         ws, ws_bytes = _workspace(_cabi.OP_FWD, T, N, K, r, dev)
         with torch.cuda.device(dev):
-            check(
-                lib.vft_qlora_fwd(
-                    x2.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, blocksize, act, dtype_code(qdtype),
-                    _ptr(bias), _ptr(lora_a), _ptr(lora_b), r, float(scale), y.data_ptr(), _ptr(t_save), _ptr(ws), ws_bytes,
-                    _ptr(codes_t), _ptr(absmax_t), _stream(),
+            if T > 0:  # an empty batch (ragged bucket on one rank) launches nothing
+                check(
+                    lib.vft_qlora_fwd(
+                        x2.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, blocksize, act, dtype_code(qdtype),
+                        _ptr(bias), _ptr(lora_a), _ptr(lora_b), r, float(scale), y.data_ptr(), _ptr(t_save), _ptr(ws),
+                        ws_bytes, _ptr(codes_t), _ptr(absmax_t), _stream(),
+                    )
                 )
-            )
         ctx.meta = (N, K, blocksize, act, dtype_code(qdtype), r, float(scale), x.shape)
         ctx.tiled = (codes_t, absmax_t)  # frozen derived buffers, not autograd-tracked
         ctx.save_for_backward(x2 if r else None, packed, absmax, lora_a, lora_b, t_save)
@@ -221,6 +222,10 @@ class QLoRALinearFunction(torch.autograd.Function):
         dx = torch.empty(x_shape, dtype=dy2.dtype, device=dev) if need_dx else None
         dt_save = torch.empty((T, LORA_LD), dtype=dy2.dtype, device=dev) if r else None
         da = db = None
+        if T == 0:  # empty batch: no launches; the adapter gradients of an empty sum are zeros
+            if need_ab:
+                da, db = torch.zeros_like(lora_a), torch.zeros_like(lora_b)
+            return dx, None, None, None, da, db, None, None, None, None, None, None
         with torch.cuda.device(dev):
             if need_dx or need_ab:
                 ws, ws_bytes = _workspace(_cabi.OP_BWD_DX, T, N, K, r, dev) if need_dx else (None, 0)
