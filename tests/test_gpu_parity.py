@@ -245,7 +245,11 @@ def test_fp16_activations(ops, T, K, N, r):
 
 
 @pytest.mark.parametrize("tiled", [False, True])
-@pytest.mark.parametrize("N,K", [(3072, 3072), (8192, 3072), (3072, 8192)])
+@pytest.mark.parametrize("N,K", [
+    (3072, 3072), (8192, 3072), (3072, 8192),                      # AuraFlow (BASELINE configs #1, #4)
+    (3840, 2304), (2304, 2304), (9216, 2304), (2304, 9216),        # Lumina2 NextDiT qkv / out / w1,w3 / w2 (config #3)
+    (640, 640), (1280, 1280), (640, 2048), (10240, 1280), (1280, 5120), (5120, 640),  # SDXL UNet (config #5)
+])
 def test_identity_activation_reproduces_weight_bit_exact(ops, N, K, tiled):
     """Size-independent property at full size: x = I_K  =>  y[k, :] = W~[:, k] exactly (single non-zero term per
     dot product), and dy = I_N => dx[n, :] = W~[n, :] exactly.  Exercises every tile, stage and lane of the
@@ -518,3 +522,72 @@ def test_empty_batch(ops):
     y3 = ops.qlora_linear(torch.empty(2, 0, K, dtype=torch.bfloat16, device="cuda"), torch.from_numpy(p).cuda(),
                           torch.from_numpy(am).cuda(), None, None, None, 0.0, N, K)
     assert y3.shape == (2, 0, N)
+
+
+AURAFLOW_SHAPES = [(3072, 3072), (8192, 3072), (3072, 8192), (18432, 3072), (3072, 2048), (3072, 16)]
+
+
+@pytest.mark.parametrize("dt_name,dt", [("float16", torch.float16), ("bfloat16", torch.bfloat16)])
+@pytest.mark.parametrize("shape", AURAFLOW_SHAPES)
+def test_auraflow_weight_shapes_full_size_bit_exact(shape, dt_name, dt):
+    """BASELINE.json config #2 at full size: every distinct weight shape of the AuraFlow DiT set (322
+    tensors of these six shapes), quantized the way Params4bit.cuda() does it (nested statistics), bit-exact against
+    the C oracle: codes, fp32 absmax, nested indices / scales / offset, and the decoded statistics."""
+    from oracle import c_oracle
+    from vft_b200.nn import quantize_4bit
+
+    g = torch.Generator().manual_seed(shape[0] * 7 + shape[1])
+    w = (torch.randn(*shape, generator=g) * 0.02).to(dt)
+    w[5, :] = 0  # an all-zero row: zero blocks (K >= 64) / blocks that are zero in part (K = 16)
+    packed, qs = quantize_4bit(w.cuda(), compress_statistics=True)
+    p, a = c_oracle.quantize(w)
+    assert np.array_equal(packed.cpu().numpy(), p)
+    q8, a2, off = c_oracle.absmax_nest(a, nf4_oracle.dynamic_map())
+    assert np.array_equal(qs.absmax.cpu().numpy(), q8) and np.array_equal(qs.state2.absmax.cpu().numpy(), a2)
+    assert float(qs.offset) == float(off)
+    assert np.array_equal(qs.absmax_f32().cpu().numpy(), c_oracle.absmax_denest(q8, a2, off, nf4_oracle.dynamic_map()))
+    # un-nested form (quantize_state_dict's path): the fp32 statistics themselves
+    _, qs_plain = quantize_4bit(w.cuda(), compress_statistics=False)
+    assert np.array_equal(qs_plain.absmax.cpu().numpy(), a)
+
+
+# BASELINE.json config #5: SDXL transformer Linears on ragged aspect-ratio buckets (batch 2): token counts from
+# generate_buckets(1024^2, step 128) at C = 1280 (w/32 * h/32) and C = 640 (w/16 * h/16), none a multiple of 128
+SDXL_RAGGED = [
+    # T, K, N, r, bias
+    (2 * 240, 1280, 1280, 16, True),      # attn to_out.0 (bias) on a 20 x 12 latent grid
+    (2 * 336, 1280, 1280, 16, False),     # attn1 to_q on 28 x 12
+    (2 * 432, 1280, 10240, 16, True),     # ff.net.0.proj (GeGLU: 8C outputs)
+    (2 * 528, 5120, 1280, 16, True),      # ff.net.2
+    (2 * 77, 2048, 1280, 16, False),      # attn2 to_k / to_v on the 77 text tokens
+    (2 * 2112, 640, 640, 16, False),      # C = 640 stage, 66 x 32 grid
+]
+
+
+@pytest.mark.parametrize("T,K,N,r,bias", SDXL_RAGGED)
+def test_sdxl_ragged_buckets_vs_oracle(ops, T, K, N, r, bias):
+    w, x, dy, a, b, bv = _make_case(T, K, N, r, seed=T + K + N, bias=bias, lead=(2, T // 2))
+    p, am = nf4_oracle.nf4_quantize(w)
+    w_deq = qlora_oracle.dequant_weight(p, am, (N, K), "bfloat16")
+    ref = qlora_oracle.qlora_linear_ref(x, w_deq, bv, a, b, 1.0, dy)
+    truth = qlora_oracle.qlora_linear_truth(x, w_deq, bv, a, b, 1.0, dy)
+    out, used = _run_cuda(ops, torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), x, dy, a, b, bv, 1.0, N, K,
+                          torch.bfloat16, 0, tiled=True)
+    assert used == TC
+    _check(out, ref, truth, ("y", "dx", "da", "db"), f"sdxl-T{T}K{K}N{N}")
+
+
+def test_lumina2_block_shapes_vs_oracle(ops):
+    """BASELINE.json config #3 shapes (NextDiT 2.6B, hidden 2304) on a 1024^2 bucket's 4096 image + 256 caption tokens,
+    sampled down to 512 + 32 tokens so that the CPU oracle finishes in seconds; adaLN (bias, T = 1) included."""
+    for T, K, N, r, bias in ((544, 2304, 3840, 16, False), (544, 2304, 9216, 16, False), (544, 9216, 2304, 16, False),
+                             (1, 1024, 9216, 0, True)):
+        w, x, dy, a, b, bv = _make_case(T, K, N, r, seed=T + K + N, bias=bias)
+        p, am = nf4_oracle.nf4_quantize(w)
+        w_deq = qlora_oracle.dequant_weight(p, am, (N, K), "bfloat16")
+        ref = qlora_oracle.qlora_linear_ref(x, w_deq, bv, a, b, 1.0, dy)
+        truth = qlora_oracle.qlora_linear_truth(x, w_deq, bv, a, b, 1.0, dy)
+        out, used = _run_cuda(ops, torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda(), x, dy, a, b, bv, 1.0, N, K,
+                              torch.bfloat16, 0, tiled=True)
+        assert used == (GEMV if T == 1 else TC)
+        _check(out, ref, truth, ("y", "dx") + (("da", "db") if r else ()), f"lumina2-T{T}K{K}N{N}")

@@ -79,8 +79,8 @@ def synthetic_state_dict(kind: str, dtype: torch.dtype = torch.float16, layers: 
         sd[f"{name}.weight"] = (torch.randn(shp[0], shp[1], generator=g, device=device) * 0.02).to(dtype)
         if len(shp) == 3:
             sd[f"{name}.bias"] = torch.zeros(shp[0], dtype=dtype, device=device)
-    sd["denoiser.register_tokens"] = (torch.randn(1, 8, dim) * 0.02).to(dtype)
-    sd["denoiser.positional_encoding"] = (torch.randn(1, 64, dim) * 0.1).to(dtype)
+    sd["denoiser.register_tokens"] = (torch.randn(1, 8, dim, device=device) * 0.02).to(dtype)
+    sd["denoiser.positional_encoding"] = (torch.randn(1, 64, dim, device=device) * 0.1).to(dtype)
     return sd
 
 
@@ -135,6 +135,8 @@ def main(argv=None) -> None:
     ap.add_argument("--synthetic", default=None, help="'auraflow': generate the weight set instead of reading model_path")
     ap.add_argument("--layers", default=None, help="with --synthetic: '<double>,<single>' layer counts (default 4,32)")
     ap.add_argument("--dtype", default="float16")
+    ap.add_argument("--gen_device", default="cpu", help="with --synthetic: where the weights are generated ('cuda' skips "
+                    "the host RNG and the upload: the tool then times quantize + pack + download + save only)")
     args = ap.parse_args(argv)
 
     validate_quant_type(args.quant_type)
@@ -143,11 +145,13 @@ def main(argv=None) -> None:
     if args.synthetic:
         layers = tuple(int(v) for v in args.layers.split(",")) if args.layers else None
         print(f"Generating synthetic {args.synthetic} weights", layers or "")
-        sd = synthetic_state_dict(args.synthetic, getattr(torch, args.dtype), layers)
+        sd = synthetic_state_dict(args.synthetic, getattr(torch, args.dtype), layers, device=args.gen_device)
     else:
         print("Loading model from", args.model_path)
         sd = load_file(args.model_path)
     n_in = sum(v.numel() for v in sd.values())
+    torch.zeros(1, device="cuda")  # CUDA context + library load are not part of the timed region
+    torch.cuda.synchronize()
     print("Quantizing bnb...")
     t0 = time.perf_counter()
     out = quantize_checkpoint(sd, args.quant_type, args.include_keys, args.exclude_keys)
@@ -157,7 +161,7 @@ def main(argv=None) -> None:
     print(f"{n_q} Linears quantized ({n_in / 1e9:.2f} G parameters in the checkpoint) in {dt:.2f} s incl. host<->device copies")
     print("Saving model to", args.save_path)
     os.makedirs(os.path.dirname(os.path.abspath(args.save_path)), exist_ok=True)
-    save_file({k: v.contiguous() for k, v in out.items()}, args.save_path)
+    save_file({k: v.detach().cpu().contiguous() for k, v in out.items()}, args.save_path)
     print("Done!")
 
 
