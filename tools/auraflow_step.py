@@ -132,7 +132,8 @@ class Denoiser(nn.Module):
     def forward(self, patches, text, g, mode="stub", ckpt=True):
         x = self.init_x_linear(patches)
         c = torch.cat([self.register_tokens.expand(text.shape[0], -1, -1), self.cond_seq_linear(text)], 1)
-        run = (lambda f, *a: checkpoint(f, *a, use_reentrant=False)) if ckpt else (lambda f, *a: f(*a))
+        # no dropout anywhere: no RNG state to preserve (and reading it is not allowed during CUDA-graph capture)
+        run = (lambda f, *a: checkpoint(f, *a, use_reentrant=False, preserve_rng_state=False)) if ckpt else (lambda f, *a: f(*a))
         for blk in self.double_layers:
             c, x = run(blk, c, x, g, mode)
         ctx = torch.cat([c, x], 1)
@@ -219,7 +220,7 @@ def run(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
         own_pg = True
     res = measure(args.batch, args.steps, args.warmup, args.attention, args.double, args.single, world, rank,
-                  overlap=args.overlap)
+                  overlap=args.overlap, graph=not args.eager)
     if rank == 0:
         print(json.dumps(res), flush=True)
     if own_pg:
@@ -228,7 +229,7 @@ def run(args):
 
 
 def measure(B=2, steps=5, warmup=2, attention="stub", n_double=4, n_single=32, world=1, rank=0, exposed=True,
-            overlap=False, group=None):
+            overlap=False, group=None, graph=True):
     """One process per GPU (the caller has set the device and, for world > 1, initialised NCCL).  Returns a dict on
     every rank (timings are the max over ranks)."""
     import torch.distributed as dist
@@ -239,7 +240,7 @@ def measure(B=2, steps=5, warmup=2, attention="stub", n_double=4, n_single=32, w
     model = build(n_double, n_single)
     params = [p for p in model.parameters() if p.requires_grad]
     n_adapter = sum(p.numel() for p in params)
-    opt = torch.optim.AdamW(params, lr=1e-4, fused=True)
+    opt = torch.optim.AdamW(params, lr=1e-4, fused=True, capturable=graph)
     reducer = LoraGradReducer(params, bucket_bytes=8 << 20, overlap=overlap, group=group) if world > 1 else None
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     patches = torch.randn(B, N_PATCH, PATCH_IN, generator=g, device=dev, dtype=torch.bfloat16)
@@ -261,6 +262,28 @@ def measure(B=2, steps=5, warmup=2, attention="stub", n_double=4, n_single=32, w
         opt.step()
         return loss
 
+    # The whole step (forward, checkpointed backward, exchange, optimizer) as ONE CUDA graph: ~5000 launches per step
+    # leave the host (tools/host_overhead.py: 40-110 us of Python per fused-layer call, which a B=1 step cannot hide).
+    graphs, launch_mode = {}, "eager"
+
+    def capture(exchange):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step(exchange)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, capture_error_mode="thread_local"):
+            out_loss = step(exchange)
+        return gr, out_loss
+
+    def run_step(exchange=True):
+        if exchange in graphs:
+            graphs[exchange][0].replay()
+            return graphs[exchange][1]
+        return step(exchange)
+
     def timed(n, exchange=True):
         if world > 1:
             dist.barrier()
@@ -268,7 +291,7 @@ def measure(B=2, steps=5, warmup=2, attention="stub", n_double=4, n_single=32, w
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
-            loss = step(exchange)
+            loss = run_step(exchange)
         e1.record()
         if world > 1:
             dist.barrier()
@@ -280,14 +303,25 @@ def measure(B=2, steps=5, warmup=2, attention="stub", n_double=4, n_single=32, w
 
     for _ in range(max(warmup, 1)):
         step()
+    if graph:
+        try:
+            graphs[True] = capture(True)
+            if world > 1 and exposed:
+                graphs[False] = capture(False)
+            launch_mode = "cuda_graph"
+        except Exception as e:  # reported, not hidden: the eager numbers are still valid
+            print(f"[auraflow_step] CUDA graph capture failed ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
+            graphs.clear()
+            torch.cuda.synchronize()
+    run_step()
     ms, loss = timed(steps)
     ms_local = None
     if world > 1 and exposed:
         # the first timed run of a process is a few ms slower than the following ones (allocator, clocks): time the
         # exchange run on both sides of the no-exchange run and keep the faster one
-        step(False)
+        run_step(False)
         ms_local, _ = timed(steps, exchange=False)
-        step()
+        run_step()
         ms2, loss = timed(steps)
         ms = min(ms, ms2)
     flops = hot_path_flops(model, B)
@@ -299,7 +333,7 @@ def measure(B=2, steps=5, warmup=2, attention="stub", n_double=4, n_single=32, w
     res = {
         "workload": f"AuraFlow-6.8B QLoRA step, Linear skeleton ({n_double} double + {n_single} single blocks), per-GPU batch {B} at 1024^2, "
                     f"LoRA r={R} on attention+MLP projections, gradient checkpointing, fused AdamW, attention={attention}",
-        "n_gpus": world, "ms_per_step": ms, "steps_per_s": 1e3 / ms, "samples_per_s": world * B * 1e3 / ms,
+        "n_gpus": world, "launch": launch_mode, "ms_per_step": ms, "steps_per_s": 1e3 / ms, "samples_per_s": world * B * 1e3 / ms,
         "hot_path_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
         "hot_path_frac_of_sustained_bf16_peak": flops / (ms * 1e-3) / 1e12 / peak,
         "hot_path_flops_per_step_per_gpu": flops, "adapter_params": n_adapter,
@@ -325,4 +359,5 @@ if __name__ == "__main__":
     ap.add_argument("--double", type=int, default=4)
     ap.add_argument("--single", type=int, default=32)
     ap.add_argument("--overlap", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="no CUDA graph: every launch goes through Python")
     run(ap.parse_args())

@@ -97,7 +97,7 @@ class Denoiser(nn.Module):
         self.final_linear = _lin(D, PATCH_IN)
 
     def forward(self, patches, caption, c, mode="stub"):
-        run = lambda f, *a: checkpoint(f, *a, use_reentrant=False)
+        run = lambda f, *a: checkpoint(f, *a, use_reentrant=False, preserve_rng_state=False)  # no dropout; capture-safe
         cap = caption
         for blk in self.context_refiner:
             cap = run(blk, cap, c, mode)
@@ -161,12 +161,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--attention", default="stub", choices=["stub", "sdpa"])
+    ap.add_argument("--eager", action="store_true", help="no CUDA graph: every launch goes through Python")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     model = build()
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=1e-4, fused=True)
+    opt = torch.optim.AdamW(params, lr=1e-4, fused=True, capturable=not args.eager)
     g = torch.Generator(device=dev).manual_seed(1)
     B = args.batch
     patches = torch.randn(B, N_IMG, PATCH_IN, generator=g, device=dev, dtype=torch.bfloat16)
@@ -184,10 +185,34 @@ def main():
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
+    launch_mode, run = "eager", step
+    if not args.eager:  # the whole step as one CUDA graph (see tools/auraflow_step.py)
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                g_loss = step()
+
+            def run():
+                gr.replay()
+                return g_loss
+
+            launch_mode = "cuda_graph"
+        except Exception as e:
+            print(f"[lumina2_step] CUDA graph capture failed ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
+            torch.cuda.synchronize()
+            run = step
+    run()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        loss = step()
+        loss = run()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
@@ -202,7 +227,7 @@ def main():
         "workload": f"Lumina2 NextDiT-2.6B QLoRA step, Linear skeleton (26 + 2 + 2 blocks, {n_q} NF4 Linears), batch {B} at 1024^2 "
                     f"(4096 image + 256 caption tokens), LoRA r={R} on attention + feed_forward (not the noise refiner), "
                     f"gradient checkpointing, fused AdamW, attention={args.attention}",
-        "ms_per_step": ms, "steps_per_s": 1e3 / ms, "hot_path_tflops": flops / (ms * 1e-3) / 1e12,
+        "launch": launch_mode, "ms_per_step": ms, "steps_per_s": 1e3 / ms, "hot_path_tflops": flops / (ms * 1e-3) / 1e12,
         "hot_path_frac_of_sustained_bf16_peak": flops / (ms * 1e-3) / 1e12 / peak, "hot_path_flops_per_step": flops,
         "adapter_params": sum(p.numel() for p in params), "loss": float(loss.item()),
         "mem_gb": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
