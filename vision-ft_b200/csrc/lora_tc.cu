@@ -350,7 +350,7 @@ template <typename ActT, int kMode, int RP>
 static int launch_side(const CUtensorMap& m0, const CUtensorMap& v0, const CUtensorMap& m1, const CUtensorMap& v1,
                        const SidePair& pp, int64_t tiles, int64_t n_steps, cudaStream_t st) {
   auto kern = lora_side_kernel<ActT, kMode, RP>;
-  VFT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSideDyn));
+  VFT_OPT_IN_SMEM_ONCE(kern, kSideDyn);
   const int split = pick_split(kern, tiles, n_steps, sm_count());
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)tiles, (unsigned)split);

@@ -261,9 +261,11 @@ template <typename ActT, int TP>
 int launch_gemv_tp(const GemvArgs& g, int n_sm, cudaStream_t st) {
   // (two instead of three items in flight, or one accumulator per MMA instead of a chain of four, measured the same
   // 16.2-17.0 us on [18432, 3072]: neither prefetch depth nor the MMA chain is what bounds the kernel)
-  auto kern = (g.K % (64 * kKSlices * kItemBlocks) == 0) ? qlora_gemv_kernel<ActT, TP, true> : qlora_gemv_kernel<ActT, TP, false>;
+  const bool full = g.K % (64 * kKSlices * kItemBlocks) == 0;
+  auto kern = full ? qlora_gemv_kernel<ActT, TP, true> : qlora_gemv_kernel<ActT, TP, false>;
   const size_t smem = (size_t)2 * kLutBytes + sizeof(float) * kRedFloats + (size_t)(g.K / 4) * TP * 8;  // incl. alignment slack
-  VFT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (full) VFT_OPT_IN_SMEM_ONCE((qlora_gemv_kernel<ActT, TP, true>), VFT_MAX_DYN_SMEM);
+  else VFT_OPT_IN_SMEM_ONCE((qlora_gemv_kernel<ActT, TP, false>), VFT_MAX_DYN_SMEM);
   const int n_tiles = g.N / 16;
   int grid = n_tiles < n_sm ? n_tiles : n_sm;  // one CTA per SM; tiles go round-robin over CTAs first, groups second
   cudaLaunchConfig_t lc = {};

@@ -396,7 +396,7 @@ static int launch_tc(const LayerArgs& a, const void* act, void* out, const void*
   const char* dbg = getenv("VFT_TC_DEBUG");
   p.debug = dbg ? atoi(dbg) : 0;
   auto kern = qlora_tc_kernel<ActT, kBackward, BN, kPair>;
-  VFT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::dyn_bytes));
+  VFT_OPT_IN_SMEM_ONCE(kern, L::dyn_bytes);
   if (kPair) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * ceil_div64(OUT, 2 * kBM)), (unsigned)ceil_div64(a.T, BN));

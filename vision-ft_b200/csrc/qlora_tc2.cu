@@ -830,7 +830,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
   }
   const int dyn_bytes = cfg.stages * p.stage_bytes + p.n_stg * kStgBytes + kBarBytes + 1024;  // + 1024-B alignment slack
   auto kern = qlora_tc2_kernel<ActT, kBackward>;
-  VFT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_bytes));
+  VFT_OPT_IN_SMEM_ONCE(kern, VFT_MAX_DYN_SMEM);  // dyn_bytes depends on the plan: opt in to the limit
   // the fewest pairs that still finish in the same number of waves (T = 4096, 3072 features: 144 tiles -> 72 pairs
   // of 2 tiles instead of 74): identical run time, and the SMs left over stay free for a concurrent NCCL all-reduce
   // of the LoRA gradients, which otherwise delays the launch of the last cluster until it has drained

@@ -89,6 +89,22 @@ __device__ __forceinline__ float round_through(float v, int qdtype) {
 
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Opt a kernel instantiation in to large dynamic shared memory ONCE per device instead of on every launch (the call is
+// ~1 us of host time, and host time per layer call is what bounds small-batch steps).  `bytes` is the most the
+// instantiation will ever ask for; each expansion site owns its flag word (one bit per device ordinal).
+#define VFT_MAX_DYN_SMEM 232448 /* 227 KB: the per-block opt-in limit of sm_100 */
+#define VFT_OPT_IN_SMEM_ONCE(kern, bytes)                                                                  \
+  do {                                                                                                     \
+    static unsigned long long _vft_done = 0;                                                               \
+    int _vft_dev = 0;                                                                                      \
+    cudaGetDevice(&_vft_dev);                                                                              \
+    const unsigned long long _vft_bit = 1ull << (_vft_dev & 63);                                           \
+    if (!(__atomic_load_n(&_vft_done, __ATOMIC_RELAXED) & _vft_bit)) {                                     \
+      VFT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));  \
+      __atomic_fetch_or(&_vft_done, _vft_bit, __ATOMIC_RELAXED);                                           \
+    }                                                                                                      \
+  } while (0)
+
 // programmatic dependent launch of the fused kernels (VFT_PDL=0 switches it off for triage)
 bool pdl_enabled();
 

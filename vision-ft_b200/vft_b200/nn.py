@@ -313,22 +313,35 @@ class Linear4bit(nn.Linear):
             return x.to(self.compute_dtype)
         return x
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def _operands(self):
+        """(packed, fp32 absmax, blocksize, quant dtype, tiled copy) of the current weight, resolved once per
+        (weight storage, quant state) and then served from a single cache hit: this runs in every forward, and
+        host time per call is what bounds small-batch steps (tools/host_overhead.py)."""
+        w = self.weight
+        cache = self.__dict__.get("_vft_operands")
+        if cache is not None and cache[0] is w and cache[1] == w.data_ptr():
+            return cache[2]
         packed, qs = self._packed()
+        ops_ = (packed, qs.absmax_f32(), qs.blocksize, qs.dtype, self._tiled(packed, qs))
+        self.__dict__["_vft_operands"] = (w, w.data_ptr(), ops_)
+        return ops_
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        packed, absmax, blocksize, qdtype, tiled = self._operands()
         inp_dtype = x.dtype
         x = self._cast_input(x)
-        out = ops.qlora_linear(x, packed, qs.absmax_f32(), self.bias, None, None, 0.0, self.out_features, self.in_features,
-                               qs.blocksize, qs.dtype, self._tiled(packed, qs))
-        return out.to(inp_dtype)
+        out = ops.qlora_linear(x, packed, absmax, self.bias, None, None, 0.0, self.out_features, self.in_features,
+                               blocksize, qdtype, tiled)
+        return out if out.dtype == inp_dtype else out.to(inp_dtype)
 
     def forward_with_lora(self, x: torch.Tensor, lora_a: torch.Tensor, lora_b: torch.Tensor, scale: float) -> torch.Tensor:
         """One fused kernel sequence for base + adapter (used by LoRALinear)."""
-        packed, qs = self._packed()
+        packed, absmax, blocksize, qdtype, tiled = self._operands()
         inp_dtype = x.dtype
         x = self._cast_input(x)
-        out = ops.qlora_linear(x, packed, qs.absmax_f32(), self.bias, lora_a, lora_b, scale, self.out_features,
-                               self.in_features, qs.blocksize, qs.dtype, self._tiled(packed, qs))
-        return out.to(inp_dtype)
+        out = ops.qlora_linear(x, packed, absmax, self.bias, lora_a, lora_b, scale, self.out_features,
+                               self.in_features, blocksize, qdtype, tiled)
+        return out if out.dtype == inp_dtype else out.to(inp_dtype)
 
     def _save_to_state_dict(self, destination, prefix, keep_vars):
         super()._save_to_state_dict(destination, prefix, keep_vars)
