@@ -182,3 +182,14 @@ def test_nested_seeded_3072_hashes(golden_dir, dt_name, dt):
     assert _sha(q) == ref["nested_absmax8_sha256"] and _sha(a2) == ref["nested_absmax2_sha256"]
     assert float(off) == ref["nested_offset"]
     assert _sha(nf4_oracle.absmax_denest(q, a2, off, code)) == ref["denested_absmax_sha256"]
+
+
+def test_product_dynamic_map_matches_oracle():
+    """vft_b200.nn.create_dynamic_map (the product's host-side table, what lands in ``nested_quant_map``) against the
+    oracle's restatement of bitsandbytes.functional.create_dynamic_map -- two independent writings of the same table."""
+    from vft_b200.nn import create_dynamic_map
+
+    m = create_dynamic_map()
+    assert m.dtype == torch.float32 and np.array_equal(m.numpy(), nf4_oracle.dynamic_map())
+    m[0] = 123.0  # callers get a private copy of the cached table
+    assert create_dynamic_map()[0] == np.float32(-0.99296874)
