@@ -441,9 +441,9 @@ def run_gpu_arm(args):
         roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": UNIT,
                 "frac": achieved / peaks["bf16_tflops"],
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
-                # kernel (profiles/r01_ncu_pair_kernel_v7.txt: 30.5 MB read + 0.2 MB written; the 25 MB of output
+                # kernel (profiles/r01_ncu_pair_kernel_final.txt: 30.5 MB read + 0.3-0.7 MB written; the 25 MB of output
                 # stay in the 126 MB L2 past the end of the launch).  Algorithmic minimum x + y + packed W: 55.9 MB.
-                "traffic": 30.7e6, "traffic_source": "ncu dram bytes per launch (read + write), profiles/r01_ncu_pair_kernel_v7.txt",
+                "traffic": 31.0e6, "traffic_source": "ncu dram bytes per launch (read + write, mean of forward and backward), profiles/r01_ncu_pair_kernel_final.txt",
                 "peak_source": peaks["source"] + ", burst",
                 "kernel": "qlora_tc2_kernel (persistent CTA-pair tcgen05 GEMM; forward + backward launches)",
                 "fwd_us": t_f * 1e3, "bwd_us": t_b * 1e3, "flops_per_launch": flops_launch}
