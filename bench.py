@@ -11,9 +11,15 @@ forward+backward pass of that layer over one batch of synthetic activations.
   roofline  the dominant kernel (fused NF4-decode tcgen05 GEMM, forward + backward launches) timed alone
   cpu_baseline  the oracle port (oracle/qlora_oracle.py) on the host cores, bounded sample, rank 0 at N=1 only
 
+  extra     rank 0: NF4 quantize/pack GB/s; few-token (T = 2) weight-stream GB/s, HBM-cold; the layer census of an
+            AuraFlow step (N = 1).  All ranks: `auraflow_qlora_step_dp`, the AuraFlow-6.8B QLoRA step harness
+            (tools/auraflow_step.py: steps/s, samples/s, exposed all-reduce time) -- the second half of BASELINE's metric.
+
 `--impl reference` times the reference's CPU path for the same layer (the oracle port: bitsandbytes itself is
 not installable here) on the host cores.  Multi-GPU: weak scaling, each rank steps its own 4096 tokens and the
-LoRA gradients are all-reduced over NCCL on a side stream, overlapped with the next step.
+LoRA gradients are all-reduced over NCCL on a side stream through a 2-CTA communicator (the fused GEMM is a
+persistent kernel on 72 of the 74 SM pairs: a collective that holds more SMs costs it a wave; measurements in
+DESIGN.md section 5), overlapped with the next step.  stdout carries exactly one JSON line.
 """
 from __future__ import annotations
 
