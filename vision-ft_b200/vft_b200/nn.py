@@ -313,6 +313,13 @@ class Linear4bit(nn.Linear):
             return x.to(self.compute_dtype)
         return x
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .cpu() replace the weight: the derived device buffers (micro-tiled copy, decoded
+        # statistics) of the old one must not outlive it
+        self.__dict__.pop("_vft_operands", None)
+        self.__dict__.pop("_vft_tiled", None)
+        return super()._apply(fn, *args, **kwargs)
+
     def _operands(self):
         """(packed, fp32 absmax, blocksize, quant dtype, tiled copy) of the current weight, resolved once per
         (weight storage, quant state) and then served from a single cache hit: this runs in every forward, and
