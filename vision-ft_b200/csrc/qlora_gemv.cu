@@ -336,10 +336,29 @@ qlora_gemv_tma_kernel(const __grid_constant__ CUtensorMap map_codes, const __gri
     for (int i = 0; i < kRing && i < n_items; ++i) issue(i);
   }
 
+  // ---- x: the first units of every thread leave for L2 now and are stored after the table is built (their latency
+  // hides under the table build); unit u = ((blk*4 + j)*4 + t)*TP + g  <-  x[g][blk*64 + 16t + 4j .. +3]
+  constexpr int kPre = 4;
+  const ActT* xsrc = static_cast<const ActT*>(a.x);
+  const int units = (K / 4) * TP;
+  auto x_unit = [&](int u) {
+    const int gg = u % TP, q = u / TP;
+    const int tt = q & 3, jj = (q >> 2) & 3, bb = q >> 4;
+    uint2 v = make_uint2(0u, 0u);
+    if (gg < a.T) v = __ldg(reinterpret_cast<const uint2*>(xsrc + (size_t)gg * K + bb * 64 + 16 * tt + 4 * jj));
+    return v;
+  };
+  uint2 xpre[kPre];
+#pragma unroll
+  for (int i = 0; i < kPre; ++i) {
+    const int u = (int)threadIdx.x + i * kTmaThreads;
+    xpre[i] = u < units ? x_unit(u) : make_uint2(0u, 0u);
+  }
+
   // ---- byte -> (code[hi nibble], code[lo nibble]) pairs in ActT, one copy per lane
   {
     constexpr float kCode[16] = VFT_NF4_CODEBOOK;
-    float* s_code = reinterpret_cast<float*>(xs);  // scratch: x is staged after the table is built
+    float* s_code = reinterpret_cast<float*>(red);  // scratch: the reduction buffer is first used after a barrier
     if (threadIdx.x < 16) {
       float v = 0.0f;
 #pragma unroll
@@ -351,21 +370,13 @@ qlora_gemv_tma_kernel(const __grid_constant__ CUtensorMap map_codes, const __gri
       const int v = e >> 5;
       lut[e] = pack2<ActT>(s_code[v >> 4], s_code[v & 15]);
     }
-    __syncthreads();
   }
-  // ---- stage x in fragment order (same layout as the register-fed kernel)
-  {
-    const ActT* x = static_cast<const ActT*>(a.x);
-    const int units = (K / 4) * TP;
-#pragma unroll 4
-    for (int u = threadIdx.x; u < units; u += kTmaThreads) {
-      const int gg = u % TP, q = u / TP;
-      const int tt = q & 3, jj = (q >> 2) & 3, bb = q >> 4;
-      uint2 v = make_uint2(0u, 0u);
-      if (gg < a.T) v = __ldg(reinterpret_cast<const uint2*>(x + (size_t)gg * K + bb * 64 + 16 * tt + 4 * jj));
-      xs[u] = v;
-    }
+#pragma unroll
+  for (int i = 0; i < kPre; ++i) {
+    const int u = (int)threadIdx.x + i * kTmaThreads;
+    if (u < units) xs[u] = xpre[i];
   }
+  for (int u = (int)threadIdx.x + kPre * kTmaThreads; u < units; u += kTmaThreads) xs[u] = x_unit(u);
   __syncthreads();
 
   float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
