@@ -544,9 +544,9 @@ def run_gpu_arm(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            r = time_cpu(256, 3, 1)
+            r = time_cpu(512, 8, 1)  # ~10 s of host work on the box's cores
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                   "sample": f"256 of {TOKENS} tokens, 1 warm-up + 3 runs of the oracle port (dequant + F.linear + LoRA, autograd)"}
+                   "sample": f"512 of {TOKENS} tokens, 1 warm-up + 8 runs of the oracle port (dequant + F.linear + LoRA, autograd)"}
         kernels_per_step = 5  # lora_side<x.A^T>, qlora_tc2<fwd> | lora_side<dy.B>, qlora_tc2<bwd>, lora_side<dA,dB>
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
