@@ -10,9 +10,11 @@
  * Conventions
  *   - plain C, no torch types: raw DEVICE pointers + sizes + an explicit
  *     cudaStream_t passed as void* (NULL = legacy default stream);
- *   - nothing is allocated, nothing is freed, no global state; every buffer
- *     (outputs, saved LoRA activations, workspace) belongs to the caller and is
- *     borrowed for the duration of the call on the given stream;
+ *   - nothing is allocated, nothing is freed; every buffer (outputs, saved LoRA
+ *     activations, workspace) belongs to the caller and is borrowed for the
+ *     duration of the call on the given stream.  The only process-wide state is
+ *     the triage switches at the end of this header (forced kernel family,
+ *     VFT_* environment variables read once at first use);
  *   - re-entrant and callable from any host thread (autograd worker threads call
  *     the backward entry points); the current CUDA device is the caller's;
  *   - every function returns 0 on success or a negative vft_status; the message
@@ -63,6 +65,11 @@ const char* vft_last_error(void);
 int vft_last_path(void);
 /* Force a kernel family for subsequent calls, process-wide (tests/bench): 0 = auto. */
 void vft_force_path(int path);
+/* Triage (tests / profiling tools, not thread-safe): re-read the VFT_* environment switches, which are otherwise
+ * read once per process; SM-clock timelines of the last launch made with VFT_TC_DEBUG & 16 (rows x 256 / 16 stamps). */
+void vft_reload_env(void);
+int vft_debug_tc2_timeline(unsigned long long* out, int n);
+int vft_debug_side_timeline(unsigned long long* out, int n);
 
 /* NF4 quantize/pack.  Replaces bitsandbytes.functional.quantize_4bit(quant_type="nf4")
  * as called at /root/reference/src/modules/quant/functional.py:362-365 and, lazily, by

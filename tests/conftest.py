@@ -25,6 +25,33 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture
+def vft_env():
+    """Set VFT_* triage switches for one test: the library reads its environment once per process, so every change
+    is followed by vft_reload_env(); the previous values are restored (and re-read) afterwards."""
+    from vft_b200 import _cabi
+
+    saved = {}
+
+    def set_env(**kv):
+        for k, v in kv.items():
+            if k not in saved:
+                saved[k] = os.environ.get(k)
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+        _cabi.lib.vft_reload_env()
+
+    yield set_env
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+    _cabi.lib.vft_reload_env()
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")

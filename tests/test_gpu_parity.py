@@ -276,10 +276,8 @@ def test_identity_activation_reproduces_weight_bit_exact(ops, N, K, tiled):
 @pytest.mark.parametrize("tiled", [False, True])
 @pytest.mark.parametrize("nacc", ["1x32", "2x48", "1x176", "2x176", "1x256", "2x256", "auto"])
 @pytest.mark.parametrize("T,K,N,r,bias", [(700, 256, 640, 16, True), (1300, 192, 384, 0, False), (333, 64, 136, 8, False)])
-def test_pair_kernel_forced_tiles(ops, monkeypatch, nacc, T, K, N, r, bias, tiled):
-    monkeypatch.setenv("VFT_TC2", "1")
-    if nacc != "auto":
-        monkeypatch.setenv("VFT_TC2_NACC", nacc)
+def test_pair_kernel_forced_tiles(ops, vft_env, nacc, T, K, N, r, bias, tiled):
+    vft_env(VFT_TC2="1", VFT_TC2_NACC=None if nacc == "auto" else nacc)
     w, x, dy, a, b, bv = _make_case(T, K, N, r, seed=T + K + N + r, bias=bias)
     p, am = nf4_oracle.nf4_quantize(w)
     w_deq = qlora_oracle.dequant_weight(p, am, (N, K), "bfloat16")
@@ -291,12 +289,53 @@ def test_pair_kernel_forced_tiles(ops, monkeypatch, nacc, T, K, N, r, bias, tile
     _check(out, ref, truth, ("y", "dx") + (("da", "db") if r else ()), f"pair{nacc}-T{T}K{K}N{N}r{r}")
 
 
+# Fused down-projection (t = x . A^T inside the forward GEMM launch, qlora_tc2.cu): forced on (VFT_TC2_FUSE=1: never
+# split the contraction) over tile shapes that put the side product in every TMEM position -- the tail of one pitch,
+# of both pitches (more than 128 staged rows per CTA), above a single accumulator -- on ragged token counts, with the
+# reference's shipped rank 4, rank 16 and a rank that needs 32 padded columns; and forced off, where the side kernel
+# of lora_tc.cu must give the same t_save up to summation order.
+@pytest.mark.parametrize("nacc", ["1x32", "2x48", "1x176", "2x160", "2x176", "1x256", "auto"])
+@pytest.mark.parametrize("T,K,N,r,bias", [(700, 256, 640, 16, True), (333, 64, 264, 4, False), (1500, 320, 512, 24, False),
+                                           (4096, 192, 768, 16, False)])
+def test_pair_kernel_fused_down_projection(ops, vft_env, nacc, T, K, N, r, bias):
+    w, x, dy, a, b, bv = _make_case(T, K, N, r, seed=T + K + N + r, bias=bias)
+    p, am = nf4_oracle.nf4_quantize(w)
+    w_deq = qlora_oracle.dequant_weight(p, am, (N, K), "bfloat16")
+    ref = qlora_oracle.qlora_linear_ref(x, w_deq, bv, a, b, 1.0, dy)
+    truth = qlora_oracle.qlora_linear_truth(x, w_deq, bv, a, b, 1.0, dy)
+    packed, absmax = torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda()
+    t_saves = []
+    for fuse in ("1", "0"):
+        vft_env(VFT_TC2="1", VFT_TC2_FUSE=fuse, VFT_TC2_NACC=None if nacc == "auto" else nacc)
+        out, used = _run_cuda(ops, packed, absmax, x, dy, a, b, bv, 1.0, N, K, torch.bfloat16, TC, tiled=True)
+        assert used == TC
+        _check(out, ref, truth, ("y", "dx", "da", "db"), f"fused{fuse}-{nacc}-T{T}K{K}N{N}r{r}")
+        # t_save itself, through the C ABI: [T, 64], columns >= r exactly zero
+        ops.force_path(TC)
+        xc, ac, bc = x.cuda(), a.cuda(), b.cuda()
+        y = torch.empty(T, N, dtype=torch.bfloat16, device="cuda")
+        t_save = torch.full((T, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+        tiles = ops.nf4_tile_weight(packed, absmax, N, K)
+        from vft_b200 import _cabi
+        _cabi.check(_cabi.lib.vft_qlora_fwd(xc.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, _cabi.BF16,
+                                            _cabi.BF16, None, ac.data_ptr(), bc.data_ptr(), r, 1.0 / r, y.data_ptr(),
+                                            t_save.data_ptr(), None, 0, tiles[0].data_ptr(), tiles[1].data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        ops.force_path(0)
+        t_saves.append(t_save.float().cpu())
+    t_truth = x.double() @ a.double().t()
+    rp = 16 * ((r + 15) // 16)  # columns [r, rp) are exact zeros; nothing reads (or has to write) the ones behind
+    for ts in t_saves:
+        assert torch.all(ts[:, r:rp] == 0), "t_save padding columns must be exact zeros"
+        assert qlora_oracle.rel_l2(ts[:, :r], t_truth) <= 3e-3
+    assert qlora_oracle.max_abs(t_saves[0][:, :rp], t_saves[1][:, :rp]) <= 2 * BF16_ULP * float(t_truth.abs().max())
+
+
 @pytest.mark.parametrize("stages", ["4", "5", "8"])
-def test_pair_kernel_many_tiles_per_pair(ops, monkeypatch, stages):
+def test_pair_kernel_many_tiles_per_pair(ops, vft_env, stages):
     """More tiles than SM pairs with a tiny tile (1x32): every pair walks several tiles, ring phases wrap many times."""
-    monkeypatch.setenv("VFT_TC2", "1")
-    monkeypatch.setenv("VFT_TC2_NACC", "1x32")
-    monkeypatch.setenv("VFT_TC2_STAGES", stages)
+    vft_env(VFT_TC2="1", VFT_TC2_NACC="1x32", VFT_TC2_STAGES=stages)
     N, K, T = 1024, 320, 2500
     g = torch.Generator(device="cuda").manual_seed(5)
     w = (torch.randn(N, K, generator=g, device="cuda") * 0.02).to(torch.bfloat16)

@@ -19,13 +19,18 @@ def main():
     y = torch.empty(T, N, device=dev, dtype=torch.bfloat16)
     dx = torch.empty(T, K, device=dev, dtype=torch.bfloat16)
     st = torch.cuda.current_stream().cuda_stream
+    r = int(os.environ.get("R", "0"))
+    A = (torch.randn(max(r, 1), K, device=dev) * 0.02).to(torch.bfloat16)
+    B = (torch.randn(N, max(r, 1), device=dev) * 0.02).to(torch.bfloat16)
+    ts = torch.empty(T, 64, device=dev, dtype=torch.bfloat16)
+    AP, BP, TS = (A.data_ptr(), B.data_ptr(), ts.data_ptr()) if r else (None, None, None)
     WFB = _cabi.lib.vft_workspace_bytes(0, T, N, K, 0); WBB = _cabi.lib.vft_workspace_bytes(1, T, N, K, 0)
     wf_t = torch.empty(max(WFB, 4), dtype=torch.uint8, device=dev); wb_t = torch.empty(max(WBB, 4), dtype=torch.uint8, device=dev)
     WF = wf_t.data_ptr() if WFB else None; WB = wb_t.data_ptr() if WBB else None
     def fwd(i):
-        _cabi.check(_cabi.lib.vft_qlora_fwd(xs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, None, 0, 0.0, y.data_ptr(), None, WF, WFB, TC, TA, st))
+        _cabi.check(_cabi.lib.vft_qlora_fwd(xs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, AP, BP, r, 1.0 / max(r, 1), y.data_ptr(), TS, WF, WFB, TC, TA, st))
     def bwd(i):
-        _cabi.check(_cabi.lib.vft_qlora_bwd_dx(gs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, 0, 0.0, dx.data_ptr(), None, WB, WBB, TC, TA, st))
+        _cabi.check(_cabi.lib.vft_qlora_bwd_dx(gs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, AP, BP, r, 1.0 / max(r, 1), dx.data_ptr(), TS, WB, WBB, TC, TA, st))
     res = {}
     for name, fn in (("fwd", fwd), ("bwd", bwd)):
         for i in range(5): fn(i)
@@ -56,12 +61,12 @@ def main():
             def rel(v): return (v - t0) if v else -1
             print(f"  [{nm}] pair-kernel timeline (cycles since first producer wait), leader CTA of pair 0")
             print("   step: mma_full_seen  mma_commit   | prod_empty_seen")
-            for g in list(range(0, 12)) + list(range(40, 56)):
+            for g in list(range(0, 12)) + list(range(40, 56)) + list(range(90, 100)):
                 print(f"   {g:4d}: {rel(rows[0][g]):10d} {rel(rows[1][g]):10d}   | {rel(rows[5][g]):10d}")
             print("   decode group0 (steps 0,4,8..): empty_seen, stores issued, arrived")
             for i in list(range(0, 6)) + list(range(10, 14)):
                 print(f"   {4*i:4d}: {rel(rows[2][i]):10d} {rel(rows[6][i]):10d} {rel(rows[3][i]):10d}")
-            print("   epilogue: acc_full seen / drained per tile:", [rel(v) for v in rows[4][:6]])
+            print("   epilogue per tile (t_full seen, t box written, acc_full seen, drained):", [rel(v) for v in rows[4][:12]])
             steps = [v for v in rows[0] if v]
             if len(steps) > 20:
                 d = [steps[i + 1] - steps[i] for i in range(8, len(steps) - 1)]

@@ -326,8 +326,7 @@ static int max_active_clusters(Kern kern, int split) {
 
 template <typename Kern>
 static int pick_split(Kern kern, int64_t tiles, int64_t n_steps, int n_sm) {
-  if (const char* e = getenv("VFT_SIDE_SPLIT")) {  // triage override
-    const int s = atoi(e);
+  if (const int s = env().side_split) {  // triage override
     if (s >= 1 && s <= kMaxSplit) return s <= n_steps ? s : 1;
   }
   static int cap[5] = {0, -1, -1, -1, -1};  // per kernel instantiation: clusters of size S that fit at once
@@ -402,7 +401,7 @@ static int rowproj_tc(const void* M, const void* V, int64_t T, int64_t C, int r,
   pp.p[0] = SideParams{T, C, r, scale, out, 0};
   pp.p[1] = pp.p[0];
   pp.tiles_first = 0x7fffffff;
-  pp.debug = getenv("VFT_TC_DEBUG") ? atoi(getenv("VFT_TC_DEBUG")) : 0;
+  pp.debug = env().tc_debug;
   const int64_t tiles = ceil_div64(T, kTile);
   return launch_side_rank<ActT, kMode>(mm, mv, mm, mv, pp, tiles, ceil_div64(C, kStep), r, st);
 }
@@ -427,7 +426,7 @@ static int dab_tc(const void* dy, const void* x, const void* t_save, const void*
   pp.p[0] = SideParams{T, K, r, 1.0f, dA, 1};   // dA[j, k] = sum_t dt[t, j] x[t, k]   (dt already carries s)
   pp.p[1] = SideParams{T, N, r, scale, dB, 0};  // dB[n, j] = s * sum_t dy[t, n] t[t, j]
   pp.tiles_first = (int)ceil_div64(K, kTile);
-  pp.debug = getenv("VFT_TC_DEBUG") ? atoi(getenv("VFT_TC_DEBUG")) : 0;
+  pp.debug = env().tc_debug;
   const int64_t tiles = ceil_div64(K, kTile) + ceil_div64(N, kTile);
   return launch_side_rank<ActT, kCol>(mx, mdt, mdy, mt, pp, tiles, ceil_div64(T, kStep), r, st);
 }

@@ -486,7 +486,7 @@ int launch_gemv_tma(const GemvArgs& g, int n_sm, cudaStream_t st) {
 
 template <typename ActT, int TP>
 int launch_gemv_tp(const GemvArgs& g, int n_sm, cudaStream_t st) {
-  static const int use_tma = getenv("VFT_GEMV_TMA") ? atoi(getenv("VFT_GEMV_TMA")) : 1;  // triage switch
+  const int use_tma = env().gemv_tma;  // triage switch
   if (use_tma && g.K % (64 * kKSlices * kItemBlocks) == 0 && gemv_tma_smem(g.K, TP) <= VFT_MAX_DYN_SMEM &&
       (reinterpret_cast<uintptr_t>(g.absmax) & 15u) == 0)
     return launch_gemv_tma<ActT, TP>(g, n_sm, st);

@@ -393,8 +393,7 @@ static int launch_tc(const LayerArgs& a, const void* act, void* out, const void*
   p.bias = kBackward ? nullptr : a.bias;
   p.lora_w = kBackward ? a.lora_a : a.lora_b;
   p.out = out;
-  const char* dbg = getenv("VFT_TC_DEBUG");
-  p.debug = dbg ? atoi(dbg) : 0;
+  p.debug = env().tc_debug;
   auto kern = qlora_tc_kernel<ActT, kBackward, BN, kPair>;
   VFT_OPT_IN_SMEM_ONCE(kern, L::dyn_bytes);
   if (kPair) {
@@ -424,8 +423,7 @@ static int launch_tc_bn(const LayerArgs& a, const void* act, void* out, const vo
   const int64_t OUT = kBackward ? a.K : a.N;
   // Measured on B200 (T=4096, 3072x3072): 86.8 us with the pair vs 83.2 us without -- this kernel is bound by the
   // decode warps' ALU work, not by shared-memory bandwidth, so pairing alone buys nothing.  Opt-in for triage.
-  const char* pair = getenv("VFT_TC_PAIR");
-  if (a.T > 128 && OUT >= 2 * kBM && pair && pair[0] == '1')
+  if (a.T > 128 && OUT >= 2 * kBM && env().tc_pair)
     return launch_tc<ActT, kBackward, 256, true>(a, act, out, lora_act, st);
   if (a.T > 128) return launch_tc<ActT, kBackward, 256, false>(a, act, out, lora_act, st);
   if (a.T > 64) return launch_tc<ActT, kBackward, 128, false>(a, act, out, lora_act, st);
@@ -456,7 +454,11 @@ bool tc_supported(const LayerArgs& a, bool backward) {
   return true;
 }
 
-int tc_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st) {
+bool tc_fuses_down(const LayerArgs& a) {
+  return tc_supported(a, false) && aligned16(a.lora_a) && tc2_fuses_down(a);
+}
+
+int tc_fwd(const LayerArgs& a, const void* x, void* y, void* t_save, cudaStream_t st) {
   if (!aligned16(x)) { set_error("x must be 16-byte aligned for the TMA path"); return VFT_ERR_INVALID; }
   if (tc2_preferred(a, false)) return tc2_fwd(a, x, y, t_save, st);
   if (a.act_dtype == VFT_BF16) return launch_tc_bn<__nv_bfloat16, false>(a, x, y, t_save, st);

@@ -52,11 +52,12 @@ constexpr int kAllocWarp = kEpiWarp0 + 5;       // warp 21: TMEM allocation
 constexpr int kStoreWarp = kEpiWarp0 + 6;       // warp 22: issues the TMA stores of the staged output tiles
 constexpr int kMmaWarp = kEpiWarp0 + 7;         // warp 23: MMA issuer
 constexpr int kThreads = (kEpiWarp0 + 8) * 32;  // 768
-// registers per thread after the role split (launch: 80 x 768): 4 x 128 x (88 - 80) <= 128 x (80 - 40) + 128 x (80 - 72)
-constexpr int kCtrlRegs = 40, kEpiRegs = 72, kDecRegs = 88;
+// registers per thread after the role split (launch: 80 x 768): 5 x 128 x (88 - 80) <= 128 x (80 - 40)
+constexpr int kCtrlRegs = 40, kEpiRegs = 88, kDecRegs = 88;
 constexpr int kATileBytes = kBM * kBK * 2;                // 16 KB decoded weight tile
 constexpr int kMaxStages = 8;
 constexpr int kMaxAcc = 2;
+constexpr int kMaxFuseRP = 32;  // largest padded rank whose down-projection is fused into the forward launch
 // TMEM columns.  Backward (weights staged in shared memory): two accumulators of up to 256 columns.  Forward
 // (kTmemA): the decoded weight tile itself lives in tensor memory -- 4 ring stages of 32 columns (64 16-bit values
 // per lane) above two accumulators of up to 192 columns -- so it costs no shared-memory bandwidth at all: the
@@ -72,7 +73,7 @@ struct AccLayout {
 constexpr int kTmemCols = 512;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kMaxStg = 16;  // output staging tiles
-constexpr int kBarBytes = (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg) * 8 + 16;
+constexpr int kBarBytes = (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg + 2) * 8 + 16;
 constexpr int kStgBytes = 32 * kBM * 2;  // one staging tile [32 tokens][128 features] of 16-bit outputs (8 KB)
 constexpr int kEpiBytes = 2 * kStgBytes;  // the minimum: two tiles
 
@@ -102,6 +103,15 @@ struct Tc2Params {
   float* partial;
   int debug;        // VFT_TC_DEBUG triage mask (results are garbage when non-zero): 1 = no decode stores,
                     // 2 = no MMAs, 4 = no epilogue stores, 8 = no TMA loads
+  // Fused adapter down-projection (forward, n_split == 1): t = x . A^T is accumulated next to the main product by one
+  // extra tcgen05.mma per 128 staged token rows and ring step (M = token rows of the pair, N = r_pad, A operand =
+  // the activation box that is in shared memory anyway, B operand = a [r_pad/2 x 64] box of lora_down.weight per
+  // CTA) into spare TMEM columns; at the end of the tile's contraction the epilogue warps round it to the
+  // activation dtype and write it into the adapter step's activation box (and, feature block 0 only, to t_save).
+  int fuse;         // 0: the adapter step TMA-loads t_save / dt_save written by a side kernel
+  int r_pad;        // 16, 32 or 64: MMA N of the side product
+  int la_bytes;     // bytes of one CTA's lora_down box: (r_pad / 2) * 128
+  void* save;       // t_save [T, VFT_LORA_LD] (written when fuse)
 };
 
 // Timeline of the leader CTA of pair 0 for performance triage (VFT_TC_DEBUG & 16): SM clock per event.
@@ -109,6 +119,14 @@ constexpr int kTlRows = 7, kTlCols = 256;
 __device__ unsigned long long g_tc2_timeline[kTlRows * kTlCols];
 __device__ __forceinline__ void tl_mark(const Tc2Params& p, int row, int col) {
   if ((p.debug & 16) && blockIdx.x == 0 && col < kTlCols) g_tc2_timeline[row * kTlCols + col] = (unsigned long long)clock64();
+}
+
+// Pin a loop-invariant address in a register: without it the compiler rebuilds shared-memory addresses from the
+// cluster/CTA special registers and the kernel parameters inside the hot loops (chains of S2UR / LDCU / ULEA with
+// their latencies in series, ~150 cycles per barrier operation in the accumulator drain).
+__device__ __forceinline__ uint32_t pinned(uint32_t v) {
+  asm volatile("mov.b32 %0, %0;" : "+r"(v));
+  return v;
 }
 
 __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
@@ -125,6 +143,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out16,
                  const Tc2Params p) {
   constexpr bool kTmemA = !kBackward;  // forward: decoded weights go to tensor memory, backward: shared memory
+  constexpr bool kFuse = !kBackward;   // the fused side product (p.fuse) exists in the forward kernel only
   constexpr int kAccCols = AccLayout<kTmemA>::pitch;
   constexpr int kAOff = kTmemA ? 0 : kATileBytes;  // offset of the activation boxes inside a stage
   extern __shared__ uint8_t smem_raw[];
@@ -153,11 +172,21 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   // output staging tiles: full[b] (the four epilogue warps have written tile b) / empty[b] (its TMA store has read it)
   auto bar_stg_full = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc + b); };
   auto bar_stg_empty = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc + kMaxStg + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg);
+  // fused down-projection: t_full (the tile's side product is complete in TMEM; multicast commit) and, on the leader,
+  // t_box (the epilogue warps of both CTAs have written the adapter step's activation box)
+  const uint32_t bar_t_full = bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg);
+  const uint32_t bar_t_box = bar_t_full + 8u;
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg + 2);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
-      smem_gen + S * p.stage_bytes + epi_bytes + 8 * (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg));
+      smem_gen + S * p.stage_bytes + epi_bytes + 8 * (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg + 2));
   auto stage_a = [&](int s) { return smem_base + (uint32_t)(s * p.stage_bytes); };
   auto stage_b = [&](int s, int a) { return smem_base + (uint32_t)(s * p.stage_bytes + kAOff + a * p.b_bytes); };
+  auto stage_la = [&](int s) { return stage_b(s, p.n_acc); };  // lora_down box behind the activation boxes
+  // TMEM columns of the side product of staged-row group g (128 token rows per CTA each): the tail of accumulator g's
+  // pitch (n_acc == 2: N_acc <= pitch - r_pad) or, with one accumulator, the columns below the weight ring
+  auto t_col = [&](int g) -> uint32_t {
+    return (uint32_t)(p.n_acc == 2 ? (g + 1) * kAccCols - p.r_pad : 2 * kAccCols - p.r_pad);
+  };
   // accumulators of a tile that hold at least one real token (all roles derive it the same way)
   auto accs_of = [&](int64_t t0) -> int {
     const int64_t left = p.T - t0;
@@ -186,6 +215,8 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       ptx::mbar_init(bar_empty(s), 1);         // multicast tcgen05.commit
     }
     ptx::mbar_init(bar_acc_full, 1);
+    ptx::mbar_init(bar_t_full, 1);
+    ptx::mbar_init(bar_t_box, 2 * 4);  // epilogue warps of both CTAs
     for (int a = 0; a < kMaxAcc; ++a) ptx::mbar_init(bar_acc_empty(a), 2 * 4);  // epilogue warps of both CTAs
     for (int b = 0; b < p.n_stg; ++b) {
       ptx::mbar_init(bar_stg_full(b), 4);   // one arrive per epilogue warp
@@ -229,14 +260,21 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             if (rank == 0) ptx::mbar_arrive(bar_full(s));
           } else {
             // the leader arms its barrier for the bytes of BOTH CTAs; each CTA loads its N_acc/2 token rows
-            if (rank == 0) ptx::mbar_arrive_expect_tx(bar_full(s), (uint32_t)(2 * na * p.b_bytes));
-            const uint32_t leader_bar = ptx::mapa(bar_full(s), 0);
-            for (int a = 0; a < na; ++a) {
-              const int trow = (int)(t0 + (int64_t)a * p.N_acc) + (int)rank * (p.N_acc >> 1);
-              if (b < n_main)
-                ptx::tma_load_2d_pair(&map_act, stage_b(s, a), leader_bar, b * kBK, trow);
-              else
-                ptx::tma_load_2d_pair(&map_lora, stage_b(s, a), leader_bar, 0, trow);
+            if (kFuse && p.fuse && b == n_main) {  // the epilogue warps fill the adapter step's boxes themselves
+              if (rank == 0) ptx::mbar_arrive(bar_full(s));
+            } else {
+              const int la = (kFuse && p.fuse && b < n_main) ? p.la_bytes : 0;
+              if (rank == 0) ptx::mbar_arrive_expect_tx(bar_full(s), (uint32_t)(2 * (na * p.b_bytes + la)));
+              const uint32_t leader_bar = ptx::mapa(bar_full(s), 0);
+              for (int a = 0; a < na; ++a) {
+                const int trow = (int)(t0 + (int64_t)a * p.N_acc) + (int)rank * (p.N_acc >> 1);
+                if (b < n_main)
+                  ptx::tma_load_2d_pair(&map_act, stage_b(s, a), leader_bar, b * kBK, trow);
+                else
+                  ptx::tma_load_2d_pair(&map_lora, stage_b(s, a), leader_bar, 0, trow);
+              }
+              // rows [rank * r_pad/2, +r_pad/2) of lora_down.weight (rows >= r: zero fill), contraction block b
+              if (la) ptx::tma_load_2d_pair(&map_lora, stage_la(s), leader_bar, b * kBK, (int)rank * (p.r_pad >> 1));
             }
           }
           if (++s == S) {
@@ -261,8 +299,10 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       constexpr uint32_t kBStep = 32u >> 4;
       const int k_lora = (p.r + 15) / 16;
       const bool do_mma = !(p.debug & 2);
+      // side product: M = 256 (128 staged token rows per CTA), N = r_pad, both operands K-major in shared memory
+      const uint32_t idesc_t = ptx::make_idesc_f16(std::is_same<ActT, __nv_bfloat16>::value, false, false, 2 * kBM, p.r_pad);
       int g = 0, s = 0;
-      uint32_t full_par = 0, acc_par = 1;
+      uint32_t full_par = 0, acc_par = 1, tbox_par = 0;
       for (int item = pair; item < n_items; item += n_pairs) {
         const int tile = item_tile(item);
         const int64_t t0 = (int64_t)(tile / p.n_fblk) * tok_tile;
@@ -288,9 +328,29 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             if (kTmemA) ptx::umma_ts_pair(d, a_tmem + (uint32_t)(8 * k), b_desc + k * kBStep, idesc, accumulate);
             else ptx::umma_ss_pair(d, a_desc + k * kAStep, b_desc + k * kBStep, idesc, accumulate);
           };
+          if (kFuse && p.fuse && b == n_main) {  // adapter step: the epilogue warps have rounded t into this stage's boxes
+            ptx::mbar_wait(bar_t_box, tbox_par);
+            tbox_par ^= 1u;
+            ptx::tc_fence_after();
+          }
           if (ptx::elect_one()) {
             if (do_mma) {
-              if (b < n_main) {
+              if (kFuse && b < n_main && p.fuse) {
+                // side-product MMAs interleaved with the main ones: each reads 128 staged rows x 32 bytes per CTA from
+                // shared memory (32 cycles of operand fetch for 8 cycles of math), which hides under the 88 cycles of
+                // the main MMA in front of it instead of queueing at the end of the step
+                const uint64_t la_desc = ptx::make_smem_desc_sw128(stage_la(s), 16, 1024);
+                const int n_grp = (na * (p.N_acc >> 1) + kBM - 1) / kBM;
+                const uint64_t x_desc1 = b_desc0 + (uint64_t)((kBM * 128) >> 4);  // staged rows 128.. of this CTA
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                  mma(tmem_d, k, b_desc0, k > 0 ? 1u : acc0);
+                  ptx::umma_ss_pair(tmem_d + t_col(0), b_desc0 + k * kBStep, la_desc + k * kBStep, idesc_t, k > 0 ? 1u : acc0);
+                  if (na > 1) mma(tmem_d + kAccCols, k, b_desc1, k > 0 ? 1u : acc0);
+                  if (n_grp > 1)
+                    ptx::umma_ss_pair(tmem_d + t_col(1), x_desc1 + k * kBStep, la_desc + k * kBStep, idesc_t, k > 0 ? 1u : acc0);
+                }
+              } else if (b < n_main) {
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k) mma(tmem_d, k, b_desc0, k > 0 ? 1u : acc0);
                 if (na > 1) {
@@ -304,6 +364,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
                 }
               }
             }
+            if (kFuse && p.fuse && b == n_main - 1) ptx::umma_commit_pair(bar_t_full);  // t complete -> epilogue warps, both CTAs
             ptx::umma_commit_pair(bar_empty(s));  // the stage is reusable in both CTAs once these MMAs have read it
             if (b == b1 - 1) ptx::umma_commit_pair(bar_acc_full);  // item complete -> epilogue warps, both CTAs
           }
@@ -361,7 +422,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------- epilogue warps
-    ptx::setmaxnreg_dec<kEpiRegs>();
+    ptx::setmaxnreg_inc<kEpiRegs>();
     // TMEM holds D[feature (lane), token (column)] but the output is [token, feature]: each warp converts its
     // 32 features x 32 tokens to 16-bit and writes them TRANSPOSED into a staging tile [32 tokens][128 features]
     // (64 contiguous bytes per token per warp: conflict-free); one thread then hands the tile to the TMA store
@@ -369,14 +430,17 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     // store of chunk c overlaps the TMEM load + conversion of chunk c + 1.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int et = (warp - kEpiWarp0) * 32 + lane;
-    const uint32_t lane_base = tmem_d + ((uint32_t)(quad * 32) << 16);
+    const uint32_t lane_base = pinned(tmem_d + ((uint32_t)(quad * 32) << 16));
     // stmatrix row address of this thread inside a staging tile: matrix k = lane / 8 (features 8k..8k+7 of the
     // quadrant's 32), row i = lane % 8 (token 8q + i); half (quad / 2), 16-byte chunk (quad % 2) * 4 + k of the
     // 128-byte row, XOR-swizzled with the token (SWIZZLE_128B, matching the store's tensor map)
     const int sm_k = lane >> 3, sm_i = lane & 7;
     const uint32_t st_off = (uint32_t)((quad >> 1) * 4096 + sm_i * 128 + ((((quad & 1) * 4 + sm_k) ^ sm_i) << 4));
-    const uint32_t epi_smem = bar_base - (uint32_t)epi_bytes + st_off;
+    const uint32_t epi_smem = pinned(bar_base - (uint32_t)epi_bytes + st_off);
+    const uint32_t stg_full0 = pinned(bar_stg_full(0)), stg_empty0 = pinned(bar_stg_empty(0));
+    const uint32_t acc_empty_leader = pinned(ptx::mapa(bar_acc_empty(0), 0));  // + 8 a: the leader's barrier
     uint32_t it = 0, sb = 0, sphase = 1;  // staging tile of the next live chunk; parity of its "empty" wait
+    int ring_pos = 0;                     // ring stage of this pair's next work item (fused down-projection)
     ptx::griddep_wait();  // bias / split-K workspace (zeroed by a memset node) / output ordering
     for (int item = pair; item < n_items; item += n_pairs, ++it) {
       const int tile = item_tile(item);
@@ -392,65 +456,176 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
           if (f < OUT) bias_v[u] = to_f32<ActT>(static_cast<const ActT*>(p.bias)[f]);
         }
       }
+      if (kFuse && p.fuse) {
+        // Side product of this tile: lane = staged token row (group g: rows 128 g ..), r_pad fp32 columns.  Round to
+        // the activation dtype and write the rows into the adapter step's activation boxes (K-major, 128-byte rows,
+        // SWIZZLE_128B: 16-byte chunk c of row i sits at chunk c ^ (i % 8)); that stage was last read by MMAs that
+        // were issued before the commit we have just waited for, so it is free.
+        const int s_ad = (ring_pos + n_main) % S;
+        ring_pos = (ring_pos + n_main + 1) % S;
+        const int half = p.N_acc >> 1;
+        const int rows = na * half;
+        const int n_grp = (rows + kBM - 1) / kBM;
+        ptx::mbar_wait(bar_t_full, it & 1u);
+        ptx::tc_fence_after();
+        if (et == 0) tl_mark(p, 4, 4 * (int)it);
+        auto load_rows = [&](int gr, uint32_t (&pk)[kMaxFuseRP / 2]) {
+#pragma unroll
+          for (int c16 = 0; c16 < kMaxFuseRP; c16 += 16) {
+            if (c16 < p.r_pad) {
+              uint32_t v[16];
+              ptx::tmem_ld_32x32b_x16(lane_base + t_col(gr) + (uint32_t)c16, v);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                pk[(c16 >> 1) + e] = pack2<ActT>(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pk[(c16 >> 1) + e] = 0u;
+            }
+          }
+        };
+        for (int gr = 0; gr < n_grp; ++gr) {
+          const int i = gr * kBM + quad * 32 + lane;  // staged row of this thread
+          uint32_t pk[kMaxFuseRP / 2];                // r_pad 16-bit values (columns >= r are exact zeros)
+          load_rows(gr, pk);
+          if (i < rows) {
+            const int a = i >= half ? 1 : 0, ri = i - a * half;
+            const uint32_t row_addr = stage_b(s_ad, a) + (uint32_t)((ri >> 3) * 1024 + (ri & 7) * 128);
+#pragma unroll
+            for (int c = 0; c < kMaxFuseRP / 8; ++c)
+              if (c < (p.r_pad >> 3))
+                ptx::sts128(row_addr + (uint32_t)((c ^ (ri & 7)) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          }
+        }
+        ptx::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar_t_box, 0));
+        if (et == 0) tl_mark(p, 4, 4 * (int)it + 1);
+        // Feature block 0 also saves the rows for the backward pass (t_save [T, VFT_LORA_LD]: the first r_pad columns;
+        // nothing reads the others), while the adapter step's MMAs run.  TMEM still holds the side product: nothing
+        // overwrites it before the drain below.
+        if (tile % p.n_fblk == 0) {
+          for (int gr = 0; gr < n_grp; ++gr) {
+            const int i = gr * kBM + quad * 32 + lane;
+            uint32_t pk[kMaxFuseRP / 2];
+            load_rows(gr, pk);
+            const int a = i >= half ? 1 : 0;
+            const int64_t tok = t0 + (int64_t)a * p.N_acc + (int64_t)rank * half + (i - a * half);
+            if (i < rows && tok < p.T) {
+              uint4* orow = reinterpret_cast<uint4*>(static_cast<ActT*>(p.save) + tok * VFT_LORA_LD);
+#pragma unroll
+              for (int c = 0; c < kMaxFuseRP / 8; ++c)
+                if (c < (p.r_pad >> 3)) orow[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            }
+          }
+        }
+      }
       ptx::mbar_wait(bar_acc_full, it & 1u);
       ptx::tc_fence_after();
-      if (et == 0) tl_mark(p, 4, 2 * (int)it);
-      for (int a = 0; a < na; ++a) {
-        const int64_t ta = t0 + (int64_t)a * p.N_acc;
+      if (et == 0) tl_mark(p, 4, 4 * (int)it + 2);
+      if (p.n_split > 1) {
+        // split-K: the fp32 partial tile is ADDED to the workspace (few-token problems only)
+        for (int a = 0; a < na; ++a) {
+          const int64_t ta = t0 + (int64_t)a * p.N_acc;
 #pragma unroll 1
-        for (int c0 = 0; c0 < p.N_acc; c0 += 32) {
-          const bool live = ta + c0 < p.T;  // warp-uniform; dead chunks still release the accumulator below
-          // 16x256b: mma-style fragments -- r[4q], r[4q+1] = (lane t/4, tokens 8q + 2(t%4), +1); r[4q+2], r[4q+3] = lane + 8
-          uint32_t v0[16], v1[16];  // lanes 0..15 / 16..31 of the quadrant, 32 token columns
-          if (live) {
-            ptx::tmem_ld_16x256b_x4(lane_base + (uint32_t)(a * kAccCols + c0), v0);
-            ptx::tmem_ld_16x256b_x4(lane_base + (16u << 16) + (uint32_t)(a * kAccCols + c0), v1);
-            ptx::tmem_ld_wait();
-          }
-          if (c0 + 32 >= p.N_acc) {  // accumulator a is in registers / not needed: the issuer may overwrite it
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar_acc_empty(a), 0));
-          }
-          if (!live) continue;
-          if (p.n_split > 1) {  // split-K: add the fp32 partial tile to the workspace
-            if (!(p.debug & 4)) {
+          for (int c0 = 0; c0 < p.N_acc; c0 += 32) {
+            const bool live = ta + c0 < p.T;  // warp-uniform; dead chunks still release the accumulator below
+            // 16x256b: mma-style fragments -- r[4q], r[4q+1] = (lane t/4, tokens 8q + 2(t%4), +1); r[4q+2], r[4q+3] = lane + 8
+            uint32_t v0[16], v1[16];  // lanes 0..15 / 16..31 of the quadrant, 32 token columns
+            if (live) {
+              ptx::tmem_ld_16x256b_x4(lane_base + (uint32_t)(a * kAccCols + c0), v0);
+              ptx::tmem_ld_16x256b_x4(lane_base + (16u << 16) + (uint32_t)(a * kAccCols + c0), v1);
+              ptx::tmem_ld_wait();
+            }
+            if (c0 + 32 >= p.N_acc) {  // accumulator a is in registers / not needed: the issuer may overwrite it
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar_acc_empty(a), 0));
+            }
+            if (!live || (p.debug & 4)) continue;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 4; ++q) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int64_t t = ta + c0 + 8 * q + 2 * (lane & 3) + (e & 1);
-                  const int col = c0 + 8 * q + 2 * (lane & 3) + (e & 1);
-                  const int64_t f_lo = feat0 + quad * 32 + (lane >> 2) + ((e >> 1) ? 8 : 0);
-                  if (col < p.N_acc && t < p.T) {
-                    if (f_lo < OUT) atomicAdd(p.partial + t * OUT + f_lo, __uint_as_float(v0[4 * q + e]));
-                    if (f_lo + 16 < OUT) atomicAdd(p.partial + t * OUT + f_lo + 16, __uint_as_float(v1[4 * q + e]));
-                  }
+              for (int e = 0; e < 4; ++e) {
+                const int64_t t = ta + c0 + 8 * q + 2 * (lane & 3) + (e & 1);
+                const int col = c0 + 8 * q + 2 * (lane & 3) + (e & 1);
+                const int64_t f_lo = feat0 + quad * 32 + (lane >> 2) + ((e >> 1) ? 8 : 0);
+                if (col < p.N_acc && t < p.T) {
+                  if (f_lo < OUT) atomicAdd(p.partial + t * OUT + f_lo, __uint_as_float(v0[4 * q + e]));
+                  if (f_lo + 16 < OUT) atomicAdd(p.partial + t * OUT + f_lo + 16, __uint_as_float(v1[4 * q + e]));
                 }
               }
             }
-            continue;
           }
-          const uint32_t buf = epi_smem + sb * (uint32_t)kStgBytes;
-          ptx::mbar_wait(bar_stg_empty(sb), sphase);  // the tile's previous store has read it
+        }
+      } else {
+        // Drain (one load + wait + convert + store + publish chain per chunk took ~700 cycles per 32 columns: 7.5 k cycles
+        // per tile during which the tensor pipe waits for its accumulators -- the timeline of tools/tc_probe.py).
+        auto live_chunks = [&](int a) -> int {  // live 32-column chunks of accumulator a (tokens < T)
+          const int64_t left = p.T - (t0 + (int64_t)a * p.N_acc);
+          const int cols = a < na ? (int)(left < p.N_acc ? (left > 0 ? left : 0) : p.N_acc) : 0;
+          return (cols + 31) >> 5;
+        };
+        const int nl0 = live_chunks(0), nl1 = live_chunks(1);
+        const int total = nl0 + nl1;
+        auto release = [&](int a) {  // accumulator a is in registers / holds nothing we need: the issuer may overwrite it
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(acc_empty_leader + 8u * (uint32_t)a);
+        };
+        if (nl0 == 0) release(0);
+        if (na > 1 && nl1 == 0) release(1);
+        auto chunk_addr = [&](int j) -> uint32_t {
+          const int a = j >= nl0 ? 1 : 0;
+          return lane_base + (uint32_t)(a * kAccCols + (j - a * nl0) * 32);
+        };
+        // 16x256b: mma-style fragments -- r[4q], r[4q+1] = (lane t/4, tokens 8q + 2(t%4), +1); r[4q+2], r[4q+3] = lane + 8
+        // A tcgen05.ld takes ~300 cycles to come back here: the chunk that has landed is converted to 16-bit pairs
+        // first (16 registers), the loads of the next chunk are issued into the 32 registers that frees, and only then
+        // does the warp walk its chain of waits (staging tile free -> stmatrix -> proxy fence -> arrive), under which
+        // those loads complete.
+        uint32_t v0[16], v1[16];  // lanes 0..15 / 16..31 of the quadrant, 32 token columns
+        auto load_chunk = [&](int j) {
+          const uint32_t addr = chunk_addr(j);
+          ptx::tmem_ld_16x256b_x4(addr, v0);
+          ptx::tmem_ld_16x256b_x4(addr + (16u << 16), v1);
+        };
+        if (total > 0) load_chunk(0);
+#pragma unroll 1
+        for (int j = 0; j < total; ++j) {
+          uint32_t m[16];
+          ptx::tmem_ld_wait();  // chunk j
 #pragma unroll
           for (int q = 0; q < 4; ++q) {  // tokens 8q..8q+7: four 8x8 matrices = feature groups 0-7, 8-15, 16-23, 24-31
-            const uint32_t m0 = pack2<ActT>(__uint_as_float(v0[4 * q]) + bias_v[0], __uint_as_float(v0[4 * q + 1]) + bias_v[0]);
-            const uint32_t m1 = pack2<ActT>(__uint_as_float(v0[4 * q + 2]) + bias_v[1], __uint_as_float(v0[4 * q + 3]) + bias_v[1]);
-            const uint32_t m2 = pack2<ActT>(__uint_as_float(v1[4 * q]) + bias_v[2], __uint_as_float(v1[4 * q + 1]) + bias_v[2]);
-            const uint32_t m3 = pack2<ActT>(__uint_as_float(v1[4 * q + 2]) + bias_v[3], __uint_as_float(v1[4 * q + 3]) + bias_v[3]);
-            ptx::stmatrix_x4_trans(buf + (uint32_t)(q * 1024), m0, m1, m2, m3);
+            m[4 * q] = pack2<ActT>(__uint_as_float(v0[4 * q]) + bias_v[0], __uint_as_float(v0[4 * q + 1]) + bias_v[0]);
+            m[4 * q + 1] = pack2<ActT>(__uint_as_float(v0[4 * q + 2]) + bias_v[1], __uint_as_float(v0[4 * q + 3]) + bias_v[1]);
+            m[4 * q + 2] = pack2<ActT>(__uint_as_float(v1[4 * q]) + bias_v[2], __uint_as_float(v1[4 * q + 1]) + bias_v[2]);
+            m[4 * q + 3] = pack2<ActT>(__uint_as_float(v1[4 * q + 2]) + bias_v[3], __uint_as_float(v1[4 * q + 3]) + bias_v[3]);
+          }
+          {  // the accumulator this chunk completes is in registers: the issuer may overwrite it
+            const int a = j >= nl0 ? 1 : 0;
+            if (j + 1 == nl0 + a * nl1) release(a);
+          }
+          if (j + 1 < total) load_chunk(j + 1);
+          const uint32_t buf = epi_smem + sb * (uint32_t)kStgBytes;
+          ptx::mbar_wait(stg_empty0 + 8u * sb, sphase);  // the tile's previous store has read it
+          if (!(p.debug & 4)) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              ptx::stmatrix_x4_trans(buf + (uint32_t)(q * 1024), m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar_stg_full(sb));  // the store warp takes it from here
+          if (lane == 0) ptx::mbar_arrive(stg_full0 + 8u * sb);  // the store warp takes it from here
           if (++sb == (uint32_t)p.n_stg) {  // live chunks walk round the staging tiles
             sb = 0;
             sphase ^= 1u;
           }
         }
       }
-      if (et == 0) tl_mark(p, 4, 2 * (int)it + 1);
+      if (et == 0) tl_mark(p, 4, 4 * (int)it + 3);
       for (int a = na; a < p.n_acc; ++a) {  // unused accumulators of a ragged last token block: keep phases in step
         if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar_acc_empty(a), 0));
       }
@@ -659,26 +834,28 @@ struct Tc2Config {
 // K = 64), decode ~600 ALU-pipe cycles per 128 x 64 weight tile, shared memory 128 B/clk over the activation
 // boxes (written by TMA, read by the MMA) and -- backward only -- the decoded tile (written once, read once per
 // accumulator).
-static int max_stages(bool tmem_a, int n_acc, int N_acc) {
-  const int stage_bytes = (tmem_a ? 0 : kATileBytes) + n_acc * (N_acc / 2) * 128;
+// `rp`: padded rank of a fused down-projection (0: none) -- costs a [rp/2 x 64] box per stage and the last rp columns
+// of each accumulator pitch.
+static int max_stages(bool tmem_a, int n_acc, int N_acc, int rp) {
+  const int stage_bytes = (tmem_a ? 0 : kATileBytes) + n_acc * (N_acc / 2) * 128 + (rp / 2) * 128;
   int stages = (kSmemLimit - kBarBytes - kEpiBytes - 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (tmem_a && stages > kTmemAStages) stages = kTmemAStages;  // the weight ring in tensor memory has 4 slots
   // four stages (one per decode group) keep the tensor pipe fed; shared memory beyond that is worth more as output
   // staging (see n_stg), which shortens the accumulator drain at tile boundaries
-  if (const char* e = getenv("VFT_TC2_MAXSTAGES")) {
-    const int v = atoi(e);
-    if (v >= kGroups && stages > v) stages = v;
-  } else if (stages > kGroups) {
-    stages = kGroups;
-  }
+  const int cap = env().tc2_max_stages >= kGroups ? env().tc2_max_stages : kGroups;
+  if (stages > cap) stages = cap;
   return stages;
 }
 
-static bool config_ok(bool tmem_a, int n_acc, int N_acc) {
+static bool config_ok(bool tmem_a, int n_acc, int N_acc, int rp) {
   if (n_acc < 1 || n_acc > kMaxAcc || N_acc < 16 || N_acc > 256 || N_acc % 16 != 0) return false;
   if (tmem_a && n_acc == 2 && N_acc > AccLayout<true>::pitch) return false;
-  return max_stages(tmem_a, n_acc, N_acc) >= kGroups;  // a decode group may run at most one ring phase ahead
+  if (rp > 0) {  // side-product columns: the tail of each pitch (two accumulators) / the columns above the only one
+    const int pitch = tmem_a ? AccLayout<true>::pitch : AccLayout<false>::pitch;
+    if (n_acc == 2 ? N_acc > pitch - rp : N_acc > 2 * pitch - rp) return false;
+  }
+  return max_stages(tmem_a, n_acc, N_acc, rp) >= kGroups;  // a decode group may run at most one ring phase ahead
 }
 
 // Split-K plan: with fewer tiles than half the SM pairs, the contraction of every tile is divided over n_split work
@@ -695,7 +872,8 @@ struct Tc2Plan {
 // tile (written once, read once per accumulator); per work item ~2500 cycles of fill + ~20 cycles per token of
 // epilogue (128 per token when the partial tile leaves through fp32 atomics); a split adds a memset and a finalize
 // launch (~6000 cycles).  In practice the split wins only for a few tokens (adaLN / modulation layers, T = batch).
-static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a, int n_pairs, bool allow_split = true) {
+static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a, int n_pairs, bool allow_split = true,
+                        int rp = 0) {
   Tc2Plan best = {};
   double best_cost = 1e300;
   const int n_main = (int)ceil_div64(RED, kBK);
@@ -703,7 +881,7 @@ static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a,
   const int64_t ws = T * OUT * (int64_t)sizeof(float);
   for (int n_acc = 1; n_acc <= kMaxAcc; ++n_acc) {
     for (int N_acc = 32; N_acc <= 256; N_acc += 16) {
-      if (!config_ok(tmem_a, n_acc, N_acc)) continue;
+      if (!config_ok(tmem_a, n_acc, N_acc, rp)) continue;
       const int b_bytes = (N_acc / 2) * 128;
       const int64_t tok = (int64_t)n_acc * N_acc;
       const int64_t tiles = n_f * ceil_div64(T, tok);
@@ -728,7 +906,7 @@ static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a,
       const double cost = waves * ((k_per + (r > 0 ? 1 : 0)) * step + 2500.0 + epi) + (split > 1 ? 6000.0 : 0.0);
       if (cost < best_cost * 0.999 || (cost < best_cost * 1.001 && N_acc > best.cfg.N_acc)) {
         best_cost = cost;
-        best.cfg = {n_acc, N_acc, max_stages(tmem_a, n_acc, N_acc), cost};
+        best.cfg = {n_acc, N_acc, max_stages(tmem_a, n_acc, N_acc, rp), cost};
         best.n_tiles = (int)tiles;
         best.n_split = split;
         best.k_per = k_per;
@@ -746,34 +924,60 @@ static int device_pairs() {
   return n_sm / 2 > 0 ? n_sm / 2 : 1;
 }
 
+// Padded rank of the down-projection that the forward launch can fuse (0: it cannot): 16-bit adapter rows that TMA
+// can address, a rank that fits the spare accumulator columns, and a problem large enough to run unsplit.
+static int fuse_rank(const LayerArgs& a, bool backward) {
+  if (backward || a.r <= 0 || env().tc2_fuse == 0) return 0;
+  const int rp = a.r <= 16 ? 16 : 32;
+  if (a.r > kMaxFuseRP || (reinterpret_cast<uintptr_t>(a.lora_a) & 15u) != 0) return 0;
+  return rp;
+}
+
+struct Tc2Choice {
+  Tc2Plan plan;
+  int rp;  // > 0: fused down-projection
+};
+
+static Tc2Choice choose_tc2(const LayerArgs& a, bool backward, int n_pairs) {
+  const int64_t OUT = backward ? a.K : a.N;
+  const int64_t RED = backward ? a.N : a.K;
+  const bool tmem_a = !backward;
+  Tc2Choice c;
+  c.rp = fuse_rank(a, backward);
+  if (c.rp > 0) {
+    c.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs, /*allow_split=*/env().tc2_fuse != 1, c.rp);
+    if (c.plan.n_split == 1 && c.plan.cfg.N_acc > 0) return c;
+    c.rp = 0;  // few tokens: the contraction is split over work items, the side product stays a kernel of its own
+  }
+  c.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs);
+  if (c.plan.n_split > 1 && (a.ws == nullptr || a.ws_bytes < c.plan.ws_bytes || env().tc2_nosplit))
+    c.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs, /*allow_split=*/false);  // no workspace: unsplit shape
+  return c;
+}
+
 template <typename ActT, bool kBackward>
-static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void* lora_act, cudaStream_t st) {
+static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora_act, cudaStream_t st) {
   const int64_t OUT = kBackward ? a.K : a.N;
   const int64_t RED = kBackward ? a.N : a.K;
   const int n_pairs = device_pairs();
   constexpr bool kTmemA = !kBackward;
-  const char* nosplit = getenv("VFT_TC2_NOSPLIT");
-  Tc2Plan plan = plan_tc2(a.T, OUT, RED, a.r, kTmemA, n_pairs);
-  if (plan.n_split > 1 && (a.ws == nullptr || a.ws_bytes < plan.ws_bytes || (nosplit && nosplit[0] == '1')))
-    plan = plan_tc2(a.T, OUT, RED, a.r, kTmemA, n_pairs, /*allow_split=*/false);  // no workspace: unsplit shape
+  const VftEnv& ev = env();
+  const Tc2Choice choice = choose_tc2(a, kBackward, n_pairs);
+  const Tc2Plan& plan = choice.plan;
+  const int rp = choice.rp;
   Tc2Config cfg = plan.cfg;
   bool forced_cfg = false;
-  if (const char* e = getenv("VFT_TC2_NACC")) {  // triage override: "<n_acc>x<N_acc>" (clamped to what the path allows)
-    int na = 0, nn = 0;
-    if (sscanf(e, "%dx%d", &na, &nn) == 2) {
-      if (kTmemA && na == 2 && nn > AccLayout<true>::pitch) nn = AccLayout<true>::pitch;
-      if (config_ok(kTmemA, na, nn)) {
-        cfg.n_acc = na;
-        cfg.N_acc = nn;
-        cfg.stages = max_stages(kTmemA, na, nn);
-        forced_cfg = true;
-      }
+  if (ev.tc2_force_na > 0) {  // triage override VFT_TC2_NACC="<n_acc>x<N_acc>" (clamped to what the path allows)
+    int na = ev.tc2_force_na, nn = ev.tc2_force_nn;
+    if (kTmemA && na == 2 && nn > AccLayout<true>::pitch) nn = AccLayout<true>::pitch;
+    if (config_ok(kTmemA, na, nn, rp)) {
+      cfg.n_acc = na;
+      cfg.N_acc = nn;
+      cfg.stages = max_stages(kTmemA, na, nn, rp);
+      forced_cfg = true;
     }
   }
-  if (const char* e = getenv("VFT_TC2_STAGES")) {
-    const int s = atoi(e);
-    if (s >= kGroups && s <= cfg.stages) cfg.stages = s;
-  }
+  if (ev.tc2_stages >= kGroups && ev.tc2_stages <= cfg.stages) cfg.stages = ev.tc2_stages;
 
   Tc2Params p;
   p.T = a.T; p.N = a.N; p.K = a.K; p.r = a.r; p.qdtype = a.qdtype; p.scale = a.scale;
@@ -786,8 +990,12 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
   p.n_acc = cfg.n_acc;
   p.N_acc = cfg.N_acc;
   p.stages = cfg.stages;
+  p.fuse = rp > 0 ? 1 : 0;
+  p.r_pad = rp > 0 ? rp : 16;
+  p.la_bytes = rp > 0 ? (rp / 2) * 128 : 0;
+  p.save = lora_act;
   p.b_bytes = (cfg.N_acc / 2) * 128;
-  p.stage_bytes = (kTmemA ? 0 : kATileBytes) + cfg.n_acc * p.b_bytes;
+  p.stage_bytes = (kTmemA ? 0 : kATileBytes) + cfg.n_acc * p.b_bytes + p.la_bytes;
   p.n_fblk = (int)ceil_div64(OUT, 2 * kBM);
   p.n_tiles = p.n_fblk * (int)ceil_div64(a.T, (int64_t)cfg.n_acc * cfg.N_acc);
   p.n_split = 1;
@@ -799,8 +1007,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
     p.partial = static_cast<float*>(a.ws);
     VFT_CUDA_OK(cudaMemsetAsync(a.ws, 0, (size_t)plan.ws_bytes, st));
   }
-  const char* dbg = getenv("VFT_TC_DEBUG");
-  p.debug = dbg ? atoi(dbg) : 0;
+  p.debug = ev.tc_debug;
 
   const CUtensorMapDataType dt =
       std::is_same<ActT, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -813,7 +1020,11 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
   if (rc != VFT_OK) return rc;
   rc = make_map_2d(&map_out16, dt, out, (uint64_t)OUT, (uint64_t)a.T, (uint64_t)OUT * 2, 64, 16, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != VFT_OK) return rc;
-  if (a.r > 0) {
+  if (rp > 0) {  // lora_down.weight [r, K]: boxes of [rp/2 rows x 64 contraction elements], rows >= r zero-filled
+    rc = make_map_2d(&map_lora, dt, a.lora_a, (uint64_t)a.K, (uint64_t)a.r, (uint64_t)a.K * 2, kBK, rp / 2,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != VFT_OK) return rc;
+  } else if (a.r > 0) {
     rc = make_map_2d(&map_lora, dt, lora_act, VFT_LORA_LD, (uint64_t)a.T, VFT_LORA_LD * 2, kBK, cfg.N_acc / 2,
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != VFT_OK) return rc;
@@ -824,10 +1035,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, const void
   // output staging tiles from what the ring leaves over (a whole tile of 2 x 176 tokens is 11 of them)
   p.n_stg = (kSmemLimit - kBarBytes - 1024 - cfg.stages * p.stage_bytes) / kStgBytes;
   if (p.n_stg > kMaxStg) p.n_stg = kMaxStg;
-  if (const char* e = getenv("VFT_TC2_NSTG")) {
-    const int v = atoi(e);
-    if (v >= 2 && v <= p.n_stg) p.n_stg = v;
-  }
+  if (ev.tc2_n_stg >= 2 && ev.tc2_n_stg <= p.n_stg) p.n_stg = ev.tc2_n_stg;
   const int dyn_bytes = cfg.stages * p.stage_bytes + p.n_stg * kStgBytes + kBarBytes + 1024;  // + 1024-B alignment slack
   auto kern = qlora_tc2_kernel<ActT, kBackward>;
   VFT_OPT_IN_SMEM_ONCE(kern, VFT_MAX_DYN_SMEM);  // dyn_bytes depends on the plan: opt in to the limit
@@ -878,7 +1086,7 @@ namespace vft {
 bool tc2_preferred(const LayerArgs& a, bool backward) {
   const int64_t OUT = backward ? a.K : a.N;
   if (OUT % 8 != 0) return false;  // row stride of the output must be a multiple of 16 bytes (TMA store)
-  if (const char* e = getenv("VFT_TC2")) return e[0] != '0' && OUT >= kBM + 1 && a.T >= 1;
+  if (env().tc2 >= 0) return env().tc2 != 0 && OUT >= kBM + 1 && a.T >= 1;
   return OUT >= 2 * kBM;  // every token count: small problems are split along the contraction
 }
 
@@ -886,17 +1094,23 @@ bool tc2_preferred(const LayerArgs& a, bool backward) {
 int64_t tc2_workspace_bytes(int64_t T, int64_t N, int64_t K, int r, bool backward) {
   const int64_t OUT = backward ? K : N, RED = backward ? N : K;
   if (T <= 0 || OUT % 8 != 0 || OUT < 2 * kBM || K % 64 != 0) return 0;
-  return plan_tc2(T, OUT, RED, r, !backward, device_pairs()).ws_bytes;
+  return plan_tc2(T, OUT, RED, r, !backward, device_pairs()).ws_bytes;  // (a fused plan never splits)
 }
 
-int tc2_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st) {
+// True when tc2_fwd computes t_save = x . A^T itself (fused down-projection): the caller then skips the side kernel.
+bool tc2_fuses_down(const LayerArgs& a) {
+  if (a.T <= 0 || !tc2_preferred(a, false)) return false;
+  return choose_tc2(a, false, device_pairs()).rp > 0;
+}
+
+int tc2_fwd(const LayerArgs& a, const void* x, void* y, void* t_save, cudaStream_t st) {
   if (a.act_dtype == VFT_BF16) return launch_tc2<__nv_bfloat16, false>(a, x, y, t_save, st);
   return launch_tc2<__half, false>(a, x, y, t_save, st);
 }
 
 int tc2_bwd_dx(const LayerArgs& a, const void* dy, void* dx, const void* dt_save, cudaStream_t st) {
-  if (a.act_dtype == VFT_BF16) return launch_tc2<__nv_bfloat16, true>(a, dy, dx, dt_save, st);
-  return launch_tc2<__half, true>(a, dy, dx, dt_save, st);
+  if (a.act_dtype == VFT_BF16) return launch_tc2<__nv_bfloat16, true>(a, dy, dx, const_cast<void*>(dt_save), st);
+  return launch_tc2<__half, true>(a, dy, dx, const_cast<void*>(dt_save), st);
 }
 
 }  // namespace vft

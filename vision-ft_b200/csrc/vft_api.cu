@@ -51,16 +51,39 @@ static bool use_tc(const LayerArgs& a, bool backward, int* status) {
   return ok;
 }
 
-bool pdl_enabled() {
-  const char* e = getenv("VFT_PDL");
-  return !(e && e[0] == '0');
+void VftEnv::load() {
+  *this = VftEnv();
+  auto num = [](const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+  };
+  auto is = [](const char* name, char c) {
+    const char* e = getenv(name);
+    return e && e[0] == c;
+  };
+  pdl = !is("VFT_PDL", '0');
+  side_mma = is("VFT_SIDE_MMA", '1');
+  side_split = num("VFT_SIDE_SPLIT", 0);
+  gemv_tma = num("VFT_GEMV_TMA", 1);
+  tc_pair = is("VFT_TC_PAIR", '1');
+  tc_debug = num("VFT_TC_DEBUG", 0);
+  if (const char* e = getenv("VFT_TC2")) tc2 = e[0] != '0';
+  tc2_max_stages = num("VFT_TC2_MAXSTAGES", 0);
+  tc2_stages = num("VFT_TC2_STAGES", 0);
+  tc2_n_stg = num("VFT_TC2_NSTG", 0);
+  if (const char* e = getenv("VFT_TC2_NACC")) {
+    if (sscanf(e, "%dx%d", &tc2_force_na, &tc2_force_nn) != 2) tc2_force_na = tc2_force_nn = 0;
+  }
+  tc2_nosplit = is("VFT_TC2_NOSPLIT", '1');
+  tc2_fuse = num("VFT_TC2_FUSE", -1);
 }
-
-// triage switch: VFT_SIDE_MMA=1 keeps the mma.sync adapter kernels (lora_mma.cu) instead of lora_tc.cu
-static bool side_mma() {
-  const char* e = getenv("VFT_SIDE_MMA");
-  return e && e[0] == '1';
+static VftEnv& env_mut() {
+  static VftEnv e = [] { VftEnv v; v.load(); return v; }();
+  return e;
 }
+const VftEnv& env() { return env_mut(); }
+void reload_env() { env_mut().load(); }
+static bool side_mma() { return env().side_mma; }
 
 }  // namespace vft
 
@@ -72,6 +95,7 @@ int vft_abi_version(void) { return VFT_ABI_VERSION; }
 const char* vft_last_error(void) { return g_error; }
 int vft_last_path(void) { return g_path; }
 void vft_force_path(int path) { g_forced.store(path, std::memory_order_relaxed); }
+void vft_reload_env(void) { reload_env(); }
 
 int vft_nf4_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t* packed, float* absmax,
                      void* stream) {
@@ -176,23 +200,29 @@ int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* 
   if (rc != VFT_OK) return rc;
   VFT_REQUIRE(r == 0 || t_save != nullptr, "t_save is required when r > 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (r > 0) {
+  const bool gemv = (forced_path() == 0 || forced_path() == VFT_PATH_GEMV) && gemv_supported(a);
+  if (!gemv && forced_path() == VFT_PATH_GEMV) {
+    set_error("streaming path forced but shape/dtype not supported (T=%lld N=%lld K=%lld)", (long long)T, (long long)N,
+              (long long)K);
+    return VFT_ERR_UNSUPPORTED;
+  }
+  bool tc = false;
+  if (!gemv) {
+    tc = use_tc(a, false, &rc);
+    if (rc != VFT_OK) return rc;
+  }
+  // t_save = x . A^T: inside the GEMM launch when the persistent tcgen05 kernel takes the call unsplit, else a kernel
+  // of its own in front of it
+  if (r > 0 && !(tc && tc_fuses_down(a))) {
     rc = (forced_path() == VFT_PATH_SIMT) ? simt_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st)
                                           : side_mma() ? mma_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st)
                                                        : tc_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st);
     if (rc != VFT_OK) return rc;
   }
-  if ((forced_path() == 0 || forced_path() == VFT_PATH_GEMV) && gemv_supported(a)) {
+  if (gemv) {
     set_path(VFT_PATH_GEMV);  // T <= 8: the launch is a weight stream, not a GEMM
     return gemv_fwd(a, x, y, t_save, st);
   }
-  if (forced_path() == VFT_PATH_GEMV) {
-    set_error("streaming path forced but shape/dtype not supported (T=%lld N=%lld K=%lld)", (long long)T, (long long)N,
-              (long long)K);
-    return VFT_ERR_UNSUPPORTED;
-  }
-  const bool tc = use_tc(a, false, &rc);
-  if (rc != VFT_OK) return rc;
   set_path(tc ? VFT_PATH_TCGEN05 : VFT_PATH_SIMT);
   return tc ? tc_fwd(a, x, y, t_save, st) : simt_fwd(a, x, y, t_save, st);
 }

@@ -105,8 +105,26 @@ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
     }                                                                                                      \
   } while (0)
 
-// programmatic dependent launch of the fused kernels (VFT_PDL=0 switches it off for triage)
-bool pdl_enabled();
+// Triage switches.  The environment is read ONCE per process (getenv on every launch is host time on the hot path);
+// vft_reload_env() re-reads it (tests that flip a switch between calls; not thread-safe).
+struct VftEnv {
+  bool pdl = true;         // VFT_PDL=0: no programmatic dependent launch
+  bool side_mma = false;   // VFT_SIDE_MMA=1: mma.sync adapter kernels (lora_mma.cu) instead of lora_tc.cu
+  int side_split = 0;      // VFT_SIDE_SPLIT: cluster size of the adapter side kernels
+  int gemv_tma = 1;        // VFT_GEMV_TMA=0: register-fed few-token kernel
+  bool tc_pair = false;    // VFT_TC_PAIR=1: CTA-pair form of the one-tile-per-CTA kernel
+  int tc_debug = 0;        // VFT_TC_DEBUG: bit mask, see qlora_tc2.cu (results are garbage when non-zero)
+  int tc2 = -1;            // VFT_TC2: -1 unset, 0 persistent pair kernel off, 1 on for every shape it can take
+  int tc2_max_stages = 0, tc2_stages = 0, tc2_n_stg = 0;   // VFT_TC2_MAXSTAGES / _STAGES / _NSTG
+  int tc2_force_na = 0, tc2_force_nn = 0;                   // VFT_TC2_NACC="<n_acc>x<N_acc>"
+  bool tc2_nosplit = false;                                 // VFT_TC2_NOSPLIT=1
+  int tc2_fuse = -1;  // VFT_TC2_FUSE: 0 = adapter side products as separate kernels, 1 = fused whenever the shape
+                      // allows it (never split the contraction), unset = the planner decides
+  void load();
+};
+const VftEnv& env();
+void reload_env();
+inline bool pdl_enabled() { return env().pdl; }
 
 // ---------------------------------------------------------------------------
 // launchers implemented across the .cu files (all return vft_status)
@@ -172,12 +190,14 @@ int gemv_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cud
 
 // tcgen05 family
 bool tc_supported(const LayerArgs& a, bool backward);
-int tc_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st);
+int tc_fwd(const LayerArgs& a, const void* x, void* y, void* t_save, cudaStream_t st);
+bool tc_fuses_down(const LayerArgs& a);  // tc_fwd will write t_save = x . A^T itself
 int tc_bwd_dx(const LayerArgs& a, const void* dy, void* dx, const void* dt_save, cudaStream_t st);
 // persistent CTA-pair form (qlora_tc2.cu); same contract, used by tc_fwd / tc_bwd_dx for large token counts
 bool tc2_preferred(const LayerArgs& a, bool backward);
 int64_t tc2_workspace_bytes(int64_t T, int64_t N, int64_t K, int r, bool backward);
-int tc2_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st);
+int tc2_fwd(const LayerArgs& a, const void* x, void* y, void* t_save, cudaStream_t st);
+bool tc2_fuses_down(const LayerArgs& a);  // tc2_fwd computes t_save itself (no side kernel needed)
 int tc2_bwd_dx(const LayerArgs& a, const void* dy, void* dx, const void* dt_save, cudaStream_t st);
 
 }  // namespace vft

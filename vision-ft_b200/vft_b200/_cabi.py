@@ -10,7 +10,10 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvft_b200.so")
+# VFT_LIB: A/B measurements against another build of the same library (tools/*_probe.py); symbols that build lacks
+# are then skipped and its ABI version is not checked.  Never set in the product path.
+_ALT_LIB = os.environ.get("VFT_LIB")
+LIB_PATH = _ALT_LIB if _ALT_LIB else os.path.join(_HERE, "libvft_b200.so")
 
 ABI_VERSION = 3
 LORA_LD = 64
@@ -26,6 +29,9 @@ SYMBOLS = {
     "vft_last_error": (_c.c_char_p, []),
     "vft_last_path": (_i, []),
     "vft_force_path": (None, [_i]),
+    "vft_reload_env": (None, []),
+    "vft_debug_tc2_timeline": (_i, [_p, _i]),
+    "vft_debug_side_timeline": (_i, [_p, _i]),
     "vft_nf4_quantize": (_i, [_p, _i, _i64, _i, _p, _p, _p]),
     "vft_nf4_dequantize": (_i, [_p, _p, _i64, _i, _p, _i, _p]),
     "vft_nf4_quantize_host": (_i, [_p, _i, _i64, _i, _p, _p]),
@@ -58,10 +64,12 @@ def _load() -> ctypes.CDLL:
         )
     lib = ctypes.CDLL(LIB_PATH)
     for name, (restype, argtypes) in SYMBOLS.items():
+        if _ALT_LIB and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.vft_abi_version() != ABI_VERSION:
+    if not _ALT_LIB and lib.vft_abi_version() != ABI_VERSION:
         raise VftLibraryError(f"ABI mismatch: library {lib.vft_abi_version()} != binding {ABI_VERSION}")
     return lib
 
