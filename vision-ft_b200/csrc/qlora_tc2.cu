@@ -137,13 +137,13 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
   return v;
 }
 
-template <typename ActT, bool kBackward>
+template <typename ActT, bool kBackward, bool kFuse>
 __global__ void __launch_bounds__(kThreads, 1)
 qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_lora,
                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out16,
                  const Tc2Params p) {
   constexpr bool kTmemA = !kBackward;  // forward: decoded weights go to tensor memory, backward: shared memory
-  constexpr bool kFuse = !kBackward;   // the fused side product (p.fuse) exists in the forward kernel only
+  static_assert(!(kFuse && kBackward), "the fused side product exists in the forward kernel only");
   constexpr int kAccCols = AccLayout<kTmemA>::pitch;
   constexpr int kAOff = kTmemA ? 0 : kATileBytes;  // offset of the activation boxes inside a stage
   extern __shared__ uint8_t smem_raw[];
@@ -260,10 +260,10 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             if (rank == 0) ptx::mbar_arrive(bar_full(s));
           } else {
             // the leader arms its barrier for the bytes of BOTH CTAs; each CTA loads its N_acc/2 token rows
-            if (kFuse && p.fuse && b == n_main) {  // the epilogue warps fill the adapter step's boxes themselves
+            if (kFuse && b == n_main) {  // the epilogue warps fill the adapter step's boxes themselves
               if (rank == 0) ptx::mbar_arrive(bar_full(s));
             } else {
-              const int la = (kFuse && p.fuse && b < n_main) ? p.la_bytes : 0;
+              const int la = (kFuse && b < n_main) ? p.la_bytes : 0;
               if (rank == 0) ptx::mbar_arrive_expect_tx(bar_full(s), (uint32_t)(2 * (na * p.b_bytes + la)));
               const uint32_t leader_bar = ptx::mapa(bar_full(s), 0);
               for (int a = 0; a < na; ++a) {
@@ -328,14 +328,14 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             if (kTmemA) ptx::umma_ts_pair(d, a_tmem + (uint32_t)(8 * k), b_desc + k * kBStep, idesc, accumulate);
             else ptx::umma_ss_pair(d, a_desc + k * kAStep, b_desc + k * kBStep, idesc, accumulate);
           };
-          if (kFuse && p.fuse && b == n_main) {  // adapter step: the epilogue warps have rounded t into this stage's boxes
+          if (kFuse && b == n_main) {  // adapter step: the epilogue warps have rounded t into this stage's boxes
             ptx::mbar_wait(bar_t_box, tbox_par);
             tbox_par ^= 1u;
             ptx::tc_fence_after();
           }
           if (ptx::elect_one()) {
             if (do_mma) {
-              if (kFuse && b < n_main && p.fuse) {
+              if (kFuse && b < n_main) {
                 // side-product MMAs interleaved with the main ones: each reads 128 staged rows x 32 bytes per CTA from
                 // shared memory (32 cycles of operand fetch for 8 cycles of math), which hides under the 88 cycles of
                 // the main MMA in front of it instead of queueing at the end of the step
@@ -364,7 +364,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
                 }
               }
             }
-            if (kFuse && p.fuse && b == n_main - 1) ptx::umma_commit_pair(bar_t_full);  // t complete -> epilogue warps, both CTAs
+            if (kFuse && b == n_main - 1) ptx::umma_commit_pair(bar_t_full);  // t complete -> epilogue warps, both CTAs
             ptx::umma_commit_pair(bar_empty(s));  // the stage is reusable in both CTAs once these MMAs have read it
             if (b == b1 - 1) ptx::umma_commit_pair(bar_acc_full);  // item complete -> epilogue warps, both CTAs
           }
@@ -449,14 +449,15 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       const int64_t feat0 = (int64_t)(tile % p.n_fblk) * (2 * kBM) + (int64_t)rank * kBM;
       // bias of the four feature rows this thread holds fragments of: quadrant base + lane / 4 + {0, 8, 16, 24}
       float bias_v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      if (!kBackward && p.bias != nullptr) {
+      const bool has_bias = !kBackward && p.bias != nullptr;
+      if (has_bias) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int64_t f = feat0 + quad * 32 + (lane >> 2) + 8 * u;
           if (f < OUT) bias_v[u] = to_f32<ActT>(static_cast<const ActT*>(p.bias)[f]);
         }
       }
-      if (kFuse && p.fuse) {
+      if (kFuse) {
         // Side product of this tile: lane = staged token row (group g: rows 128 g ..), r_pad fp32 columns.  Round to
         // the activation dtype and write the rows into the adapter step's activation boxes (K-major, 128-byte rows,
         // SWIZZLE_128B: 16-byte chunk c of row i sits at chunk c ^ (i % 8)); that stage was last read by MMAs that
@@ -561,67 +562,59 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
           }
         }
       } else {
-        // Drain (one load + wait + convert + store + publish chain per chunk took ~700 cycles per 32 columns: 7.5 k cycles
-        // per tile during which the tensor pipe waits for its accumulators -- the timeline of tools/tc_probe.py).
-        auto live_chunks = [&](int a) -> int {  // live 32-column chunks of accumulator a (tokens < T)
-          const int64_t left = p.T - (t0 + (int64_t)a * p.N_acc);
-          const int cols = a < na ? (int)(left < p.N_acc ? (left > 0 ? left : 0) : p.N_acc) : 0;
-          return (cols + 31) >> 5;
-        };
-        const int nl0 = live_chunks(0), nl1 = live_chunks(1);
-        const int total = nl0 + nl1;
-        auto release = [&](int a) {  // accumulator a is in registers / holds nothing we need: the issuer may overwrite it
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_cluster(acc_empty_leader + 8u * (uint32_t)a);
-        };
-        if (nl0 == 0) release(0);
-        if (na > 1 && nl1 == 0) release(1);
-        auto chunk_addr = [&](int j) -> uint32_t {
-          const int a = j >= nl0 ? 1 : 0;
-          return lane_base + (uint32_t)(a * kAccCols + (j - a * nl0) * 32);
-        };
-        // 16x256b: mma-style fragments -- r[4q], r[4q+1] = (lane t/4, tokens 8q + 2(t%4), +1); r[4q+2], r[4q+3] = lane + 8
-        // A tcgen05.ld takes ~300 cycles to come back here: the chunk that has landed is converted to 16-bit pairs
-        // first (16 registers), the loads of the next chunk are issued into the 32 registers that frees, and only then
-        // does the warp walk its chain of waits (staging tile free -> stmatrix -> proxy fence -> arrive), under which
-        // those loads complete.
-        uint32_t v0[16], v1[16];  // lanes 0..15 / 16..31 of the quadrant, 32 token columns
-        auto load_chunk = [&](int j) {
-          const uint32_t addr = chunk_addr(j);
-          ptx::tmem_ld_16x256b_x4(addr, v0);
-          ptx::tmem_ld_16x256b_x4(addr + (16u << 16), v1);
-        };
-        if (total > 0) load_chunk(0);
+        // Drain: per 32-column chunk one load -> convert -> stmatrix -> proxy fence -> publish chain (~520 cycles per
+        // chunk and warp: a single warp issues it at a few cycles per instruction).  Measured alternatives, all slower:
+        // loads issued one chunk ahead (convert first, then the next tcgen05.ld, then the chain: 6.7 k cycles per
+        // 2 x 176-token tile against 5.7 k), a warp-private transpose patch + st.global.v4 (8.2 k), one st.global.b16
+        // per token from the 32x32b load shape (21 k).
+        for (int a = 0; a < na; ++a) {
+          const int64_t ta = t0 + (int64_t)a * p.N_acc;
 #pragma unroll 1
-        for (int j = 0; j < total; ++j) {
-          uint32_t m[16];
-          ptx::tmem_ld_wait();  // chunk j
+          for (int c0 = 0; c0 < p.N_acc; c0 += 32) {
+            const bool live = ta + c0 < p.T;  // warp-uniform; dead chunks still release the accumulator below
+            // 16x256b: mma-style fragments -- r[4q], r[4q+1] = (lane t/4, tokens 8q + 2(t%4), +1); r[4q+2], r[4q+3] = lane + 8
+            uint32_t v0[16], v1[16];  // lanes 0..15 / 16..31 of the quadrant, 32 token columns
+            if (live) {
+              ptx::tmem_ld_16x256b_x4(lane_base + (uint32_t)(a * kAccCols + c0), v0);
+              ptx::tmem_ld_16x256b_x4(lane_base + (16u << 16) + (uint32_t)(a * kAccCols + c0), v1);
+              ptx::tmem_ld_wait();
+            }
+            if (c0 + 32 >= p.N_acc) {  // accumulator a is in registers / not needed: the issuer may overwrite it
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive_cluster(acc_empty_leader + 8u * (uint32_t)a);
+            }
+            if (!live) continue;
+            const uint32_t buf = epi_smem + sb * (uint32_t)kStgBytes;
+            ptx::mbar_wait(stg_empty0 + 8u * sb, sphase);  // the tile's previous store has read it
+            // tokens 8q..8q+7: four 8x8 matrices = feature groups 0-7, 8-15, 16-23, 24-31 (the 32 bias adds are
+            // skipped when there is no bias: this chain is issue-bound)
+            if (has_bias) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {  // tokens 8q..8q+7: four 8x8 matrices = feature groups 0-7, 8-15, 16-23, 24-31
-            m[4 * q] = pack2<ActT>(__uint_as_float(v0[4 * q]) + bias_v[0], __uint_as_float(v0[4 * q + 1]) + bias_v[0]);
-            m[4 * q + 1] = pack2<ActT>(__uint_as_float(v0[4 * q + 2]) + bias_v[1], __uint_as_float(v0[4 * q + 3]) + bias_v[1]);
-            m[4 * q + 2] = pack2<ActT>(__uint_as_float(v1[4 * q]) + bias_v[2], __uint_as_float(v1[4 * q + 1]) + bias_v[2]);
-            m[4 * q + 3] = pack2<ActT>(__uint_as_float(v1[4 * q + 2]) + bias_v[3], __uint_as_float(v1[4 * q + 3]) + bias_v[3]);
-          }
-          {  // the accumulator this chunk completes is in registers: the issuer may overwrite it
-            const int a = j >= nl0 ? 1 : 0;
-            if (j + 1 == nl0 + a * nl1) release(a);
-          }
-          if (j + 1 < total) load_chunk(j + 1);
-          const uint32_t buf = epi_smem + sb * (uint32_t)kStgBytes;
-          ptx::mbar_wait(stg_empty0 + 8u * sb, sphase);  // the tile's previous store has read it
-          if (!(p.debug & 4)) {
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t m0 = pack2<ActT>(__uint_as_float(v0[4 * q]) + bias_v[0], __uint_as_float(v0[4 * q + 1]) + bias_v[0]);
+                const uint32_t m1 = pack2<ActT>(__uint_as_float(v0[4 * q + 2]) + bias_v[1], __uint_as_float(v0[4 * q + 3]) + bias_v[1]);
+                const uint32_t m2 = pack2<ActT>(__uint_as_float(v1[4 * q]) + bias_v[2], __uint_as_float(v1[4 * q + 1]) + bias_v[2]);
+                const uint32_t m3 = pack2<ActT>(__uint_as_float(v1[4 * q + 2]) + bias_v[3], __uint_as_float(v1[4 * q + 3]) + bias_v[3]);
+                ptx::stmatrix_x4_trans(buf + (uint32_t)(q * 1024), m0, m1, m2, m3);
+              }
+            } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              ptx::stmatrix_x4_trans(buf + (uint32_t)(q * 1024), m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
-          }
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(stg_full0 + 8u * sb);  // the store warp takes it from here
-          if (++sb == (uint32_t)p.n_stg) {  // live chunks walk round the staging tiles
-            sb = 0;
-            sphase ^= 1u;
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t m0 = pack2<ActT>(__uint_as_float(v0[4 * q]), __uint_as_float(v0[4 * q + 1]));
+                const uint32_t m1 = pack2<ActT>(__uint_as_float(v0[4 * q + 2]), __uint_as_float(v0[4 * q + 3]));
+                const uint32_t m2 = pack2<ActT>(__uint_as_float(v1[4 * q]), __uint_as_float(v1[4 * q + 1]));
+                const uint32_t m3 = pack2<ActT>(__uint_as_float(v1[4 * q + 2]), __uint_as_float(v1[4 * q + 3]));
+                ptx::stmatrix_x4_trans(buf + (uint32_t)(q * 1024), m0, m1, m2, m3);
+              }
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(stg_full0 + 8u * sb);  // the store warp takes it from here
+            if (++sb == (uint32_t)p.n_stg) {  // live chunks walk round the staging tiles
+              sb = 0;
+              sphase ^= 1u;
+            }
           }
         }
       }
@@ -927,7 +920,11 @@ static int device_pairs() {
 // Padded rank of the down-projection that the forward launch can fuse (0: it cannot): 16-bit adapter rows that TMA
 // can address, a rank that fits the spare accumulator columns, and a problem large enough to run unsplit.
 static int fuse_rank(const LayerArgs& a, bool backward) {
-  if (backward || a.r <= 0 || env().tc2_fuse == 0) return 0;
+  // Off unless VFT_TC2_FUSE=1: measured at config #1 (T = 4096, 3072 x 3072, r = 16) the fused launch takes 64.8 us
+  // against 62.6 us for side kernel + plain launch -- the side-product MMAs re-read the staged activations from shared
+  // memory (+118 cycles on a 713-cycle ring step) and the round trip TMEM -> registers -> activation box -> adapter MMA
+  // sits between the last main MMA and the drain (+4.5 k cycles per tile).
+  if (backward || a.r <= 0 || env().tc2_fuse != 1) return 0;
   const int rp = a.r <= 16 ? 16 : 32;
   if (a.r > kMaxFuseRP || (reinterpret_cast<uintptr_t>(a.lora_a) & 15u) != 0) return 0;
   return rp;
@@ -945,7 +942,7 @@ static Tc2Choice choose_tc2(const LayerArgs& a, bool backward, int n_pairs) {
   Tc2Choice c;
   c.rp = fuse_rank(a, backward);
   if (c.rp > 0) {
-    c.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs, /*allow_split=*/env().tc2_fuse != 1, c.rp);
+    c.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs, /*allow_split=*/false, c.rp);
     if (c.plan.n_split == 1 && c.plan.cfg.N_acc > 0) return c;
     c.rp = 0;  // few tokens: the contraction is split over work items, the side product stays a kernel of its own
   }
@@ -1037,8 +1034,11 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   if (p.n_stg > kMaxStg) p.n_stg = kMaxStg;
   if (ev.tc2_n_stg >= 2 && ev.tc2_n_stg <= p.n_stg) p.n_stg = ev.tc2_n_stg;
   const int dyn_bytes = cfg.stages * p.stage_bytes + p.n_stg * kStgBytes + kBarBytes + 1024;  // + 1024-B alignment slack
-  auto kern = qlora_tc2_kernel<ActT, kBackward>;
-  VFT_OPT_IN_SMEM_ONCE(kern, VFT_MAX_DYN_SMEM);  // dyn_bytes depends on the plan: opt in to the limit
+  auto kern_plain = qlora_tc2_kernel<ActT, kBackward, false>;
+  auto kern_fused = qlora_tc2_kernel<ActT, false, true>;
+  VFT_OPT_IN_SMEM_ONCE(kern_plain, VFT_MAX_DYN_SMEM);  // dyn_bytes depends on the plan: opt in to the limit
+  if (!kBackward) VFT_OPT_IN_SMEM_ONCE(kern_fused, VFT_MAX_DYN_SMEM);
+  auto kern = (!kBackward && rp > 0) ? kern_fused : kern_plain;
   // the fewest pairs that still finish in the same number of waves (T = 4096, 3072 features: 144 tiles -> 72 pairs
   // of 2 tiles instead of 74): identical run time, and the SMs left over stay free for a concurrent NCCL all-reduce
   // of the LoRA gradients, which otherwise delays the launch of the last cluster until it has drained
