@@ -74,14 +74,27 @@ def make_cpu_case(T):
 
 def cpu_step(case, T):
     """What the reference does per call on its CPU path: dequantize W to bf16 (forward), F.linear + LoRA,
-    autograd backward (MatMul4Bit.backward dequantizes again)."""
-    from oracle import nf4_oracle, qlora_oracle
+    autograd backward (MatMul4Bit.backward dequantizes again).  The dequantisation is the plain-C restatement
+    (oracle/nf4_ref.c, OpenMP over all host threads -- bitsandbytes' CPU kernel is multi-threaded C++ too), the GEMMs
+    are torch's CPU bf16 matmuls on all host threads."""
+    from oracle import c_oracle, qlora_oracle
 
     p, a, _, x, dy, la, lb = case
-    w_deq = nf4_oracle.nf4_dequantize(p, a, (N_FEAT, K_FEAT), "bfloat16")  # forward dequant
+    n = N_FEAT * K_FEAT
+    w_deq = c_oracle.dequantize(p, a, n, "bfloat16").reshape(N_FEAT, K_FEAT)  # forward dequant
     out = qlora_oracle.qlora_linear_ref(x, w_deq, None, la, lb, 1.0, dy)
-    nf4_oracle.nf4_dequantize(p, a, (N_FEAT, K_FEAT), "bfloat16")  # backward dequant
+    c_oracle.dequantize(p, a, n, "bfloat16")  # backward dequant
     return out
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def time_cpu(T, steps, warmup):
@@ -98,24 +111,28 @@ def time_cpu(T, steps, warmup):
         cpu_step(case, T)
         times.append(time.perf_counter() - t0)
     mean = sum(times) / len(times)
-    return {"value": layer_flops(T) / mean / 1e12, "ms": mean * 1e3, "cores": torch.get_num_threads()}
+    return {"value": layer_flops(T) / mean / 1e12, "ms": mean * 1e3, "cores": torch.get_num_threads(),
+            "cpu_model": cpu_model()}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    T = 256  # bounded sample of the 4096-token batch (same layer, same seeds)
-    res = time_cpu(T, max(args.steps, 1), max(args.warmup, 1))
+    T = TOKENS  # the same configuration as the GPU arm: the full 4096-token batch per step (~1 s of host work each)
+    steps = max(1, min(args.steps, 20))  # bounded: the whole run stays within a couple of minutes
+    res = time_cpu(T, steps, max(1, min(args.warmup, 3)))
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms"], "higher_is_better": True,
+        "steps": steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": res["ms"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "single NF4 Linear 3072x3072 + LoRA r=16 fwd+bwd, bf16 (BASELINE configs[0])",
-                   "tokens_per_step": T, "note": "CPU path: dequantize W -> bf16, F.linear + LoRA, autograd backward"},
+        "config": {"workload": "single NF4 Linear 3072x3072 + LoRA r=16 fwd+bwd on 4096 tokens, bf16 (BASELINE configs[0])",
+                   "N": N_FEAT, "K": K_FEAT, "r": RANK, "tokens_per_gpu": T, "tokens_per_step": T, "same_config": True,
+                   "note": "CPU path: dequantize W -> bf16 (C, OpenMP), F.linear + LoRA, autograd backward, second dequantize"},
         "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port",
-                         "sample": f"{T} of {TOKENS} tokens per step; oracle port of the bitsandbytes+LoRA CPU path "
-                                   "(bitsandbytes 0.48.2 is not installable offline)"},
+                         "cpu_model": res["cpu_model"],
+                         "sample": f"all {TOKENS} tokens per step, {steps} timed steps; oracle port of the bitsandbytes+LoRA "
+                                   "CPU path (bitsandbytes 0.48.2 is not installable offline)"},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -154,7 +171,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.005)
+            self._stop.wait(0.01)
 
     def start(self):
         if self.nv is not None:
@@ -231,6 +248,7 @@ def run_gpu_arm(args):
         except Exception:  # pragma: no cover - older torch: default channel count
             pg_opts = None
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120), pg_options=pg_opts)
+    comm_group = None  # the default group: the 2-CTA communicator configured above
     peaks = measured_peaks()
     model = build_layer(dev)
     layer = model.linear
@@ -268,19 +286,37 @@ def run_gpu_arm(args):
                 step(i)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        # N > 1, --exchange graph (default): the all-reduce of the PREVIOUS step's gradient bucket is captured inside the
+        # step's graph on a forked stream, i.e. the exchange overlaps the next step's forward/backward and costs no host
+        # time per step (an eager NCCL call + event bookkeeping per 150-us step made the host loop the pacing item at 8
+        # ranks).  The buckets are allocated up front so that graph i can name the bucket graph i-1 fills.
+        n_grad = sum(p.numel() for p in params)
+        grad_bufs = [torch.zeros(n_grad, device=dev, dtype=torch.bfloat16) if world > 1 else None for _ in range(n_sets)]
+        in_graph = world > 1 and args.exchange == "graph"
+        fork = torch.cuda.Stream() if in_graph else None
         for i in range(n_sets):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
+                cur = torch.cuda.current_stream()
+                if in_graph:
+                    fork.wait_stream(cur)
+                    with torch.cuda.stream(fork):
+                        dist.all_reduce(grad_bufs[(i - 1) % n_sets], group=comm_group)
                 step(i)
-                # the flat bucket exists for the NCCL exchange only: a single rank has nothing to pack
-                flat = torch.cat([p.grad.reshape(-1) for p in params]) if world > 1 else None
+                if world > 1:  # the flat bucket exists for the NCCL exchange only: a single rank has nothing to pack
+                    torch.cat([p.grad.reshape(-1) for p in params], out=grad_bufs[i])
+                if in_graph:
+                    cur.wait_stream(fork)
             graphs.append(g)
-            grad_bufs.append(flat)
         torch.cuda.synchronize()
     except Exception as e:  # pragma: no cover - reported, not hidden
         print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
         graphs, launch_mode = [], "eager"
+        if args.exchange == "graph":
+            args.exchange = "overlap"
         torch.cuda.synchronize()
+    if world > 1:
+        launch_mode += f"+allreduce:{args.exchange}"
 
     comm = torch.cuda.Stream() if (world > 1 and args.exchange == "overlap") else None
     comm_events = [None] * n_sets
@@ -304,7 +340,7 @@ def run_gpu_arm(args):
                 done = torch.cuda.Event()
                 done.record()
             comm_events[s] = done
-        elif world > 1 and exchange:
+        elif world > 1 and exchange and args.exchange == "inorder":
             dist.all_reduce(flat)  # in stream order, right behind the step that produced the gradients
 
     def barrier():
@@ -312,12 +348,20 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # Everything with a host-side cost that differs between ranks happens BEFORE the barrier: nvmlInit() serialises the
+    # ranks of a node on a driver lock (8 processes: milliseconds), and a rank that starts its timed region late makes
+    # every other rank wait for it inside the per-step collective -- round 1's 8-GPU line measured exactly that skew.
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    align = torch.zeros(1, device=dev)
     for i in range(max(args.warmup, 3)):
         run_step(i)
+    if comm is not None:
+        torch.cuda.current_stream().wait_stream(comm)
     barrier()
-    sampler = ClockSampler(local)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.all_reduce(align)  # ranks leave this collective together ON THE DEVICE, right in front of the first event
     e0.record()
     for i in range(args.steps):
         run_step(i)
@@ -329,7 +373,7 @@ def run_gpu_arm(args):
     # keep the GPU under the same load a little longer if the region was too short to sample clocks
     t_end = time.time() + 0.25
     while len(sampler.samples) < 8 and time.time() < t_end:
-        run_step(0, exchange=False)  # rank-local padding: the number of iterations differs per rank, so no collective
+        step(0)  # rank-local padding (eager launches): the number of iterations differs per rank, so no collective
     torch.cuda.synchronize()
     clocks = sampler.stop()
     if world > 1:
@@ -544,9 +588,10 @@ def run_gpu_arm(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            r = time_cpu(512, 8, 1)  # ~10 s of host work on the box's cores
-            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                   "sample": f"512 of {TOKENS} tokens, 1 warm-up + 8 runs of the oracle port (dequant + F.linear + LoRA, autograd)"}
+            r = time_cpu(TOKENS, 5, 1)  # ~10 s of host work on the box's cores, the full 4096-token batch per run
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "cpu_model": r["cpu_model"],
+                   "sample": f"all {TOKENS} tokens, 1 warm-up + 5 runs of the oracle port (C/OpenMP dequant + F.linear + LoRA, "
+                             "autograd, second dequant)"}
         kernels_per_step = 5  # lora_side<x.A^T>, qlora_tc2<fwd> | lora_side<dy.B>, qlora_tc2<bwd>, lora_side<dA,dB>
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -566,10 +611,26 @@ def run_gpu_arm(args):
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        # Tear-down: the captured step graphs hold NCCL work; destroying the process group under them was seen to block
+        # for ever (torch 2.11 / NCCL 2.28).  Drop the graphs first, give destroy_process_group() ten seconds in a helper
+        # thread, and leave with exit code 0 either way -- the JSON line is already on stdout.
+        import gc
+
+        graphs.clear()
+        gc.collect()
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(10.0)
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
+    if os.environ.get("BENCH_WATCHDOG"):  # triage: dump every thread's stack and exit if the run takes longer than this
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -578,8 +639,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-census", action="store_true")
     ap.add_argument("--no-aura-step", action="store_true")
-    ap.add_argument("--exchange", default="overlap", choices=["inorder", "overlap"],
-                    help="N > 1: LoRA-gradient all-reduce in stream order behind each step, or on a side stream")
+    ap.add_argument("--exchange", default="graph", choices=["inorder", "overlap", "graph"],
+                    help="N > 1: LoRA-gradient all-reduce in stream order behind each step, on a side stream (eager NCCL "
+                         "call per step), or captured in the next step's CUDA graph on a forked stream (default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
