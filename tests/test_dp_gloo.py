@@ -79,6 +79,25 @@ def _worker(rank, world, port, out):
             reducer.wait()
             want2 = [sum(gs) / world for gs in zip(*[_local_grads(r, (2,)) for r in range(world)])]
             ok = ok and all(torch.allclose(p.grad, w, rtol=1e-5, atol=1e-7) for p, w in zip(trainable, want2))
+            # Rank 1 skips the last layer in this step (its adapter gets no gradient there): both ranks must still run
+            # the same collectives, rank 1 contributes zeros and RECEIVES the average (replicas must not drift)
+            for p in trainable:
+                p.grad = None
+            x = _batch(rank, 3)
+            h = model[3](model[2](model[1](model[0](x))))
+            (model[4](h) if rank == 0 else h).pow(2).mean().backward()
+            reducer.wait()
+            ref = _build()
+            xr = _batch(0, 3)
+            ref(xr).pow(2).mean().backward()
+            ref1 = _build()
+            x1 = _batch(1, 3)
+            ref1[3](ref1[2](ref1[1](ref1[0](x1)))).pow(2).mean().backward()
+            g0 = [p.grad for p in ref.parameters() if p.requires_grad]
+            g1 = [p.grad if p.grad is not None else torch.zeros_like(p) for p in ref1.parameters() if p.requires_grad]
+            want3 = [(a + b) / world for a, b in zip(g0, g1)]
+            ok = ok and all(p.grad is not None and torch.allclose(p.grad, w, rtol=1e-5, atol=1e-7)
+                            for p, w in zip(trainable, want3))
             reducer.remove()
             ok_all = ok_all and ok
         out[rank] = bool(ok_all)

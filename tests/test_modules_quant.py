@@ -284,3 +284,52 @@ def test_quantized_module_matches_oracle_and_moves_between_devices():
         model.linear(x)
     model.cuda()
     assert torch.equal(model.linear(x.cuda()), y)
+
+
+@pytest.mark.gpu
+@torch.no_grad()
+def test_deepcopy_owns_its_quant_state_and_inplace_updates_invalidate_derived_buffers():
+    """(a) a deep-copied module (EMA / reference copy) must not share its QuantState with the original --
+    moving the copy must leave the original on its device; (b) packed bytes / statistics overwritten IN PLACE (same
+    storage, same pointers) must rebuild the micro-tiled copy and the decoded statistics: the tcgen05 path (tiled copy)
+    and the few-token path (checkpoint layout) have to agree."""
+    import copy
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.linear = nn.Linear(256, 512, bias=False, dtype=torch.bfloat16)
+
+    torch.manual_seed(7)
+    model = M()
+    quantize_inplace(model, "bnb_nf4", include_keys=["linear"])
+    model.cuda()
+    x_many = torch.randn(96, 256, dtype=torch.bfloat16, device="cuda")   # tcgen05 path
+    x_few = x_many[:2].contiguous()                                       # few-token streaming path
+    y0 = model.linear(x_many)
+
+    # (a)
+    clone = copy.deepcopy(model)
+    assert clone.linear.weight.quant_state is not model.linear.weight.quant_state
+    assert clone.linear.weight.module is clone.linear and clone.linear.quant_state is clone.linear.weight.quant_state
+    assert clone.linear.weight.quant_state.absmax.data_ptr() != model.linear.weight.quant_state.absmax.data_ptr()
+    assert torch.equal(clone.linear(x_many), y0)
+    clone.cpu()
+    assert model.linear.weight.quant_state.absmax.is_cuda and model.linear.weight.quant_state.state2.absmax.is_cuda
+    assert torch.equal(model.linear(x_many), y0)
+
+    # (b) a second weight quantized into the SAME storage
+    other = M()
+    quantize_inplace(other, "bnb_nf4", include_keys=["linear"])
+    other.cuda()
+    y_other_many, y_other_few = other.linear(x_many), other.linear(x_few)
+    assert not torch.equal(y_other_many, y0)
+    w, qs = model.linear.weight, model.linear.weight.quant_state
+    ptrs = (w.data_ptr(), qs.absmax.data_ptr(), qs.state2.absmax.data_ptr())
+    w.data.copy_(other.linear.weight.data)
+    qs.absmax.copy_(other.linear.weight.quant_state.absmax)
+    qs.state2.absmax.copy_(other.linear.weight.quant_state.state2.absmax)
+    qs.offset = other.linear.weight.quant_state.offset.clone()
+    assert ptrs == (w.data_ptr(), qs.absmax.data_ptr(), qs.state2.absmax.data_ptr())
+    assert torch.equal(model.linear(x_many), y_other_many)
+    assert torch.equal(model.linear(x_few), y_other_few)

@@ -73,6 +73,8 @@ class LoRALinear(PeftLayer):
             torch.tensor(self.config.alpha, dtype=self.lora_down.weight.dtype), requires_grad=False
         )
         self.dropout = self._make_dropout()
+        if self.alpha.device.type != "meta":
+            self._scale_value()  # resolve alpha / rank on the host once, now (never on the hot path, never in a trace)
 
     def set_enabled(self, enabled: bool) -> None:
         self.enabled = enabled
@@ -102,6 +104,8 @@ class LoRALinear(PeftLayer):
     def _scale_value(self) -> float:
         # alpha is a frozen 0-dim parameter; cache its host value so the hot path never syncs
         cached = getattr(self, "_scale_cache", None)
+        if cached is not None and torch.compiler.is_compiling():
+            return cached[1]  # a torch.compile trace must not read pointers / sync: the value of the last eager call
         key = (self.alpha.data_ptr(), self.alpha._version, self.rank)
         if cached is None or cached[0] != key:
             # same rounding as the reference: (alpha / rank) evaluated in the adapter dtype

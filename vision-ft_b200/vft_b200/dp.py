@@ -76,6 +76,7 @@ class LoraGradReducer:
                 self._where[id(p)] = (b, i)
         self._cuda = bool(self.buckets) and self.buckets[0].flat.is_cuda
         self.stream = torch.cuda.Stream(device=self.buckets[0].flat.device) if self._cuda else None
+        self._next = 0  # first bucket that has not been launched in this step
         self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in plist]
 
     # ------------------------------------------------------------------ hooks
@@ -84,8 +85,12 @@ class LoraGradReducer:
             return
         b, _ = self._where[id(p)]
         b.pending -= 1
-        if b.pending == 0 and self.overlap:
-            self._launch(b)
+        # Collectives leave in BUCKET ORDER on every rank: a bucket that is complete is launched only once all buckets
+        # before it have left (the order in which buckets complete can differ between ranks -- a branch not taken on
+        # one of them -- and ranks issuing the same collectives in different orders deadlock or mix up buffers).
+        while self.overlap and self._next < len(self.buckets) and self.buckets[self._next].pending == 0:
+            self._launch(self.buckets[self._next])
+            self._next += 1
 
     def _pack(self, b: _Bucket) -> None:
         """All gradients of the bucket -> its flat buffer, one multi-tensor copy (missing gradients count as zero)."""
@@ -118,26 +123,29 @@ class LoraGradReducer:
             self.enabled = prev
 
     def wait(self) -> None:
-        """Block the current stream until every bucket is reduced; write the (averaged) sums back into .grad."""
+        """Block the current stream until every bucket is reduced; write the (averaged) sums back into .grad.
+
+        EVERY bucket is reduced on EVERY rank at each call, whether or not a gradient reached it on this rank (as DDP
+        does): which parameters receive a gradient can differ between ranks (a branch not taken, an empty ragged
+        bucket), and a rank-local decision to skip a bucket would make the ranks issue different collective sequences.
+        A parameter without a local gradient contributes zeros and RECEIVES the average (its .grad is created), so
+        the replicas stay identical."""
         if self.world == 1:
             return
-        ready = []
-        for b in self.buckets:  # first pass: everything that has not left yet leaves now
-            if b.pending == len(b.params) and b.work is None:
-                continue  # no gradient reached this bucket in this step
-            if b.work is None:
-                # deferred mode, or a bucket some of whose parameters received no gradient (they count as zero)
-                self._launch(b)
-            ready.append(b)
-        for b in ready:  # second pass: join and write back
+        for b in self.buckets[self._next:]:  # first pass: everything that has not left yet leaves now, in bucket order
+            # deferred mode, or a bucket some (or all) of whose parameters received no gradient: they count as zero
+            self._launch(b)
+        self._next = 0
+        for b in self.buckets:  # second pass: join and write back
             b.work.wait()
             if self._cuda:
                 torch.cuda.current_stream(b.flat.device).wait_stream(self.stream)
             if self.average and not self._cuda:
                 b.flat.div_(self.world)
-            have = [(p.grad, v) for v, p in zip(b.views, b.params) if p.grad is not None]
-            if have:
-                torch._foreach_copy_([g for g, _ in have], [v for _, v in have])
+            for v, p in zip(b.views, b.params):
+                if p.grad is None:
+                    p.grad = torch.empty_like(p)
+            torch._foreach_copy_([p.grad for p in b.params], list(b.views))
             b.pending = len(b.params)
             b.work = None
 

@@ -92,12 +92,30 @@ class QuantState:
     def absmax_f32(self) -> torch.Tensor:
         if not self.nested:
             return self.absmax
+        # keyed on identity + in-place version of everything it is decoded from: an absmax / state2 that is
+        # reassigned, or overwritten in place (weight.data.copy_, a reload into the same storage), invalidates it
+        s2 = self.state2
+        key = (self.absmax.data_ptr(), self.absmax._version, s2.absmax.data_ptr(), s2.absmax._version,
+               float(self.offset), self.absmax.device)
         cached = self.__dict__.get("_absmax_f32")
-        if cached is None or cached.device != self.absmax.device:
-            s2 = self.state2
-            cached = ops.absmax_denest(self.absmax, s2.absmax, s2.code, float(self.offset), s2.blocksize)
+        if cached is None or cached[0] != key:
+            cached = (key, ops.absmax_denest(self.absmax, s2.absmax, s2.code, float(self.offset), s2.blocksize))
             self.__dict__["_absmax_f32"] = cached
-        return cached
+        return cached[1]
+
+    def __deepcopy__(self, memo):
+        """Tensors cloned, derived buffers dropped (bitsandbytes deep-copies its QuantState too: a copied model --
+        EMA, reference copy -- must not share statistics that .to() moves in place)."""
+        import copy
+
+        new = QuantState(
+            absmax=self.absmax.clone(), shape=self.shape, dtype=self.dtype, blocksize=self.blocksize,
+            quant_type=self.quant_type, code=self.code.clone(),
+            offset=self.offset.clone() if torch.is_tensor(self.offset) else self.offset,
+            state2=copy.deepcopy(self.state2, memo),
+        )
+        memo[id(self)] = new
+        return new
 
     def to(self, device) -> "QuantState":
         self.absmax = self.absmax.to(device)
@@ -216,10 +234,19 @@ class Params4bit(torch.nn.Parameter):
         return self
 
     def __deepcopy__(self, memo):
+        import copy
+
+        # the owning module is resolved through memo (deepcopy of a model reaches it before its parameters); the
+        # quant state is copied, not shared
+        state = copy.deepcopy(self.quant_state, memo)
+        module = memo.get(id(self.module), self.module) if self.module is not None else None
         new = type(self).__new__(
-            type(self), self.data.clone(), self.requires_grad, self.quant_state, self.blocksize,
-            self.compress_statistics, self.quant_type, self.quant_storage, self.module, self.bnb_quantized,
+            type(self), self.data.clone(), self.requires_grad, state, self.blocksize,
+            self.compress_statistics, self.quant_type, self.quant_storage, module, self.bnb_quantized,
         )
+        memo[id(self)] = new
+        if module is not None and module is not self.module and state is not None:
+            module.quant_state = state
         return new
 
     @classmethod
@@ -284,6 +311,10 @@ class Linear4bit(nn.Linear):
         self.quant_state = None
         self.quant_storage = quant_storage
 
+    # derived device buffers (instance attributes once built; never parameters, buffers or state_dict entries)
+    _vft_operands = None
+    _vft_tiled = None
+
     def _packed(self):
         w = self.weight
         qs = getattr(w, "quant_state", None) or self.quant_state
@@ -298,8 +329,10 @@ class Linear4bit(nn.Linear):
         """Micro-tiled copy of the packed weight for the fused kernels, built once per (storage, device) on first
         use.  Derived data: not a parameter, not a buffer, never in state_dict()."""
         absmax = qs.absmax_f32()
-        key = (packed.data_ptr(), absmax.data_ptr(), packed.device)
-        cache = self.__dict__.get("_vft_tiled")
+        # identity AND in-place version: packed bytes rewritten in the same storage must rebuild the copy (the
+        # few-token kernel reads the checkpoint layout directly: a stale copy would make the two paths disagree)
+        key = (packed.data_ptr(), packed._version, absmax.data_ptr(), absmax._version, packed.device)
+        cache = self._vft_tiled
         if cache is None or cache[0] != key:
             tiles = ops.nf4_tile_weight(packed, absmax, self.out_features, self.in_features, qs.blocksize)
             cache = (key, tiles)
@@ -318,19 +351,30 @@ class Linear4bit(nn.Linear):
         # statistics) of the old one must not outlive it
         self.__dict__.pop("_vft_operands", None)
         self.__dict__.pop("_vft_tiled", None)
-        return super()._apply(fn, *args, **kwargs)
+        out = super()._apply(fn, *args, **kwargs)
+        # build them right away when the (quantized) weight now lives on a CUDA device: the first forward then finds
+        # them, and so does a torch.compile trace (which must not look at data pointers / version counters)
+        w = self.weight
+        if getattr(w, "bnb_quantized", False) and w.is_cuda and getattr(w, "quant_state", None) is not None:
+            self._operands()
+        return out
 
     def _operands(self):
         """(packed, fp32 absmax, blocksize, quant dtype, tiled copy) of the current weight, resolved once per
         (weight storage, quant state) and then served from a single cache hit: this runs in every forward, and
         host time per call is what bounds small-batch steps (tools/host_overhead.py)."""
         w = self.weight
-        cache = self.__dict__.get("_vft_operands")
-        if cache is not None and cache[0] is w and cache[1] == w.data_ptr():
+        cache = self._vft_operands
+        if torch.compiler.is_compiling():
+            # under torch.compile the buffers prepared by .cuda() / the first eager call are used as they are
+            if cache is None:
+                raise RuntimeError("Linear4bit: move the module to a CUDA device before compiling it")
+            return cache[2]
+        if cache is not None and cache[0] is w and cache[1] == (w.data_ptr(), w._version, cache[3].absmax._version):
             return cache[2]
         packed, qs = self._packed()
         ops_ = (packed, qs.absmax_f32(), qs.blocksize, qs.dtype, self._tiled(packed, qs))
-        self.__dict__["_vft_operands"] = (w, w.data_ptr(), ops_)
+        self.__dict__["_vft_operands"] = (w, (w.data_ptr(), w._version, qs.absmax._version), ops_, qs)
         return ops_
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -284,8 +284,125 @@ class QLoRALinearFunction(torch.autograd.Function):
         return dx, None, None, None, da, db, None, None, None, None, None, None
 
 
+# ----------------------------------------------------------------------------- torch.library registration
+# The reference compiles its denoiser with torch.compile(fullgraph=True) (configs/auraflow/lora.yml:82-85,
+# /root/reference/src/models/for_training.py:60-65).  An autograd.Function whose forward goes through ctypes cannot be
+# traced without a graph break, so the same two C-ABI call sequences are ALSO registered as custom operators with fake
+# (meta) implementations and an autograd formula; qlora_linear() switches to them while a compiler is tracing and keeps
+# the leaner autograd.Function for eager calls (an operator dispatch costs tens of microseconds of host time per call).
+def _empty(like: torch.Tensor) -> torch.Tensor:
+    return like.new_empty((0,))
+
+
+@torch.library.custom_op("vft_b200::qlora_fwd", mutates_args=())
+def _qlora_fwd_op(x: torch.Tensor, packed: torch.Tensor, absmax: torch.Tensor, bias: torch.Tensor | None,
+                  lora_a: torch.Tensor | None, lora_b: torch.Tensor | None, scale: float, out_features: int,
+                  in_features: int, blocksize: int, qdtype: int, codes_t: torch.Tensor | None,
+                  absmax_t: torch.Tensor | None) -> tuple[torch.Tensor, torch.Tensor]:
+    dev = _require_cuda(x, packed, absmax, bias, lora_a, lora_b)
+    N, K = out_features, in_features
+    if x.shape[-1] != K:
+        raise RuntimeError(f"input feature size {x.shape[-1]} does not match in_features {K}")
+    x2 = x.reshape(-1, K).contiguous()
+    T = x2.shape[0]
+    r = 0 if lora_a is None else int(lora_a.shape[0])
+    if r and (lora_a.dtype != x.dtype or lora_b.dtype != x.dtype):
+        raise RuntimeError("fused LoRA needs adapter weights in the activation dtype")
+    la = lora_a.contiguous() if r else None
+    lb = lora_b.contiguous() if r else None
+    if bias is not None:
+        bias = bias.to(x.dtype).contiguous()
+    y = torch.empty((*x.shape[:-1], N), dtype=x.dtype, device=dev)
+    t_save = torch.empty((T, LORA_LD), dtype=x.dtype, device=dev) if r else _empty(x)
+    ws, ws_bytes = _workspace(_cabi.OP_FWD, T, N, K, r, dev)
+    with _on_device(dev):
+        if T > 0:
+            check(lib.vft_qlora_fwd(x2.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, blocksize, dtype_code(x.dtype),
+                                    qdtype, _ptr(bias), _ptr(la), _ptr(lb), r, float(scale), y.data_ptr(),
+                                    t_save.data_ptr() if r else None, _ptr(ws), ws_bytes, _ptr(codes_t), _ptr(absmax_t), _stream()))
+    return y, t_save
+
+
+@_qlora_fwd_op.register_fake
+def _(x, packed, absmax, bias, lora_a, lora_b, scale, out_features, in_features, blocksize, qdtype, codes_t, absmax_t):
+    T = x.numel() // in_features
+    y = x.new_empty((*x.shape[:-1], out_features))
+    t_save = x.new_empty((T, LORA_LD)) if lora_a is not None else x.new_empty((0,))
+    return y, t_save
+
+
+@torch.library.custom_op("vft_b200::qlora_bwd", mutates_args=())
+def _qlora_bwd_op(dy: torch.Tensor, x: torch.Tensor, packed: torch.Tensor, absmax: torch.Tensor,
+                  lora_a: torch.Tensor | None, lora_b: torch.Tensor | None, t_save: torch.Tensor, scale: float,
+                  out_features: int, in_features: int, blocksize: int, qdtype: int, codes_t: torch.Tensor | None,
+                  absmax_t: torch.Tensor | None, need_dx: bool, need_ab: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    dev = dy.device
+    N, K = out_features, in_features
+    dy2 = dy.reshape(-1, N).to(x.dtype).contiguous()
+    x2 = x.reshape(-1, K).contiguous()
+    T = dy2.shape[0]
+    r = 0 if lora_a is None else int(lora_a.shape[0])
+    need_ab = need_ab and r > 0
+    la = lora_a.contiguous() if r else None
+    lb = lora_b.contiguous() if r else None
+    dx = torch.empty(x.shape, dtype=x.dtype, device=dev) if need_dx else _empty(x)
+    da = torch.zeros_like(la) if need_ab else _empty(x)
+    db = torch.zeros_like(lb) if need_ab else _empty(x)
+    if T == 0 or not (need_dx or need_ab):
+        return dx, da, db
+    dt_save = torch.empty((T, LORA_LD), dtype=x.dtype, device=dev) if r else None
+    act = dtype_code(x.dtype)
+    with _on_device(dev):
+        ws, ws_bytes = _workspace(_cabi.OP_BWD_DX, T, N, K, r, dev) if need_dx else (None, 0)
+        check(lib.vft_qlora_bwd_dx(dy2.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, blocksize, act, qdtype,
+                                   _ptr(la), _ptr(lb), r, float(scale), dx.data_ptr() if need_dx else None, _ptr(dt_save),
+                                   _ptr(ws), ws_bytes, _ptr(codes_t), _ptr(absmax_t), _stream()))
+        if need_ab:
+            ws_bytes = _workspace_bytes(_cabi.OP_BWD_DAB, T, N, K, r)
+            ws = torch.empty((max(ws_bytes, 4),), dtype=torch.uint8, device=dev)
+            check(lib.vft_lora_bwd_dab(dy2.data_ptr(), x2.data_ptr(), t_save.data_ptr(), dt_save.data_ptr(), T, N, K, r, act,
+                                       float(scale), da.data_ptr(), db.data_ptr(), ws.data_ptr(), ws_bytes, _stream()))
+    return dx, da, db
+
+
+@_qlora_bwd_op.register_fake
+def _(dy, x, packed, absmax, lora_a, lora_b, t_save, scale, out_features, in_features, blocksize, qdtype, codes_t,
+      absmax_t, need_dx, need_ab):
+    dx = x.new_empty(x.shape) if need_dx else x.new_empty((0,))
+    ab = need_ab and lora_a is not None
+    da = lora_a.new_empty(lora_a.shape) if ab else x.new_empty((0,))
+    db = lora_b.new_empty(lora_b.shape) if ab else x.new_empty((0,))
+    return dx, da, db
+
+
+def _op_setup_context(ctx, inputs, output):
+    x, packed, absmax, bias, lora_a, lora_b, scale, N, K, blocksize, qdtype, codes_t, absmax_t = inputs
+    _, t_save = output
+    ctx.meta = (float(scale), N, K, blocksize, qdtype)
+    ctx.save_for_backward(x, packed, absmax, lora_a, lora_b, t_save, codes_t, absmax_t)
+
+
+def _op_backward(ctx, dy, _dt_save):
+    scale, N, K, blocksize, qdtype = ctx.meta
+    x, packed, absmax, lora_a, lora_b, t_save, codes_t, absmax_t = ctx.saved_tensors
+    need_dx = ctx.needs_input_grad[0]
+    need_ab = lora_a is not None and (ctx.needs_input_grad[4] or ctx.needs_input_grad[5])
+    dx, da, db = _qlora_bwd_op(dy, x, packed, absmax, lora_a, lora_b, t_save, scale, N, K, blocksize, qdtype,
+                               codes_t, absmax_t, need_dx, need_ab)
+    return (dx if need_dx else None, None, None, None, da if need_ab else None, db if need_ab else None,
+            None, None, None, None, None, None, None)
+
+
+_qlora_fwd_op.register_autograd(_op_backward, setup_context=_op_setup_context)
+
+
 def qlora_linear(x, packed, absmax, bias, lora_a, lora_b, scale, out_features, in_features, blocksize=64,
                  qdtype=torch.bfloat16, tiled=None):
     """``tiled``: optional (codes_t, absmax_t) from :func:`nf4_tile_weight` for the same weight."""
+    if torch.compiler.is_compiling():  # traced by torch.compile: the registered operator (no graph break)
+        codes_t, absmax_t = tiled if tiled is not None else (None, None)
+        y, _ = _qlora_fwd_op(x, packed, absmax, bias, lora_a, lora_b, float(scale), int(out_features), int(in_features),
+                             int(blocksize), dtype_code(qdtype), codes_t, absmax_t)
+        return y
     return QLoRALinearFunction.apply(x, packed, absmax, bias, lora_a, lora_b, scale, out_features, in_features,
                                      blocksize, qdtype, tiled)
