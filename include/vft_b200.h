@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VFT_ABI_VERSION 3
+#define VFT_ABI_VERSION 4
 #define VFT_LORA_LD 64 /* leading dimension (elements) of the saved LoRA activations t_save / dt_save */
 
 enum vft_dtype { VFT_F32 = 0, VFT_F16 = 1, VFT_BF16 = 2 };
@@ -112,6 +112,12 @@ int vft_nf4_tile_weight(const uint8_t* packed, const float* absmax, int64_t N, i
  * bisection of v * (1.0f/absmax2) over code256 (nearest entry; a value exactly on a midpoint keeps the pivot). */
 int vft_absmax_nest(const float* absmax, int64_t nblocks, int blocksize2, const float* code256, uint8_t* absmax8,
                     float* absmax2, float* offset, void* ws, int64_t ws_bytes, void* stream);
+
+/* Same encode around a GIVEN offset (device fp32 scalar, read on the stream): bitsandbytes takes
+ * offset = absmax.mean() from torch on the device, whose summation order is torch's; a caller that wants checkpoints
+ * byte-identical to bitsandbytes' computes that scalar the same way and passes it here.  No workspace. */
+int vft_absmax_nest_at(const float* absmax, int64_t nblocks, int blocksize2, const float* code256, const float* offset,
+                       uint8_t* absmax8, float* absmax2, void* stream);
 
 /* Decode side: absmax_out[i] = code256[absmax8[i]] * absmax2[i / blocksize2] + offset (two fp32 roundings), i.e.
  * bitsandbytes.functional.dequantize_blockwise(absmax8, state2) + offset -- what every dequantize_4bit of a nested

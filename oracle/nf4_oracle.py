@@ -272,7 +272,7 @@ def dquantize8(code: np.ndarray, x: np.ndarray) -> np.ndarray:
     return out.astype(np.uint8)
 
 
-def absmax_nest(absmax, code: np.ndarray | None = None, blocksize2: int = NESTED_BLOCKSIZE):
+def absmax_nest(absmax, code: np.ndarray | None = None, blocksize2: int = NESTED_BLOCKSIZE, offset=None):
     """fp32 absmax -> (absmax8 uint8[n], absmax2 fp32[ceil(n/256)], offset fp32, code fp32[256]).
 
     ``offset`` is the correctly rounded fp32 mean (float64 accumulation).  bitsandbytes takes torch's fp32
@@ -281,7 +281,8 @@ def absmax_nest(absmax, code: np.ndarray | None = None, blocksize2: int = NESTED
     a = np.ascontiguousarray(np.asarray(absmax, np.float32).reshape(-1))
     code = dynamic_map() if code is None else np.asarray(code, np.float32)
     n = a.size
-    offset = np.float32(a.astype(np.float64).sum() / n)
+    # ``offset`` given: encode around that value (the module path passes torch's ``absmax.mean()``, as bitsandbytes does)
+    offset = np.float32(a.astype(np.float64).sum() / n) if offset is None else np.float32(offset)
     v = (a - offset).astype(np.float32)
     nb = (n + blocksize2 - 1) // blocksize2
     pad = nb * blocksize2 - n

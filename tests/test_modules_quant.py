@@ -265,7 +265,11 @@ def test_quantized_module_matches_oracle_and_moves_between_devices():
     assert torch.equal(model.linear.weight.data.cpu(), torch.from_numpy(p))
     # module default compress_statistics=True (bnb.py:44): nested statistics, each piece bit-exact vs the oracle
     qs = model.linear.weight.quant_state
-    q8, a2, off, code2 = nf4_oracle.absmax_nest(a)
+    # the module encodes around torch's fp32 absmax.mean() on the device (what bitsandbytes does); it must sit within
+    # a few ulps of the correctly rounded mean, and every other piece follows from it bit for bit
+    exact_mean = float(a.astype("float64").mean())
+    assert abs(float(qs.offset) - exact_mean) <= 4 * 2.0 ** -24 * exact_mean
+    q8, a2, off, code2 = nf4_oracle.absmax_nest(a, offset=float(qs.offset))
     assert qs.nested and torch.equal(qs.absmax.cpu(), torch.from_numpy(q8))
     assert torch.equal(qs.state2.absmax.cpu(), torch.from_numpy(a2)) and float(qs.offset) == float(off)
     assert torch.equal(qs.state2.code.cpu(), torch.from_numpy(code2))

@@ -66,7 +66,10 @@ def test_quantize_checkpoint_file_roundtrip(tmp_path):
         if f"{k}.quant_state.bitsandbytes__nf4" in disk:
             n_q += 1
             p, a = nf4_oracle.nf4_quantize(v)
-            q8, a2, off, code2 = nf4_oracle.absmax_nest(a)
+            meta = nf4_oracle.unpack_quant_state_blob(disk[f"{k}.quant_state.bitsandbytes__nf4"])
+            exact_mean = float(a.astype("float64").mean())
+            assert abs(meta["nested_offset"] - exact_mean) <= 4 * 2.0 ** -24 * exact_mean, k  # torch's fp32 mean on the device
+            q8, a2, off, code2 = nf4_oracle.absmax_nest(a, offset=meta["nested_offset"])
             assert disk[k].dtype == torch.uint8 and np.array_equal(disk[k].numpy(), p), k
             assert np.array_equal(disk[f"{k}.absmax"].numpy(), q8), k
             assert np.array_equal(disk[f"{k}.nested_absmax"].numpy(), a2), k

@@ -84,16 +84,21 @@ __global__ void __launch_bounds__(kNestThreads) absmax_nest_kernel(const float* 
                                                                    const float* __restrict__ code,
                                                                    const double* __restrict__ parts,
                                                                    uint8_t* __restrict__ q, float* __restrict__ absmax2,
-                                                                   float* __restrict__ offset_out) {
+                                                                   float* __restrict__ offset_out,
+                                                                   const float* __restrict__ offset_in) {
   __shared__ float s_code[256];
   __shared__ float s_offset;
   s_code[threadIdx.x] = code[threadIdx.x];
   if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int p = 0; p < kSumParts; ++p) t += parts[p];
-    const float off = (float)(t / (double)n);
-    s_offset = off;
-    if (blockIdx.x == 0) *offset_out = off;
+    if (offset_in != nullptr) {  // the caller's offset (bitsandbytes: torch's absmax.mean() on the device)
+      s_offset = *offset_in;
+    } else {
+      double t = 0.0;
+      for (int p = 0; p < kSumParts; ++p) t += parts[p];
+      const float off = (float)(t / (double)n);
+      s_offset = off;
+      if (blockIdx.x == 0) *offset_out = off;
+    }
   }
   __syncthreads();
   const float off = s_offset;
@@ -166,22 +171,26 @@ __global__ void __launch_bounds__(256) absmax_denest_kernel(const uint8_t* __res
 int64_t absmax_nest_workspace_bytes() { return (int64_t)sizeof(double) * kSumParts; }
 
 int launch_absmax_nest(const float* absmax, int64_t n, int blocksize2, const float* code256, uint8_t* absmax8,
-                       float* absmax2, float* offset_out, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                       float* absmax2, float* offset_out, void* ws, int64_t ws_bytes, cudaStream_t st,
+                       const float* offset_in) {
   VFT_REQUIRE(blocksize2 == 256, "nested statistics use blocksize 256 (bitsandbytes), got %d", blocksize2);
   VFT_REQUIRE(n > 0, "empty statistics vector");
   VFT_REQUIRE((reinterpret_cast<uintptr_t>(absmax) & 15u) == 0 && (reinterpret_cast<uintptr_t>(absmax8) & 7u) == 0,
               "absmax must be 16-byte aligned, absmax8 8-byte aligned");
-  if (ws == nullptr || ws_bytes < absmax_nest_workspace_bytes()) {
-    set_error("workspace too small: need %lld bytes, got %lld", (long long)absmax_nest_workspace_bytes(),
-              (long long)ws_bytes);
-    return VFT_ERR_WORKSPACE;
+  double* parts = nullptr;
+  if (offset_in == nullptr) {
+    if (ws == nullptr || ws_bytes < absmax_nest_workspace_bytes()) {
+      set_error("workspace too small: need %lld bytes, got %lld", (long long)absmax_nest_workspace_bytes(),
+                (long long)ws_bytes);
+      return VFT_ERR_WORKSPACE;
+    }
+    parts = static_cast<double*>(ws);
+    absmax_sum_kernel<<<kSumParts, kSumThreads, 0, st>>>(absmax, n, parts);
+    VFT_CUDA_OK(cudaGetLastError());
   }
-  double* parts = static_cast<double*>(ws);
-  absmax_sum_kernel<<<kSumParts, kSumThreads, 0, st>>>(absmax, n, parts);
-  VFT_CUDA_OK(cudaGetLastError());
   const int64_t nblk = ceil_div64(n, 256);
   const int grid = (int)(ceil_div64(nblk, kNestThreads / 32) < 148 * 4 ? ceil_div64(nblk, kNestThreads / 32) : 148 * 4);
-  absmax_nest_kernel<<<grid, kNestThreads, 0, st>>>(absmax, n, code256, parts, absmax8, absmax2, offset_out);
+  absmax_nest_kernel<<<grid, kNestThreads, 0, st>>>(absmax, n, code256, parts, absmax8, absmax2, offset_out, offset_in);
   VFT_CUDA_OK(cudaGetLastError());
   return VFT_OK;
 }

@@ -173,6 +173,13 @@ int vft_absmax_nest(const float* absmax, int64_t nblocks, int blocksize2, const 
                             static_cast<cudaStream_t>(stream));
 }
 
+int vft_absmax_nest_at(const float* absmax, int64_t nblocks, int blocksize2, const float* code256, const float* offset,
+                       uint8_t* absmax8, float* absmax2, void* stream) {
+  VFT_REQUIRE(absmax && code256 && offset && absmax8 && absmax2, "null pointer");
+  return launch_absmax_nest(absmax, nblocks, blocksize2, code256, absmax8, absmax2, nullptr, nullptr, 0,
+                            static_cast<cudaStream_t>(stream), offset);
+}
+
 int vft_absmax_denest(const uint8_t* absmax8, const float* absmax2, const float* code256, float offset,
                       int64_t nblocks, int blocksize2, float* absmax_out, void* stream) {
   VFT_REQUIRE(nblocks >= 0, "nblocks must be >= 0");

@@ -139,7 +139,8 @@ int launch_tile_weight(const uint8_t* packed, const float* absmax, int64_t N, in
 // nested block statistics (absmax_nest.cu)
 int64_t absmax_nest_workspace_bytes();
 int launch_absmax_nest(const float* absmax, int64_t n, int blocksize2, const float* code256, uint8_t* absmax8,
-                       float* absmax2, float* offset_out, void* ws, int64_t ws_bytes, cudaStream_t st);
+                       float* absmax2, float* offset_out, void* ws, int64_t ws_bytes, cudaStream_t st,
+                       const float* offset_in = nullptr);
 int launch_absmax_denest(const uint8_t* absmax8, const float* absmax2, const float* code256, float offset, int64_t n,
                          int blocksize2, float* out, cudaStream_t st);
 

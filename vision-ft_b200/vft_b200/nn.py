@@ -204,7 +204,11 @@ def quantize_4bit(w: torch.Tensor, blocksize: int = 64, compress_statistics: boo
         return packed, QuantState(absmax=absmax, shape=w.shape, dtype=w.dtype, blocksize=blocksize, quant_type="nf4")
     # nested statistics: offset = mean(absmax); 8-bit dynamic-map blockwise code of (absmax - offset), blocksize 256
     code2 = create_dynamic_map().to(absmax.device)
-    absmax8, absmax2, offset = ops.absmax_nest(absmax, code2, NESTED_BLOCKSIZE)
+    # offset exactly as bitsandbytes takes it -- torch's fp32 absmax.mean() on the device -- so that a checkpoint written
+    # here can be byte-identical to one written by the reference on the same machine (nested_offset sits in the JSON blob
+    # and every nested index depends on it); the library's own fp64-accumulated mean (offset=None) differs from it by
+    # at most the rounding of torch's summation order
+    absmax8, absmax2, offset = ops.absmax_nest(absmax, code2, NESTED_BLOCKSIZE, offset=absmax.mean())
     state2 = QuantState(absmax=absmax2, shape=absmax.shape, dtype=torch.float32, blocksize=NESTED_BLOCKSIZE,
                         quant_type="dynamic8", code=code2)
     return packed, QuantState(absmax=absmax8, shape=w.shape, dtype=w.dtype, blocksize=blocksize, quant_type="nf4",

@@ -118,8 +118,10 @@ def nf4_dequantize(packed: torch.Tensor, absmax: torch.Tensor, shape, dtype: tor
     return out
 
 
-def absmax_nest(absmax: torch.Tensor, code256: torch.Tensor, blocksize2: int = 256):
-    """Nested statistics encode: fp32 absmax -> (absmax8 uint8 [n], absmax2 fp32 [ceil(n/256)], offset fp32 0-dim)."""
+def absmax_nest(absmax: torch.Tensor, code256: torch.Tensor, blocksize2: int = 256, offset: torch.Tensor | None = None):
+    """Nested statistics encode: fp32 absmax -> (absmax8 uint8 [n], absmax2 fp32 [ceil(n/256)], offset fp32 0-dim).
+    ``offset``: a 0-dim fp32 device tensor to encode around (bitsandbytes: ``absmax.mean()``); None = the correctly
+    rounded mean, accumulated in fp64 in a fixed order by the library."""
     dev = _require_cuda(absmax, code256)
     absmax = absmax.contiguous().float()
     code256 = code256.contiguous().float()
@@ -128,6 +130,12 @@ def absmax_nest(absmax: torch.Tensor, code256: torch.Tensor, blocksize2: int = 2
     n = absmax.numel()
     absmax8 = torch.empty((n,), dtype=torch.uint8, device=dev)
     absmax2 = torch.empty(((n + blocksize2 - 1) // blocksize2,), dtype=torch.float32, device=dev)
+    if offset is not None:
+        offset = offset.detach().to(device=dev, dtype=torch.float32).reshape(()).contiguous()
+        with torch.cuda.device(dev):
+            check(lib.vft_absmax_nest_at(absmax.data_ptr(), n, blocksize2, code256.data_ptr(), offset.data_ptr(),
+                                         absmax8.data_ptr(), absmax2.data_ptr(), _stream()))
+        return absmax8, absmax2, offset
     offset = torch.empty((), dtype=torch.float32, device=dev)
     ws_bytes = lib.vft_workspace_bytes(_cabi.OP_ABSMAX_NEST, 0, 0, 0, 0)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
