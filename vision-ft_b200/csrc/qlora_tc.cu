@@ -454,8 +454,8 @@ bool tc_supported(const LayerArgs& a, bool backward) {
   return true;
 }
 
-bool tc_fuses_down(const LayerArgs& a) {
-  return tc_supported(a, false) && aligned16(a.lora_a) && tc2_fuses_down(a);
+bool tc_fuses_side(const LayerArgs& a, bool backward) {
+  return tc_supported(a, backward) && tc2_fuses_side(a, backward);
 }
 
 int tc_fwd(const LayerArgs& a, const void* x, void* y, void* t_save, cudaStream_t st) {

@@ -28,6 +28,7 @@
 //   warps 0-15  decode: four groups of 128 threads, group g owns pipeline steps g, g+4, ...
 #include <stdlib.h>
 
+#include <atomic>
 #include <type_traits>
 
 #include "nf4_lut.cuh"
@@ -57,7 +58,8 @@ constexpr int kCtrlRegs = 40, kEpiRegs = 88, kDecRegs = 88;
 constexpr int kATileBytes = kBM * kBK * 2;                // 16 KB decoded weight tile
 constexpr int kMaxStages = 8;
 constexpr int kMaxAcc = 2;
-constexpr int kMaxFuseRP = 32;  // largest padded rank whose down-projection is fused into the forward launch
+constexpr int kMaxSideRP = 32;  // largest padded rank whose side product (x.A^T / s.dy.B) is computed inside the launch
+constexpr int kMaxP0 = 8;       // slots of the side product's own little ring
 // TMEM columns.  Backward (weights staged in shared memory): two accumulators of up to 256 columns.  Forward
 // (kTmemA): the decoded weight tile itself lives in tensor memory -- 4 ring stages of 32 columns (64 16-bit values
 // per lane) above two accumulators of up to 192 columns -- so it costs no shared-memory bandwidth at all: the
@@ -73,7 +75,7 @@ struct AccLayout {
 constexpr int kTmemCols = 512;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kMaxStg = 16;  // output staging tiles
-constexpr int kBarBytes = (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg + 2) * 8 + 16;
+constexpr int kBarBytes = (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg + 2 * kMaxP0 + 1) * 8 + 16;
 constexpr int kStgBytes = 32 * kBM * 2;  // one staging tile [32 tokens][128 features] of 16-bit outputs (8 KB)
 constexpr int kEpiBytes = 2 * kStgBytes;  // the minimum: two tiles
 
@@ -103,15 +105,24 @@ struct Tc2Params {
   float* partial;
   int debug;        // VFT_TC_DEBUG triage mask (results are garbage when non-zero): 1 = no decode stores,
                     // 2 = no MMAs, 4 = no epilogue stores, 8 = no TMA loads
-  // Fused adapter down-projection (forward, n_split == 1): t = x . A^T is accumulated next to the main product by one
-  // extra tcgen05.mma per 128 staged token rows and ring step (M = token rows of the pair, N = r_pad, A operand =
-  // the activation box that is in shared memory anyway, B operand = a [r_pad/2 x 64] box of lora_down.weight per
-  // CTA) into spare TMEM columns; at the end of the tile's contraction the epilogue warps round it to the
-  // activation dtype and write it into the adapter step's activation box (and, feature block 0 only, to t_save).
-  int fuse;         // 0: the adapter step TMA-loads t_save / dt_save written by a side kernel
-  int r_pad;        // 16, 32 or 64: MMA N of the side product
-  int la_bytes;     // bytes of one CTA's lora_down box: (r_pad / 2) * 128
-  void* save;       // t_save [T, VFT_LORA_LD] (written when fuse)
+  // Side product inside the launch ("phase 0", n_split == 1).  The adapter step of every tile needs the rank-r
+  // projection of ITS tokens (forward: t = x . A^T, backward: dt = s * dy . B) -- 25 MB of activations against a
+  // 16-row operand, a kernel of its own until now (7.9 / 8.5 us at config #1 plus a launch gap each).  Here every CTA
+  // of the grid computes the projection of T / gridDim.x token rows ONCE (no redundancy between the feature blocks
+  // that share a token block), next to the main loop of its first work item: the producer thread interleaves the
+  // loads of [p0_rows x 64] activation boxes + [r_pad/2 x 64] boxes of the rank-r operand into a small ring of
+  // their own, the issuer interleaves M = 256 (128 rows per CTA, p0_rows of them real), N = r_pad MMAs into spare
+  // TMEM columns, the (otherwise idle) epilogue warps round the result and write it to t_save / dt_save, and a
+  // grid-wide counter tells the producers when every row is there -- long before the first adapter step loads it.
+  int side;           // 0: t_save / dt_save were written by a side kernel before this launch
+  int r_pad;          // 16 or 32: MMA N of the side product
+  int la_bytes;       // bytes of one CTA's box of the rank-r operand: (r_pad / 2) * 128
+  int p0_rows;        // token rows per CTA (multiple of 8, <= 128): rows [cta * p0_rows, +p0_rows)
+  int p0_slots;       // ring slots (<= kMaxP0)
+  int p0_slot_bytes;  // p0_rows * 128 + la_bytes
+  int p0_per_step;    // side-product steps issued per main ring step (2: done half-way through the first item)
+  void* save;         // t_save / dt_save [T, VFT_LORA_LD] (written when side != 0; the adapter step reads it)
+  unsigned* sync;     // {arrivals, generation} of the grid-wide counter (self-resetting; csrc pool, one pair per launch)
 };
 
 // Timeline of the leader CTA of pair 0 for performance triage (VFT_TC_DEBUG & 16): SM clock per event.
@@ -137,13 +148,13 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
   return v;
 }
 
-template <typename ActT, bool kBackward, bool kFuse>
+template <typename ActT, bool kBackward, bool kSide>
 __global__ void __launch_bounds__(kThreads, 1)
 qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_lora,
                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out16,
+                 const __grid_constant__ CUtensorMap map_p0a, const __grid_constant__ CUtensorMap map_p0w,
                  const Tc2Params p) {
   constexpr bool kTmemA = !kBackward;  // forward: decoded weights go to tensor memory, backward: shared memory
-  static_assert(!(kFuse && kBackward), "the fused side product exists in the forward kernel only");
   constexpr int kAccCols = AccLayout<kTmemA>::pitch;
   constexpr int kAOff = kTmemA ? 0 : kATileBytes;  // offset of the activation boxes inside a stage
   extern __shared__ uint8_t smem_raw[];
@@ -163,8 +174,12 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   const int tok_tile = p.n_acc * p.N_acc;
 
   // shared memory: [S stages: decoded weight tile | n_acc activation boxes][epilogue staging][barriers, TMEM slot]
+  // (side product: [p0_slots x (activation rows | rank-r operand box)] between the ring and the staging tiles; its
+  //  MMAs read 128 rows from the start of a slot whatever p0_rows is -- into the next slots / the staging tiles)
   const int epi_bytes = p.n_stg * kStgBytes;
-  const uint32_t bar_base = smem_base + (uint32_t)(S * p.stage_bytes + epi_bytes);
+  const int p0_bytes = kSide ? p.p0_slots * p.p0_slot_bytes : 0;
+  const uint32_t p0_base = smem_base + (uint32_t)(S * p.stage_bytes);
+  const uint32_t bar_base = smem_base + (uint32_t)(S * p.stage_bytes + p0_bytes + epi_bytes);
   auto bar_full = [&](int s) { return bar_base + 8u * s; };
   auto bar_empty = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   const uint32_t bar_acc_full = bar_base + 8u * (2 * kMaxStages);
@@ -172,21 +187,23 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   // output staging tiles: full[b] (the four epilogue warps have written tile b) / empty[b] (its TMA store has read it)
   auto bar_stg_full = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc + b); };
   auto bar_stg_empty = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc + kMaxStg + b); };
-  // fused down-projection: t_full (the tile's side product is complete in TMEM; multicast commit) and, on the leader,
-  // t_box (the epilogue warps of both CTAs have written the adapter step's activation box)
-  const uint32_t bar_t_full = bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg);
-  const uint32_t bar_t_box = bar_t_full + 8u;
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg + 2);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
-      smem_gen + S * p.stage_bytes + epi_bytes + 8 * (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg + 2));
+  // side product: full / empty per ring slot (same protocol as the main ring: bytes of both CTAs are counted on the
+  // leader's barrier, a multicast commit frees the slot in both) and "done" (multicast commit behind its last MMA)
+  constexpr int kBarP0 = 2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg;
+  auto bar_p0_full = [&](int i) { return bar_base + 8u * (kBarP0 + i); };
+  auto bar_p0_empty = [&](int i) { return bar_base + 8u * (kBarP0 + kMaxP0 + i); };
+  const uint32_t bar_p0_done = bar_base + 8u * (kBarP0 + 2 * kMaxP0);
+  const uint32_t tmem_slot = bar_base + 8u * (kBarP0 + 2 * kMaxP0 + 1);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
   auto stage_a = [&](int s) { return smem_base + (uint32_t)(s * p.stage_bytes); };
   auto stage_b = [&](int s, int a) { return smem_base + (uint32_t)(s * p.stage_bytes + kAOff + a * p.b_bytes); };
-  auto stage_la = [&](int s) { return stage_b(s, p.n_acc); };  // lora_down box behind the activation boxes
-  // TMEM columns of the side product of staged-row group g (128 token rows per CTA each): the tail of accumulator g's
-  // pitch (n_acc == 2: N_acc <= pitch - r_pad) or, with one accumulator, the columns below the weight ring
-  auto t_col = [&](int g) -> uint32_t {
-    return (uint32_t)(p.n_acc == 2 ? (g + 1) * kAccCols - p.r_pad : 2 * kAccCols - p.r_pad);
-  };
+  auto p0_slot = [&](int i) { return p0_base + (uint32_t)(i * p.p0_slot_bytes); };
+  // TMEM columns of the side product: the tail of accumulator 0's pitch (two accumulators: N_acc <= pitch - r_pad)
+  // or, with one accumulator, the tail of the second pitch
+  const uint32_t p0_col = (uint32_t)((p.n_acc == 2 ? 1 : 2) * kAccCols - p.r_pad);
+  const int n_p0 = kSide ? n_main : 0;  // side-product steps: one per 64 contraction elements
+  // grid-wide counter: generation before anybody of this launch can have arrived (read by the one thread that waits)
+  const int n_ctas = (int)gridDim.x;
   // accumulators of a tile that hold at least one real token (all roles derive it the same way)
   auto accs_of = [&](int64_t t0) -> int {
     const int64_t left = p.T - t0;
@@ -204,6 +221,10 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   };
 
   if (warp == kTmaWarp && ptx::elect_one()) {
+    if (kSide) {
+      ptx::tma_prefetch_desc(&map_p0a);
+      ptx::tma_prefetch_desc(&map_p0w);
+    }
     ptx::tma_prefetch_desc(&map_act);
     if (p.r > 0) ptx::tma_prefetch_desc(&map_lora);
     ptx::tma_prefetch_desc(&map_out);
@@ -215,8 +236,13 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       ptx::mbar_init(bar_empty(s), 1);         // multicast tcgen05.commit
     }
     ptx::mbar_init(bar_acc_full, 1);
-    ptx::mbar_init(bar_t_full, 1);
-    ptx::mbar_init(bar_t_box, 2 * 4);  // epilogue warps of both CTAs
+    if (kSide) {
+      for (int i = 0; i < p.p0_slots; ++i) {
+        ptx::mbar_init(bar_p0_full(i), 1);   // the leader's producer (expect_tx for both CTAs)
+        ptx::mbar_init(bar_p0_empty(i), 1);  // multicast tcgen05.commit
+      }
+      ptx::mbar_init(bar_p0_done, 1);
+    }
     for (int a = 0; a < kMaxAcc; ++a) ptx::mbar_init(bar_acc_empty(a), 2 * 4);  // epilogue warps of both CTAs
     for (int b = 0; b < p.n_stg; ++b) {
       ptx::mbar_init(bar_stg_full(b), 4);   // one arrive per epilogue warp
@@ -248,6 +274,8 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       ptx::griddep_wait();  // activations / saved adapter products come from the previous kernels
       int g = 0, s = 0;
       uint32_t empty_par = 1;
+      unsigned gen0 = 0;  // generation of the grid-wide counter before anybody of this launch can have arrived
+      if (kSide) gen0 = *reinterpret_cast<volatile unsigned*>(p.sync + 1);
       for (int item = pair; item < n_items; item += n_pairs) {
         const int tile = item_tile(item);
         const int64_t t0 = (int64_t)(tile / p.n_fblk) * tok_tile;
@@ -259,27 +287,77 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
           if (p.debug & 8) {
             if (rank == 0) ptx::mbar_arrive(bar_full(s));
           } else {
+            if (kSide && b == n_main && g == n_main) {
+              // first adapter step of this pair: its boxes are rows of t_save / dt_save that CTAs all over the grid
+              // are writing in this very launch.  Wait until the generation of the grid-wide counter moves (every
+              // epilogue warp of every CTA has published its rows; that happened a tile's worth of time ago).
+              const long long t_start = clock64();
+              unsigned gen;
+              do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(p.sync + 1) : "memory");
+                if (clock64() - t_start > 4000000000LL) __trap();
+              } while (gen == gen0);
+              tl_mark(p, 6, 252);
+              asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other SMs -> TMA reads
+            }
             // the leader arms its barrier for the bytes of BOTH CTAs; each CTA loads its N_acc/2 token rows
-            if (kFuse && b == n_main) {  // the epilogue warps fill the adapter step's boxes themselves
-              if (rank == 0) ptx::mbar_arrive(bar_full(s));
-            } else {
-              const int la = (kFuse && b < n_main) ? p.la_bytes : 0;
-              if (rank == 0) ptx::mbar_arrive_expect_tx(bar_full(s), (uint32_t)(2 * (na * p.b_bytes + la)));
-              const uint32_t leader_bar = ptx::mapa(bar_full(s), 0);
-              for (int a = 0; a < na; ++a) {
-                const int trow = (int)(t0 + (int64_t)a * p.N_acc) + (int)rank * (p.N_acc >> 1);
-                if (b < n_main)
-                  ptx::tma_load_2d_pair(&map_act, stage_b(s, a), leader_bar, b * kBK, trow);
-                else
-                  ptx::tma_load_2d_pair(&map_lora, stage_b(s, a), leader_bar, 0, trow);
-              }
-              // rows [rank * r_pad/2, +r_pad/2) of lora_down.weight (rows >= r: zero fill), contraction block b
-              if (la) ptx::tma_load_2d_pair(&map_lora, stage_la(s), leader_bar, b * kBK, (int)rank * (p.r_pad >> 1));
+            if (rank == 0) ptx::mbar_arrive_expect_tx(bar_full(s), (uint32_t)(2 * na * p.b_bytes));
+            const uint32_t leader_bar = ptx::mapa(bar_full(s), 0);
+            for (int a = 0; a < na; ++a) {
+              const int trow = (int)(t0 + (int64_t)a * p.N_acc) + (int)rank * (p.N_acc >> 1);
+              if (b < n_main)
+                ptx::tma_load_2d_pair(&map_act, stage_b(s, a), leader_bar, b * kBK, trow);
+              else
+                ptx::tma_load_2d_pair(&map_lora, stage_b(s, a), leader_bar, 0, trow);
             }
           }
           if (++s == S) {
             s = 0;
             empty_par ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (kSide && warp == kAllocWarp) {
+    // ------------------------------------------------------------- side product: its own producer + issuer
+    // A thread of its own (the TMEM-allocation warp has nothing else to do): with the side-product steps interleaved
+    // into the main producer and issuer loops, every main ring step of the first tile took 1500-2200 cycles instead
+    // of 712 -- an MMA costs the issuing thread ~40 cycles whatever its size, and barrier waits come on top.
+    // Loads of step i go to slot i % p0_slots once the MMAs of step i - p0_slots have read it; the leader's thread
+    // polls both of its duties so that neither can block the other.
+    if (ptx::elect_one()) {
+      ptx::griddep_wait();
+      const uint32_t idesc_p0 = ptx::make_idesc_f16(std::is_same<ActT, __nv_bfloat16>::value, false, false, 2 * kBM, p.r_pad);
+      int ld = 0, ld_s = 0, mm = 0, mm_s = 0;
+      uint32_t ld_par = 1, mm_par = 0;
+      while (ld < n_p0 || (rank == 0 && mm < n_p0)) {
+        if (ld < n_p0 && ptx::mbar_try_wait(bar_p0_empty(ld_s), ld_par)) {
+          const uint32_t dst = p0_slot(ld_s);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(bar_p0_full(ld_s), (uint32_t)(2 * p.p0_slot_bytes));
+          const uint32_t leader_bar = ptx::mapa(bar_p0_full(ld_s), 0);
+          ptx::tma_load_2d_pair(&map_p0a, dst, leader_bar, ld * kBK, (int)blockIdx.x * p.p0_rows);
+          ptx::tma_load_2d_pair(&map_p0w, dst + (uint32_t)(p.p0_rows * 128), leader_bar, ld * kBK,
+                                (int)rank * (p.r_pad >> 1));
+          ++ld;
+          if (++ld_s == p.p0_slots) {
+            ld_s = 0;
+            ld_par ^= 1u;
+          }
+        }
+        if (rank == 0 && mm < n_p0 && ptx::mbar_try_wait(bar_p0_full(mm_s), mm_par)) {
+          ptx::tc_fence_after();
+          // M = 256 (128 rows per CTA from the start of the slot, p0_rows of them real), N = r_pad, K-major operands
+          const uint64_t xa = ptx::make_smem_desc_sw128(p0_slot(mm_s), 16, 1024);
+          const uint64_t wa = ptx::make_smem_desc_sw128(p0_slot(mm_s) + (uint32_t)(p.p0_rows * 128), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            ptx::umma_ss_pair(tmem_d + p0_col, xa + k * (32u >> 4), wa + k * (32u >> 4), idesc_p0, (mm | k) != 0 ? 1u : 0u);
+          ptx::umma_commit_pair(bar_p0_empty(mm_s));
+          if (mm == n_p0 - 1) ptx::umma_commit_pair(bar_p0_done);  // -> epilogue warps, both CTAs
+          ++mm;
+          if (++mm_s == p.p0_slots) {
+            mm_s = 0;
+            mm_par ^= 1u;
           }
         }
       }
@@ -299,10 +377,8 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       constexpr uint32_t kBStep = 32u >> 4;
       const int k_lora = (p.r + 15) / 16;
       const bool do_mma = !(p.debug & 2);
-      // side product: M = 256 (128 staged token rows per CTA), N = r_pad, both operands K-major in shared memory
-      const uint32_t idesc_t = ptx::make_idesc_f16(std::is_same<ActT, __nv_bfloat16>::value, false, false, 2 * kBM, p.r_pad);
       int g = 0, s = 0;
-      uint32_t full_par = 0, acc_par = 1, tbox_par = 0;
+      uint32_t full_par = 0, acc_par = 1;
       for (int item = pair; item < n_items; item += n_pairs) {
         const int tile = item_tile(item);
         const int64_t t0 = (int64_t)(tile / p.n_fblk) * tok_tile;
@@ -328,29 +404,9 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             if (kTmemA) ptx::umma_ts_pair(d, a_tmem + (uint32_t)(8 * k), b_desc + k * kBStep, idesc, accumulate);
             else ptx::umma_ss_pair(d, a_desc + k * kAStep, b_desc + k * kBStep, idesc, accumulate);
           };
-          if (kFuse && b == n_main) {  // adapter step: the epilogue warps have rounded t into this stage's boxes
-            ptx::mbar_wait(bar_t_box, tbox_par);
-            tbox_par ^= 1u;
-            ptx::tc_fence_after();
-          }
           if (ptx::elect_one()) {
             if (do_mma) {
-              if (kFuse && b < n_main) {
-                // side-product MMAs interleaved with the main ones: each reads 128 staged rows x 32 bytes per CTA from
-                // shared memory (32 cycles of operand fetch for 8 cycles of math), which hides under the 88 cycles of
-                // the main MMA in front of it instead of queueing at the end of the step
-                const uint64_t la_desc = ptx::make_smem_desc_sw128(stage_la(s), 16, 1024);
-                const int n_grp = (na * (p.N_acc >> 1) + kBM - 1) / kBM;
-                const uint64_t x_desc1 = b_desc0 + (uint64_t)((kBM * 128) >> 4);  // staged rows 128.. of this CTA
-#pragma unroll
-                for (int k = 0; k < kBK / 16; ++k) {
-                  mma(tmem_d, k, b_desc0, k > 0 ? 1u : acc0);
-                  ptx::umma_ss_pair(tmem_d + t_col(0), b_desc0 + k * kBStep, la_desc + k * kBStep, idesc_t, k > 0 ? 1u : acc0);
-                  if (na > 1) mma(tmem_d + kAccCols, k, b_desc1, k > 0 ? 1u : acc0);
-                  if (n_grp > 1)
-                    ptx::umma_ss_pair(tmem_d + t_col(1), x_desc1 + k * kBStep, la_desc + k * kBStep, idesc_t, k > 0 ? 1u : acc0);
-                }
-              } else if (b < n_main) {
+              if (b < n_main) {
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k) mma(tmem_d, k, b_desc0, k > 0 ? 1u : acc0);
                 if (na > 1) {
@@ -364,7 +420,6 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
                 }
               }
             }
-            if (kFuse && b == n_main - 1) ptx::umma_commit_pair(bar_t_full);  // t complete -> epilogue warps, both CTAs
             ptx::umma_commit_pair(bar_empty(s));  // the stage is reusable in both CTAs once these MMAs have read it
             if (b == b1 - 1) ptx::umma_commit_pair(bar_acc_full);  // item complete -> epilogue warps, both CTAs
           }
@@ -440,8 +495,48 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     const uint32_t stg_full0 = pinned(bar_stg_full(0)), stg_empty0 = pinned(bar_stg_empty(0));
     const uint32_t acc_empty_leader = pinned(ptx::mapa(bar_acc_empty(0), 0));  // + 8 a: the leader's barrier
     uint32_t it = 0, sb = 0, sphase = 1;  // staging tile of the next live chunk; parity of its "empty" wait
-    int ring_pos = 0;                     // ring stage of this pair's next work item (fused down-projection)
     ptx::griddep_wait();  // bias / split-K workspace (zeroed by a memset node) / output ordering
+    if (kSide) {
+      // Side product of this CTA's token rows: lane = row, r_pad fp32 columns.  Round to the activation dtype, write
+      // the rows to t_save / dt_save (first r_pad columns; nothing reads the others) and count this warp in: the
+      // warp that completes the count resets it and bumps the generation the producers of all CTAs are watching.
+      ptx::mbar_wait(bar_p0_done, 0);
+      ptx::tc_fence_after();
+      if (et == 0) tl_mark(p, 6, 250);
+      if (quad * 32 < p.p0_rows) {
+        const int row = quad * 32 + lane;
+        const int64_t tok = (int64_t)blockIdx.x * p.p0_rows + row;
+        uint32_t pk[kMaxSideRP / 2];
+#pragma unroll
+        for (int c16 = 0; c16 < kMaxSideRP; c16 += 16) {
+          if (c16 < p.r_pad) {
+            uint32_t v[16];
+            ptx::tmem_ld_32x32b_x16(lane_base + p0_col + (uint32_t)c16, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              pk[(c16 >> 1) + e] = pack2<ActT>(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+          }
+        }
+        if (row < p.p0_rows && tok < p.T) {
+          uint4* orow = reinterpret_cast<uint4*>(static_cast<ActT*>(p.save) + tok * VFT_LORA_LD);
+#pragma unroll
+          for (int c = 0; c < kMaxSideRP / 8; ++c)
+            if (c < (p.r_pad >> 3)) orow[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        const unsigned total = 4u * (unsigned)n_ctas;
+        if (atomicAdd(p.sync, 1u) == total - 1u) {
+          atomicExch(p.sync, 0u);  // ready for the next launch that is handed this pair
+          __threadfence();
+          atomicAdd(p.sync + 1, 1u);
+        }
+      }
+      if (et == 0) tl_mark(p, 6, 251);
+    }
     for (int item = pair; item < n_items; item += n_pairs, ++it) {
       const int tile = item_tile(item);
       const int64_t t0 = (int64_t)(tile / p.n_fblk) * tok_tile;
@@ -455,72 +550,6 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         for (int u = 0; u < 4; ++u) {
           const int64_t f = feat0 + quad * 32 + (lane >> 2) + 8 * u;
           if (f < OUT) bias_v[u] = to_f32<ActT>(static_cast<const ActT*>(p.bias)[f]);
-        }
-      }
-      if (kFuse) {
-        // Side product of this tile: lane = staged token row (group g: rows 128 g ..), r_pad fp32 columns.  Round to
-        // the activation dtype and write the rows into the adapter step's activation boxes (K-major, 128-byte rows,
-        // SWIZZLE_128B: 16-byte chunk c of row i sits at chunk c ^ (i % 8)); that stage was last read by MMAs that
-        // were issued before the commit we have just waited for, so it is free.
-        const int s_ad = (ring_pos + n_main) % S;
-        ring_pos = (ring_pos + n_main + 1) % S;
-        const int half = p.N_acc >> 1;
-        const int rows = na * half;
-        const int n_grp = (rows + kBM - 1) / kBM;
-        ptx::mbar_wait(bar_t_full, it & 1u);
-        ptx::tc_fence_after();
-        if (et == 0) tl_mark(p, 4, 4 * (int)it);
-        auto load_rows = [&](int gr, uint32_t (&pk)[kMaxFuseRP / 2]) {
-#pragma unroll
-          for (int c16 = 0; c16 < kMaxFuseRP; c16 += 16) {
-            if (c16 < p.r_pad) {
-              uint32_t v[16];
-              ptx::tmem_ld_32x32b_x16(lane_base + t_col(gr) + (uint32_t)c16, v);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                pk[(c16 >> 1) + e] = pack2<ActT>(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) pk[(c16 >> 1) + e] = 0u;
-            }
-          }
-        };
-        for (int gr = 0; gr < n_grp; ++gr) {
-          const int i = gr * kBM + quad * 32 + lane;  // staged row of this thread
-          uint32_t pk[kMaxFuseRP / 2];                // r_pad 16-bit values (columns >= r are exact zeros)
-          load_rows(gr, pk);
-          if (i < rows) {
-            const int a = i >= half ? 1 : 0, ri = i - a * half;
-            const uint32_t row_addr = stage_b(s_ad, a) + (uint32_t)((ri >> 3) * 1024 + (ri & 7) * 128);
-#pragma unroll
-            for (int c = 0; c < kMaxFuseRP / 8; ++c)
-              if (c < (p.r_pad >> 3))
-                ptx::sts128(row_addr + (uint32_t)((c ^ (ri & 7)) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-          }
-        }
-        ptx::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar_t_box, 0));
-        if (et == 0) tl_mark(p, 4, 4 * (int)it + 1);
-        // Feature block 0 also saves the rows for the backward pass (t_save [T, VFT_LORA_LD]: the first r_pad columns;
-        // nothing reads the others), while the adapter step's MMAs run.  TMEM still holds the side product: nothing
-        // overwrites it before the drain below.
-        if (tile % p.n_fblk == 0) {
-          for (int gr = 0; gr < n_grp; ++gr) {
-            const int i = gr * kBM + quad * 32 + lane;
-            uint32_t pk[kMaxFuseRP / 2];
-            load_rows(gr, pk);
-            const int a = i >= half ? 1 : 0;
-            const int64_t tok = t0 + (int64_t)a * p.N_acc + (int64_t)rank * half + (i - a * half);
-            if (i < rows && tok < p.T) {
-              uint4* orow = reinterpret_cast<uint4*>(static_cast<ActT*>(p.save) + tok * VFT_LORA_LD);
-#pragma unroll
-              for (int c = 0; c < kMaxFuseRP / 8; ++c)
-                if (c < (p.r_pad >> 3)) orow[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-            }
-          }
         }
       }
       ptx::mbar_wait(bar_acc_full, it & 1u);
@@ -827,11 +856,12 @@ struct Tc2Config {
 // K = 64), decode ~600 ALU-pipe cycles per 128 x 64 weight tile, shared memory 128 B/clk over the activation
 // boxes (written by TMA, read by the MMA) and -- backward only -- the decoded tile (written once, read once per
 // accumulator).
-// `rp`: padded rank of a fused down-projection (0: none) -- costs a [rp/2 x 64] box per stage and the last rp columns
-// of each accumulator pitch.
+// `rp`: padded rank of a side product computed inside the launch (0: none) -- costs its ring (kP0Budget bytes of
+// shared memory) and the last rp columns of an accumulator pitch.
+constexpr int kP0Budget = 40 * 1024;
 static int max_stages(bool tmem_a, int n_acc, int N_acc, int rp) {
-  const int stage_bytes = (tmem_a ? 0 : kATileBytes) + n_acc * (N_acc / 2) * 128 + (rp / 2) * 128;
-  int stages = (kSmemLimit - kBarBytes - kEpiBytes - 1024) / stage_bytes;
+  const int stage_bytes = (tmem_a ? 0 : kATileBytes) + n_acc * (N_acc / 2) * 128;
+  int stages = (kSmemLimit - kBarBytes - kEpiBytes - 1024 - (rp > 0 ? kP0Budget : 0)) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (tmem_a && stages > kTmemAStages) stages = kTmemAStages;  // the weight ring in tensor memory has 4 slots
   // four stages (one per decode group) keep the tensor pipe fed; shared memory beyond that is worth more as output
@@ -844,7 +874,7 @@ static int max_stages(bool tmem_a, int n_acc, int N_acc, int rp) {
 static bool config_ok(bool tmem_a, int n_acc, int N_acc, int rp) {
   if (n_acc < 1 || n_acc > kMaxAcc || N_acc < 16 || N_acc > 256 || N_acc % 16 != 0) return false;
   if (tmem_a && n_acc == 2 && N_acc > AccLayout<true>::pitch) return false;
-  if (rp > 0) {  // side-product columns: the tail of each pitch (two accumulators) / the columns above the only one
+  if (rp > 0) {  // side-product columns: the tail of the first pitch (two accumulators) / of the second (one)
     const int pitch = tmem_a ? AccLayout<true>::pitch : AccLayout<false>::pitch;
     if (n_acc == 2 ? N_acc > pitch - rp : N_acc > 2 * pitch - rp) return false;
   }
@@ -917,39 +947,89 @@ static int device_pairs() {
   return n_sm / 2 > 0 ? n_sm / 2 : 1;
 }
 
-// Padded rank of the down-projection that the forward launch can fuse (0: it cannot): 16-bit adapter rows that TMA
-// can address, a rank that fits the spare accumulator columns, and a problem large enough to run unsplit.
-static int fuse_rank(const LayerArgs& a, bool backward) {
-  // Off unless VFT_TC2_FUSE=1: measured at config #1 (T = 4096, 3072 x 3072, r = 16) the fused launch takes 64.8 us
-  // against 62.6 us for side kernel + plain launch -- the side-product MMAs re-read the staged activations from shared
-  // memory (+118 cycles on a 713-cycle ring step) and the round trip TMEM -> registers -> activation box -> adapter MMA
-  // sits between the last main MMA and the drain (+4.5 k cycles per tile).
-  if (backward || a.r <= 0 || env().tc2_fuse != 1) return 0;
-  const int rp = a.r <= 16 ? 16 : 32;
-  if (a.r > kMaxFuseRP || (reinterpret_cast<uintptr_t>(a.lora_a) & 15u) != 0) return 0;
-  return rp;
+// Padded rank of the side product (forward: t = x . A^T, backward: dt = s * dy . B) that the launch computes itself,
+// 0 if it cannot: the rank-r operand must be a K-major [r_pad, contraction] matrix that TMA can address -- forward:
+// lora_down.weight as it is; backward: `bt` = s * lora_up.weight^T, written by the forward call -- and the rank has to
+// fit the spare accumulator columns.  VFT_TC2_FUSE=0 keeps the side kernels of lora_tc.cu.
+static int side_rank(const LayerArgs& a, bool backward) {
+  if (a.r <= 0 || a.r > kMaxSideRP || env().tc2_fuse == 0) return 0;
+  const void* w = backward ? a.bt_save : a.lora_a;
+  if (w == nullptr || (reinterpret_cast<uintptr_t>(w) & 15u) != 0) return 0;
+  return a.r <= 16 ? 16 : 32;
 }
 
 struct Tc2Choice {
   Tc2Plan plan;
-  int rp;  // > 0: fused down-projection
+  int rp;       // > 0: side product inside the launch
+  int pairs;    // CTA pairs launched
+  int p0_rows;  // token rows per CTA of the side product
 };
 
+// the fewest pairs that still finish in the same number of waves (T = 4096, 3072 features: 144 tiles -> 72 pairs
+// of 2 tiles instead of 74): identical run time, and the SMs left over stay free for a concurrent NCCL all-reduce
+// of the LoRA gradients, which otherwise delays the launch of the last cluster until it has drained
+static int pairs_for(const Tc2Plan& plan, int n_pairs) {
+  const int n_items = plan.n_tiles * plan.n_split;
+  const int waves = (n_items + n_pairs - 1) / n_pairs;
+  return (n_items + waves - 1) / waves;
+}
+
+// Everything the launch is decided by, in one place (the API asks the same function whether the side kernel can be
+// skipped): tile shape, split, side product, grid.
 static Tc2Choice choose_tc2(const LayerArgs& a, bool backward, int n_pairs) {
   const int64_t OUT = backward ? a.K : a.N;
   const int64_t RED = backward ? a.N : a.K;
   const bool tmem_a = !backward;
+  const VftEnv& ev = env();
   Tc2Choice c;
-  c.rp = fuse_rank(a, backward);
+  c.p0_rows = 0;
+  // triage override VFT_TC2_NACC="<n_acc>x<N_acc>" (clamped to what the path allows): forces the shape, never splits
+  auto forced = [&](int rp) -> bool {
+    if (ev.tc2_force_na <= 0) return false;
+    int na = ev.tc2_force_na, nn = ev.tc2_force_nn;
+    if (tmem_a && na == 2 && nn > AccLayout<true>::pitch) nn = AccLayout<true>::pitch;
+    if (!config_ok(tmem_a, na, nn, rp)) return false;
+    c.plan.cfg = {na, nn, max_stages(tmem_a, na, nn, rp), 0.0};
+    c.plan.n_tiles = (int)(ceil_div64(OUT, 2 * kBM) * ceil_div64(a.T, (int64_t)na * nn));
+    c.plan.n_split = 1;
+    c.plan.k_per = (int)ceil_div64(RED, kBK);
+    c.plan.ws_bytes = 0;
+    return true;
+  };
+  c.rp = side_rank(a, backward);
   if (c.rp > 0) {
+    // the plan the launch would take without it decides: a problem small enough to be split along the contraction
+    // keeps its side kernel (which is then tiny), so does one with more tokens than one pass of 128 rows per CTA holds
+    const Tc2Plan base = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs);
     c.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs, /*allow_split=*/false, c.rp);
-    if (c.plan.n_split == 1 && c.plan.cfg.N_acc > 0) return c;
-    c.rp = 0;  // few tokens: the contraction is split over work items, the side product stays a kernel of its own
+    forced(c.rp);
+    c.pairs = pairs_for(c.plan, n_pairs);
+    const int64_t rows = ceil_div64(ceil_div64(a.T, 2 * c.pairs), 8) * 8;
+    if ((base.n_split == 1 || ev.tc2_fuse == 1) && c.plan.cfg.N_acc > 0 && rows <= kBM) {
+      c.p0_rows = (int)rows;
+      return c;
+    }
+    c.rp = 0;
   }
   c.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs);
-  if (c.plan.n_split > 1 && (a.ws == nullptr || a.ws_bytes < c.plan.ws_bytes || env().tc2_nosplit))
+  if (c.plan.n_split > 1 && (a.ws == nullptr || a.ws_bytes < c.plan.ws_bytes || ev.tc2_nosplit))
     c.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs, /*allow_split=*/false);  // no workspace: unsplit shape
+  forced(0);
+  c.pairs = pairs_for(c.plan, n_pairs);
   return c;
+}
+
+// {arrivals, generation} pairs of the grid-wide counters of the side product, handed out round-robin per launch: zero at
+// module load, every launch leaves its pair at arrivals == 0.  Two launches share a pair only if kSyncSlots launches
+// were issued in between, i.e. the earlier one has long finished (same-stream launches run in order); the one thing
+// to avoid is replaying ONE captured graph concurrently with itself on two streams.
+constexpr int kSyncSlots = 4096;
+__device__ unsigned g_tc2_sync[2 * kSyncSlots];
+static unsigned* next_sync_pair() {
+  static std::atomic<unsigned> next{0};
+  unsigned* base = nullptr;
+  if (cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_tc2_sync) != cudaSuccess) return nullptr;
+  return base + 2 * (next.fetch_add(1, std::memory_order_relaxed) % kSyncSlots);
 }
 
 template <typename ActT, bool kBackward>
@@ -963,17 +1043,6 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   const Tc2Plan& plan = choice.plan;
   const int rp = choice.rp;
   Tc2Config cfg = plan.cfg;
-  bool forced_cfg = false;
-  if (ev.tc2_force_na > 0) {  // triage override VFT_TC2_NACC="<n_acc>x<N_acc>" (clamped to what the path allows)
-    int na = ev.tc2_force_na, nn = ev.tc2_force_nn;
-    if (kTmemA && na == 2 && nn > AccLayout<true>::pitch) nn = AccLayout<true>::pitch;
-    if (config_ok(kTmemA, na, nn, rp)) {
-      cfg.n_acc = na;
-      cfg.N_acc = nn;
-      cfg.stages = max_stages(kTmemA, na, nn, rp);
-      forced_cfg = true;
-    }
-  }
   if (ev.tc2_stages >= kGroups && ev.tc2_stages <= cfg.stages) cfg.stages = ev.tc2_stages;
 
   Tc2Params p;
@@ -987,18 +1056,31 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   p.n_acc = cfg.n_acc;
   p.N_acc = cfg.N_acc;
   p.stages = cfg.stages;
-  p.fuse = rp > 0 ? 1 : 0;
+  p.side = rp > 0 ? 1 : 0;
   p.r_pad = rp > 0 ? rp : 16;
-  p.la_bytes = rp > 0 ? (rp / 2) * 128 : 0;
+  p.la_bytes = (p.r_pad / 2) * 128;
+  p.p0_rows = rp > 0 ? choice.p0_rows : 8;
+  p.p0_slot_bytes = p.p0_rows * 128 + p.la_bytes;
+  p.p0_slots = rp > 0 ? kP0Budget / p.p0_slot_bytes : 0;
+  if (p.p0_slots > kMaxP0) p.p0_slots = kMaxP0;
+  p.p0_per_step = 2;
   p.save = lora_act;
+  p.sync = nullptr;
+  if (rp > 0) {
+    p.sync = next_sync_pair();
+    if (p.sync == nullptr) {
+      set_error("cudaGetSymbolAddress(g_tc2_sync) failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return VFT_ERR_CUDA;
+    }
+  }
   p.b_bytes = (cfg.N_acc / 2) * 128;
-  p.stage_bytes = (kTmemA ? 0 : kATileBytes) + cfg.n_acc * p.b_bytes + p.la_bytes;
+  p.stage_bytes = (kTmemA ? 0 : kATileBytes) + cfg.n_acc * p.b_bytes;
   p.n_fblk = (int)ceil_div64(OUT, 2 * kBM);
   p.n_tiles = p.n_fblk * (int)ceil_div64(a.T, (int64_t)cfg.n_acc * cfg.N_acc);
   p.n_split = 1;
   p.k_per = (int)ceil_div64(RED, kBK);
   p.partial = nullptr;
-  if (!forced_cfg && plan.n_split > 1) {
+  if (plan.n_split > 1) {
     p.n_split = plan.n_split;
     p.k_per = plan.k_per;
     p.partial = static_cast<float*>(a.ws);
@@ -1008,7 +1090,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
 
   const CUtensorMapDataType dt =
       std::is_same<ActT, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  CUtensorMap map_act, map_lora, map_out, map_out16;
+  CUtensorMap map_act, map_lora, map_out, map_out16, map_p0a, map_p0w;
   int rc = make_map_2d(&map_act, dt, act, (uint64_t)RED, (uint64_t)a.T, (uint64_t)RED * 2, kBK, cfg.N_acc / 2,
                        CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != VFT_OK) return rc;
@@ -1017,11 +1099,18 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   if (rc != VFT_OK) return rc;
   rc = make_map_2d(&map_out16, dt, out, (uint64_t)OUT, (uint64_t)a.T, (uint64_t)OUT * 2, 64, 16, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != VFT_OK) return rc;
-  if (rp > 0) {  // lora_down.weight [r, K]: boxes of [rp/2 rows x 64 contraction elements], rows >= r zero-filled
-    rc = make_map_2d(&map_lora, dt, a.lora_a, (uint64_t)a.K, (uint64_t)a.r, (uint64_t)a.K * 2, kBK, rp / 2,
+  map_p0a = map_p0w = map_act;
+  if (rp > 0) {
+    // side product: [p0_rows x 64] boxes of the activations; the rank-r operand as a K-major [rows, contraction] matrix
+    // in boxes of [rp/2 rows x 64] (forward: lora_down.weight [r, K], rows >= r zero-filled; backward: bt [rp, N])
+    rc = make_map_2d(&map_p0a, dt, act, (uint64_t)RED, (uint64_t)a.T, (uint64_t)RED * 2, kBK, (uint32_t)p.p0_rows,
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != VFT_OK) return rc;
-  } else if (a.r > 0) {
+    rc = make_map_2d(&map_p0w, dt, kBackward ? a.bt_save : a.lora_a, (uint64_t)RED, (uint64_t)(kBackward ? rp : a.r),
+                     (uint64_t)RED * 2, kBK, (uint32_t)(rp / 2), CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != VFT_OK) return rc;
+  }
+  if (a.r > 0) {
     rc = make_map_2d(&map_lora, dt, lora_act, VFT_LORA_LD, (uint64_t)a.T, VFT_LORA_LD * 2, kBK, cfg.N_acc / 2,
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != VFT_OK) return rc;
@@ -1030,21 +1119,17 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   }
 
   // output staging tiles from what the ring leaves over (a whole tile of 2 x 176 tokens is 11 of them)
-  p.n_stg = (kSmemLimit - kBarBytes - 1024 - cfg.stages * p.stage_bytes) / kStgBytes;
+  const int p0_bytes = p.p0_slots * p.p0_slot_bytes;
+  p.n_stg = (kSmemLimit - kBarBytes - 1024 - cfg.stages * p.stage_bytes - p0_bytes) / kStgBytes;
   if (p.n_stg > kMaxStg) p.n_stg = kMaxStg;
   if (ev.tc2_n_stg >= 2 && ev.tc2_n_stg <= p.n_stg) p.n_stg = ev.tc2_n_stg;
-  const int dyn_bytes = cfg.stages * p.stage_bytes + p.n_stg * kStgBytes + kBarBytes + 1024;  // + 1024-B alignment slack
+  const int dyn_bytes = cfg.stages * p.stage_bytes + p0_bytes + p.n_stg * kStgBytes + kBarBytes + 1024;  // + 1024-B alignment slack
   auto kern_plain = qlora_tc2_kernel<ActT, kBackward, false>;
-  auto kern_fused = qlora_tc2_kernel<ActT, false, true>;
+  auto kern_side = qlora_tc2_kernel<ActT, kBackward, true>;
   VFT_OPT_IN_SMEM_ONCE(kern_plain, VFT_MAX_DYN_SMEM);  // dyn_bytes depends on the plan: opt in to the limit
-  if (!kBackward) VFT_OPT_IN_SMEM_ONCE(kern_fused, VFT_MAX_DYN_SMEM);
-  auto kern = (!kBackward && rp > 0) ? kern_fused : kern_plain;
-  // the fewest pairs that still finish in the same number of waves (T = 4096, 3072 features: 144 tiles -> 72 pairs
-  // of 2 tiles instead of 74): identical run time, and the SMs left over stay free for a concurrent NCCL all-reduce
-  // of the LoRA gradients, which otherwise delays the launch of the last cluster until it has drained
-  const int n_items = p.n_tiles * p.n_split;
-  const int waves = (n_items + n_pairs - 1) / n_pairs;
-  const int pairs = (n_items + waves - 1) / waves;
+  VFT_OPT_IN_SMEM_ONCE(kern_side, VFT_MAX_DYN_SMEM);
+  auto kern = rp > 0 ? kern_side : kern_plain;
+  const int pairs = choice.pairs;
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)(2 * pairs));
   lc.blockDim = dim3(kThreads);
@@ -1059,7 +1144,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
   lc.numAttrs = pdl_enabled() ? 2 : 1;
-  VFT_CUDA_OK(cudaLaunchKernelEx(&lc, kern, map_act, map_lora, map_out, map_out16, p));
+  VFT_CUDA_OK(cudaLaunchKernelEx(&lc, kern, map_act, map_lora, map_out, map_out16, map_p0a, map_p0w, p));
   VFT_CUDA_OK(cudaGetLastError());
   if (p.n_split > 1) {
     const int64_t total8 = a.T * OUT / 8;
@@ -1097,10 +1182,10 @@ int64_t tc2_workspace_bytes(int64_t T, int64_t N, int64_t K, int r, bool backwar
   return plan_tc2(T, OUT, RED, r, !backward, device_pairs()).ws_bytes;  // (a fused plan never splits)
 }
 
-// True when tc2_fwd computes t_save = x . A^T itself (fused down-projection): the caller then skips the side kernel.
-bool tc2_fuses_down(const LayerArgs& a) {
-  if (a.T <= 0 || !tc2_preferred(a, false)) return false;
-  return choose_tc2(a, false, device_pairs()).rp > 0;
+// True when the launch computes its adapter side product (t_save / dt_save) itself: the caller then skips the side kernel.
+bool tc2_fuses_side(const LayerArgs& a, bool backward) {
+  if (a.T <= 0 || !tc2_preferred(a, backward)) return false;
+  return choose_tc2(a, backward, device_pairs()).rp > 0;
 }
 
 int tc2_fwd(const LayerArgs& a, const void* x, void* y, void* t_save, cudaStream_t st) {

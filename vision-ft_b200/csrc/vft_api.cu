@@ -220,7 +220,7 @@ int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* 
   }
   // t_save = x . A^T: inside the GEMM launch when the persistent tcgen05 kernel takes the call unsplit, else a kernel
   // of its own in front of it
-  if (r > 0 && !(tc && tc_fuses_down(a))) {
+  if (r > 0 && !(tc && tc_fuses_side(a, false))) {
     rc = (forced_path() == VFT_PATH_SIMT) ? simt_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st)
                                           : side_mma() ? mma_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st)
                                                        : tc_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st);

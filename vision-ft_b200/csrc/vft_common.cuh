@@ -157,6 +157,9 @@ struct LayerArgs {
   const float* absmax_t = nullptr;
   void* ws = nullptr;  // optional workspace (vft_workspace_bytes) for the split-K form of small problems
   int64_t ws_bytes = 0;
+  // s * lora_up.weight^T as a K-major [16 * ceil(r / 16), N] matrix: written by the forward call (when asked for), read
+  // by the backward call, which can then compute dt = s * dy . B inside its launch; nullptr = not available
+  void* bt_save = nullptr;
 };
 
 // generic CUDA-core family
@@ -192,13 +195,13 @@ int gemv_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cud
 // tcgen05 family
 bool tc_supported(const LayerArgs& a, bool backward);
 int tc_fwd(const LayerArgs& a, const void* x, void* y, void* t_save, cudaStream_t st);
-bool tc_fuses_down(const LayerArgs& a);  // tc_fwd will write t_save = x . A^T itself
+bool tc_fuses_side(const LayerArgs& a, bool backward);  // tc_fwd / tc_bwd_dx will write t_save / dt_save itself
 int tc_bwd_dx(const LayerArgs& a, const void* dy, void* dx, const void* dt_save, cudaStream_t st);
 // persistent CTA-pair form (qlora_tc2.cu); same contract, used by tc_fwd / tc_bwd_dx for large token counts
 bool tc2_preferred(const LayerArgs& a, bool backward);
 int64_t tc2_workspace_bytes(int64_t T, int64_t N, int64_t K, int r, bool backward);
 int tc2_fwd(const LayerArgs& a, const void* x, void* y, void* t_save, cudaStream_t st);
-bool tc2_fuses_down(const LayerArgs& a);  // tc2_fwd computes t_save itself (no side kernel needed)
+bool tc2_fuses_side(const LayerArgs& a, bool backward);  // the launch computes t_save / dt_save itself (no side kernel)
 int tc2_bwd_dx(const LayerArgs& a, const void* dy, void* dx, const void* dt_save, cudaStream_t st);
 
 }  // namespace vft
