@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VFT_ABI_VERSION 4
+#define VFT_ABI_VERSION 5
 #define VFT_LORA_LD 64 /* leading dimension (elements) of the saved LoRA activations t_save / dt_save */
 
 enum vft_dtype { VFT_F32 = 0, VFT_F16 = 1, VFT_BF16 = 2 };
@@ -137,23 +137,28 @@ int64_t vft_workspace_bytes(int op, int64_t T, int64_t N, int64_t K, int r);
  *   qdtype     quant_state.dtype: W~ is rounded to it first, then to act_dtype
  *   lora_a [r,K] (lora_down.weight), lora_b [N,r] (lora_up.weight); both NULL and
  *   r = 0 for an NF4-only layer.  scale = alpha / rank.
- *   t_save [T, VFT_LORA_LD] out: x . A^T rounded to act_dtype, zero padded; required
- *   when r > 0 (the backward reads it).
+ *   t_save [T, VFT_LORA_LD] out: x . A^T rounded to act_dtype in the first 16*ceil(r/16) columns (columns
+ *   [r, 16*ceil(r/16)) are zeros, the ones behind are not written and never read); required when r > 0 (the
+ *   backward reads it).
+ *   bt_save [16*ceil(r/16), N] out, optional (NULL: not wanted): scale * lora_b^T rounded to act_dtype, rows >= r
+ *   zero -- the K-major form of the adapter's up-projection that lets vft_qlora_bwd_dx compute dt inside its launch.
  *   codes_t / absmax_t: the micro-tiled copy of the same weight, or both NULL. */
 int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
                   int blocksize, int act_dtype, int qdtype, const void* bias, const void* lora_a, const void* lora_b,
-                  int r, float scale, void* y, void* t_save, void* ws, int64_t ws_bytes, const uint8_t* codes_t,
-                  const float* absmax_t, void* stream);
+                  int r, float scale, void* y, void* t_save, void* bt_save, void* ws, int64_t ws_bytes,
+                  const uint8_t* codes_t, const float* absmax_t, void* stream);
 
 /* Fused backward w.r.t. the input.  Replaces MatMul4Bit.backward (second dequant +
  * cuBLAS) and the dX half of the adapter's autograd:
  *     dt_save[T, VFT_LORA_LD] = scale * dy . B        (rounded to act_dtype)
  *     dx[T,K] = dy[T,N] . W~ + dt . A
- * dx may be NULL when only dt_save is wanted (input does not require grad). */
+ * dx may be NULL when only dt_save is wanted (input does not require grad).
+ * bt_save: what the forward call left (see there), or NULL; with it dt is computed inside the GEMM launch
+ * (as dy . bt^T: the scale is folded into the 16-bit rows of bt) instead of by a kernel in front of it. */
 int vft_qlora_bwd_dx(const void* dy, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
                      int blocksize, int act_dtype, int qdtype, const void* lora_a, const void* lora_b, int r,
-                     float scale, void* dx, void* dt_save, void* ws, int64_t ws_bytes, const uint8_t* codes_t,
-                     const float* absmax_t, void* stream);
+                     float scale, void* dx, void* dt_save, const void* bt_save, void* ws, int64_t ws_bytes,
+                     const uint8_t* codes_t, const float* absmax_t, void* stream);
 
 /* Adapter weight gradients (autograd of lora.py:100-104):
  *     dA[r,K] = dt^T . x        dB[N,r] = scale * dy^T . t

@@ -319,7 +319,7 @@ def test_pair_kernel_fused_down_projection(ops, vft_env, nacc, T, K, N, r, bias)
         from vft_b200 import _cabi
         _cabi.check(_cabi.lib.vft_qlora_fwd(xc.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, _cabi.BF16,
                                             _cabi.BF16, None, ac.data_ptr(), bc.data_ptr(), r, 1.0 / r, y.data_ptr(),
-                                            t_save.data_ptr(), None, 0, tiles[0].data_ptr(), tiles[1].data_ptr(),
+                                            t_save.data_ptr(), None, None, 0, tiles[0].data_ptr(), tiles[1].data_ptr(),
                                             torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
         ops.force_path(0)
@@ -429,18 +429,31 @@ def test_quantize_4bit_nested_seeded_hashes(golden_dir, dt_name, dt):
     ref = json.load(open(os.path.join(golden_dir, "nf4_hashes.json")))[dt_name]
     g = torch.Generator().manual_seed(ref["seed"])
     w = (torch.randn(*ref["shape"], generator=g) * ref["std"]).to(dt)
+    from vft_b200 import ops as vops
+    from vft_b200.nn import create_dynamic_map
+
+    # (1) the library's own offset (correctly rounded mean, fp64 accumulation): the committed hashes
+    packed0, absmax0 = vops.nf4_quantize(w.cuda())
+    q8, a2, off = vops.absmax_nest(absmax0, create_dynamic_map().cuda())
+    assert _sha(packed0.cpu().numpy()) == ref["packed_sha256"]
+    assert _sha(q8.cpu().numpy()) == ref["nested_absmax8_sha256"]
+    assert _sha(a2.cpu().numpy()) == ref["nested_absmax2_sha256"]
+    assert float(off) == ref["nested_offset"]
+    # (2) the module path encodes around torch's absmax.mean() on the device (what bitsandbytes does): within a few
+    # ulps of the committed value, and every piece bit-exact against the oracle run around the same offset
     packed, qs = quantize_4bit(w.cuda(), compress_statistics=True)
     assert qs.nested and qs.absmax.dtype == torch.uint8
-    assert _sha(packed.cpu().numpy()) == ref["packed_sha256"]
-    assert _sha(qs.absmax.cpu().numpy()) == ref["nested_absmax8_sha256"]
-    assert _sha(qs.state2.absmax.cpu().numpy()) == ref["nested_absmax2_sha256"]
-    assert float(qs.offset) == ref["nested_offset"]
-    assert _sha(qs.absmax_f32().cpu().numpy()) == ref["denested_absmax_sha256"]
+    assert torch.equal(packed, packed0)
+    assert abs(float(qs.offset) - ref["nested_offset"]) <= 4 * 2.0 ** -24 * ref["nested_offset"]
+    q8o, a2o, _, _ = nf4_oracle.absmax_nest(absmax0.cpu().numpy(), offset=float(qs.offset))
+    assert np.array_equal(qs.absmax.cpu().numpy(), q8o) and np.array_equal(qs.state2.absmax.cpu().numpy(), a2o)
+    if float(qs.offset) == ref["nested_offset"]:
+        assert _sha(qs.absmax_f32().cpu().numpy()) == ref["denested_absmax_sha256"]
     d = qs.as_dict(packed=True)
     assert set(d) == {"absmax", "quant_map", "nested_absmax", "nested_quant_map", "quant_state.bitsandbytes__nf4"}
     meta = nf4_oracle.unpack_quant_state_blob(d["quant_state.bitsandbytes__nf4"])
     assert meta == {"quant_type": "nf4", "blocksize": 64, "dtype": dt_name, "shape": ref["shape"],
-                    "nested_blocksize": 256, "nested_dtype": "float32", "nested_offset": ref["nested_offset"]}
+                    "nested_blocksize": 256, "nested_dtype": "float32", "nested_offset": float(qs.offset)}
     # dequantize with the de-nested statistics == oracle decode of the same pieces
     want = nf4_oracle.nf4_dequantize(packed.cpu().numpy(), nf4_oracle.quant_state_absmax_f32(qs), ref["shape"], dt_name)
     assert torch.equal(dequantize_4bit(packed, qs).cpu(), want)
@@ -581,10 +594,20 @@ def test_auraflow_weight_shapes_full_size_bit_exact(shape, dt_name, dt):
     packed, qs = quantize_4bit(w.cuda(), compress_statistics=True)
     p, a = c_oracle.quantize(w)
     assert np.array_equal(packed.cpu().numpy(), p)
-    q8, a2, off = c_oracle.absmax_nest(a, nf4_oracle.dynamic_map())
+    # the module encodes around torch's absmax.mean() on the device (as bitsandbytes does): a few ulps from the C
+    # oracle's correctly rounded mean at most; every piece bit-exact against the oracle run around the module's offset
+    _, _, off_c = c_oracle.absmax_nest(a, nf4_oracle.dynamic_map())
+    assert abs(float(qs.offset) - float(off_c)) <= 4 * 2.0 ** -24 * float(off_c)
+    q8, a2, off, _ = nf4_oracle.absmax_nest(a, offset=float(qs.offset))
     assert np.array_equal(qs.absmax.cpu().numpy(), q8) and np.array_equal(qs.state2.absmax.cpu().numpy(), a2)
     assert float(qs.offset) == float(off)
     assert np.array_equal(qs.absmax_f32().cpu().numpy(), c_oracle.absmax_denest(q8, a2, off, nf4_oracle.dynamic_map()))
+    # and the library's own mean (offset=None) is the C oracle's, bit for bit
+    from vft_b200 import ops as vops
+    from vft_b200.nn import create_dynamic_map
+    q8l, a2l, offl = vops.absmax_nest(torch.from_numpy(a).cuda(), create_dynamic_map().cuda())
+    q8c, a2c, _ = c_oracle.absmax_nest(a, nf4_oracle.dynamic_map())
+    assert float(offl) == float(off_c) and np.array_equal(q8l.cpu().numpy(), q8c) and np.array_equal(a2l.cpu().numpy(), a2c)
     # un-nested form (quantize_state_dict's path): the fp32 statistics themselves
     _, qs_plain = quantize_4bit(w.cuda(), compress_statistics=False)
     assert np.array_equal(qs_plain.absmax.cpu().numpy(), a)

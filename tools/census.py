@@ -58,6 +58,7 @@ def time_layer(N, K, T, lora, bias, dev):
     y = torch.empty(T, N, device=dev, dtype=bf); dx = torch.empty(T, K, device=dev, dtype=bf)
     ts = torch.empty(T, 64, device=dev, dtype=bf); dts = torch.empty(T, 64, device=dev, dtype=bf)
     dA = torch.empty(R, K, device=dev, dtype=bf); dB = torch.empty(N, R, device=dev, dtype=bf)
+    bt = torch.empty(16 * ((R + 15) // 16), N, device=dev, dtype=bf)
     wsb = _cabi.lib.vft_workspace_bytes(_cabi.OP_BWD_DAB, T, N, K, R)
     ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=dev)
     wf_b = _cabi.lib.vft_workspace_bytes(_cabi.OP_FWD, T, N, K, r_) if True else 0
@@ -68,9 +69,9 @@ def time_layer(N, K, T, lora, bias, dev):
     P = lambda t: None if t is None else t.data_ptr()
     side = torch.cuda.Stream()
     def fwd(i, st):
-        _cabi.check(L.vft_qlora_fwd(xs[i % nset].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, P(bv), P(A), P(B_), r, 1.0 / R, y.data_ptr(), P(ts) if lora else None, wf.data_ptr() if wf_b else None, wf_b, TC, TA, st))
+        _cabi.check(L.vft_qlora_fwd(xs[i % nset].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, P(bv), P(A), P(B_), r, 1.0 / R, y.data_ptr(), P(ts) if lora else None, P(bt) if lora else None, wf.data_ptr() if wf_b else None, wf_b, TC, TA, st))
     def bwd(i, st):
-        _cabi.check(L.vft_qlora_bwd_dx(gs[i % nset].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, P(A), P(B_), r, 1.0 / R, dx.data_ptr(), P(dts) if lora else None, wb.data_ptr() if wb_b else None, wb_b, TC, TA, st))
+        _cabi.check(L.vft_qlora_bwd_dx(gs[i % nset].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, P(A), P(B_), r, 1.0 / R, dx.data_ptr(), P(dts) if lora else None, P(bt) if lora else None, wb.data_ptr() if wb_b else None, wb_b, TC, TA, st))
         if lora:
             _cabi.check(L.vft_lora_bwd_dab(gs[i % nset].data_ptr(), xs[i % nset].data_ptr(), ts.data_ptr(), dts.data_ptr(), T, N, K, R, 2, 1.0 / R, dA.data_ptr(), dB.data_ptr(), ws.data_ptr(), wsb, st))
     out = {}

@@ -24,17 +24,19 @@ def main():
     B = (torch.randn(N, r, device=dev) * 0.02).to(bf)
     y = torch.empty(T, N, device=dev, dtype=bf); dx = torch.empty(T, K, device=dev, dtype=bf)
     ts = torch.empty(T, 64, device=dev, dtype=bf); dts = torch.empty(T, 64, device=dev, dtype=bf)
+    bt = torch.empty(16 * ((r + 15) // 16), N, device=dev, dtype=bf)
+    BT = None if os.environ.get("VFT_NO_BT") else bt.data_ptr()
     dA = torch.empty_like(A); dB = torch.empty_like(B)
     wsb = _cabi.lib.vft_workspace_bytes(_cabi.OP_BWD_DAB, T, N, K, r)
     ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     L = _cabi.lib
     calls = {
-        "fwd  (NF4 only)": lambda i: L.vft_qlora_fwd(xs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, None, 0, 0.0, y.data_ptr(), None, None, 0, TC, TA, st),
-        "fwd  (+LoRA)   ": lambda i: L.vft_qlora_fwd(xs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, A.data_ptr(), B.data_ptr(), r, 1.0 / r, y.data_ptr(), ts.data_ptr(), None, 0, TC, TA, st),
-        "bwd  (NF4 only)": lambda i: L.vft_qlora_bwd_dx(gs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, 0, 0.0, dx.data_ptr(), None, None, 0, TC, TA, st),
-        "bwd  (+LoRA)   ": lambda i: L.vft_qlora_bwd_dx(gs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, A.data_ptr(), B.data_ptr(), r, 1.0 / r, dx.data_ptr(), dts.data_ptr(), None, 0, TC, TA, st),
-        "dt only        ": lambda i: L.vft_qlora_bwd_dx(gs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, A.data_ptr(), B.data_ptr(), r, 1.0 / r, None, dts.data_ptr(), None, 0, TC, TA, st),
+        "fwd  (NF4 only)": lambda i: L.vft_qlora_fwd(xs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, None, 0, 0.0, y.data_ptr(), None, None, None, 0, TC, TA, st),
+        "fwd  (+LoRA)   ": lambda i: L.vft_qlora_fwd(xs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, A.data_ptr(), B.data_ptr(), r, 1.0 / r, y.data_ptr(), ts.data_ptr(), BT, None, 0, TC, TA, st),
+        "bwd  (NF4 only)": lambda i: L.vft_qlora_bwd_dx(gs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, 0, 0.0, dx.data_ptr(), None, None, None, 0, TC, TA, st),
+        "bwd  (+LoRA)   ": lambda i: L.vft_qlora_bwd_dx(gs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, A.data_ptr(), B.data_ptr(), r, 1.0 / r, dx.data_ptr(), dts.data_ptr(), BT, None, 0, TC, TA, st),
+        "dt only        ": lambda i: L.vft_qlora_bwd_dx(gs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, A.data_ptr(), B.data_ptr(), r, 1.0 / r, None, dts.data_ptr(), None, None, 0, TC, TA, st),
         "dA/dB          ": lambda i: L.vft_lora_bwd_dab(gs[i % NSET].data_ptr(), xs[i % NSET].data_ptr(), ts.data_ptr(), dts.data_ptr(), T, N, K, r, 2, 1.0 / r, dA.data_ptr(), dB.data_ptr(), ws.data_ptr(), wsb, st),
     }
     tot = {}

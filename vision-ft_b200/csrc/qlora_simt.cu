@@ -188,6 +188,29 @@ static int rowdot_typed(const void* m, const void* v, int64_t T, int64_t C, int 
   return VFT_OK;
 }
 
+// bt[j, n] = scale * B[n, j] for j < r, 0 for r <= j < 16 * ceil(r / 16): what the persistent tcgen05 forward writes on its
+// way (qlora_tc2.cu); the other forward paths launch this
+template <typename ActT>
+__global__ void lora_bt_kernel(const ActT* __restrict__ b, int64_t N, int r, int rows, float scale, ActT* __restrict__ bt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * rows) return;
+  const int64_t j = i / N, n = i % N;
+  bt[i] = from_f32<ActT>(j < r ? scale * to_f32<ActT>(b[n * r + j]) : 0.0f);
+}
+
+int simt_lora_bt(const void* b, int64_t N, int r, float scale, int act_dtype, void* bt, cudaStream_t st) {
+  const int rows = ((r + 15) / 16) * 16;
+  const unsigned grid = (unsigned)ceil_div64(N * rows, 256);
+  if (act_dtype == VFT_BF16)
+    lora_bt_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(b), N, r, rows, scale, static_cast<__nv_bfloat16*>(bt));
+  else if (act_dtype == VFT_F16)
+    lora_bt_kernel<<<grid, 256, 0, st>>>(static_cast<const __half*>(b), N, r, rows, scale, static_cast<__half*>(bt));
+  else
+    lora_bt_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(b), N, r, rows, scale, static_cast<float*>(bt));
+  VFT_CUDA_OK(cudaGetLastError());
+  return VFT_OK;
+}
+
 int simt_lora_down(const void* x, const void* a, int64_t T, int64_t K, int r, int act_dtype, void* t_save,
                    cudaStream_t st) {
   if (T == 0) return VFT_OK;

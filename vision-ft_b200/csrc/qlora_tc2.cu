@@ -123,6 +123,7 @@ struct Tc2Params {
   int p0_per_step;    // side-product steps issued per main ring step (2: done half-way through the first item)
   void* save;         // t_save / dt_save [T, VFT_LORA_LD] (written when side != 0; the adapter step reads it)
   unsigned* sync;     // {arrivals, generation} of the grid-wide counter (self-resetting; csrc pool, one pair per launch)
+  void* bt_out;       // forward, optional: s * lora_up.weight^T as [16 * ceil(r / 16), N] for the backward's side product
 };
 
 // Timeline of the leader CTA of pair 0 for performance triage (VFT_TC_DEBUG & 16): SM clock per event.
@@ -595,7 +596,10 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         // chunk and warp: a single warp issues it at a few cycles per instruction).  Measured alternatives, all slower:
         // loads issued one chunk ahead (convert first, then the next tcgen05.ld, then the chain: 6.7 k cycles per
         // 2 x 176-token tile against 5.7 k), a warp-private transpose patch + st.global.v4 (8.2 k), one st.global.b16
-        // per token from the 32x32b load shape (21 k).
+        // per token from the 32x32b load shape (21 k).  Letting the idle decode warps take four fifths of the LAST
+        // tile's chunks (staging tiles handed out through a counter instead of per-tile mbarriers) shortened that
+        // drain from 7.1 k to 3.4 k cycles on the epilogue warp's clock and left the launch where it was (58.0 us with,
+        // 58.2 us without): every CTA of the grid drains at the same moment, and 13 MB of output leave in one burst.
         for (int a = 0; a < na; ++a) {
           const int64_t ta = t0 + (int64_t)a * p.N_acc;
 #pragma unroll 1
@@ -773,6 +777,25 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
                 const float b0 = (j < p.r) ? p.scale * to_f32<ActT>(lw[n * p.r + j]) : 0.0f;
                 const float b1 = (j + 1 < p.r) ? p.scale * to_f32<ActT>(lw[n * p.r + j + 1]) : 0.0f;
                 v[c][e] = pack2<ActT>(b0, b1);
+              }
+            }
+          }
+        }
+        if (!kBackward && p.bt_out != nullptr && item_tile(cur.item) / p.n_fblk == 0 && cur.f0 + row < p.N) {
+          // The scaled rows this thread has just built, once more as columns of bt = s * B^T [16 * ceil(r / 16), N]
+          // (K-major for the backward launch, which computes dt = dy . bt^T itself): the tiles of token block 0 cover
+          // every out-feature exactly once; per j the warp writes 32 consecutive elements.
+          ActT* bt = static_cast<ActT*>(p.bt_out) + (cur.f0 + row);
+          const int bt_rows = ((p.r + 15) >> 4) << 4;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = c * 8 + 2 * e;
+              if (j < bt_rows) {
+                const uint32_t w2 = v[c][e];
+                reinterpret_cast<uint16_t*>(bt)[(int64_t)j * p.N] = (uint16_t)(w2 & 0xffffu);
+                reinterpret_cast<uint16_t*>(bt)[(int64_t)(j + 1) * p.N] = (uint16_t)(w2 >> 16);
               }
             }
           }
@@ -1065,6 +1088,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   if (p.p0_slots > kMaxP0) p.p0_slots = kMaxP0;
   p.p0_per_step = 2;
   p.save = lora_act;
+  p.bt_out = kBackward ? nullptr : a.bt_save;
   p.sync = nullptr;
   if (rp > 0) {
     p.sync = next_sync_pair();

@@ -198,11 +198,11 @@ int64_t vft_workspace_bytes(int op, int64_t T, int64_t N, int64_t K, int r) {
 
 int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
                   int blocksize, int act_dtype, int qdtype, const void* bias, const void* lora_a, const void* lora_b,
-                  int r, float scale, void* y, void* t_save, void* ws, int64_t ws_bytes, const uint8_t* codes_t,
-                  const float* absmax_t, void* stream) {
+                  int r, float scale, void* y, void* t_save, void* bt_save, void* ws, int64_t ws_bytes,
+                  const uint8_t* codes_t, const float* absmax_t, void* stream) {
   VFT_REQUIRE((codes_t == nullptr) == (absmax_t == nullptr), "codes_t / absmax_t must be given together");
   LayerArgs a{T, N, K, blocksize, act_dtype, qdtype, r, scale, packed, absmax, bias, lora_a, lora_b, codes_t, absmax_t,
-              ws, ws_bytes};
+              ws, ws_bytes, r > 0 ? bt_save : nullptr};
   int rc = check_layer(a, x, y);
   if (rc != VFT_OK) return rc;
   VFT_REQUIRE(r == 0 || t_save != nullptr, "t_save is required when r > 0");
@@ -226,6 +226,12 @@ int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* 
                                                        : tc_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st);
     if (rc != VFT_OK) return rc;
   }
+  // bt_save = s * B^T for the backward call: the persistent tcgen05 forward writes it on its way, every other path
+  // gets a small kernel
+  if (a.bt_save != nullptr && !(tc && tc2_preferred(a, false))) {
+    rc = simt_lora_bt(lora_b, N, r, scale, act_dtype, a.bt_save, st);
+    if (rc != VFT_OK) return rc;
+  }
   if (gemv) {
     set_path(VFT_PATH_GEMV);  // T <= 8: the launch is a weight stream, not a GEMM
     return gemv_fwd(a, x, y, t_save, st);
@@ -236,16 +242,23 @@ int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* 
 
 int vft_qlora_bwd_dx(const void* dy, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
                      int blocksize, int act_dtype, int qdtype, const void* lora_a, const void* lora_b, int r,
-                     float scale, void* dx, void* dt_save, void* ws, int64_t ws_bytes, const uint8_t* codes_t,
-                     const float* absmax_t, void* stream) {
+                     float scale, void* dx, void* dt_save, const void* bt_save, void* ws, int64_t ws_bytes,
+                     const uint8_t* codes_t, const float* absmax_t, void* stream) {
   VFT_REQUIRE((codes_t == nullptr) == (absmax_t == nullptr), "codes_t / absmax_t must be given together");
   LayerArgs a{T, N, K, blocksize, act_dtype, qdtype, r, scale, packed, absmax, nullptr, lora_a, lora_b, codes_t, absmax_t,
-              ws, ws_bytes};
+              ws, ws_bytes, r > 0 ? const_cast<void*>(bt_save) : nullptr};
   int rc = check_layer(a, dy, dx, /*out_optional=*/true);  // dx == NULL: only dt_save is wanted
   if (rc != VFT_OK) return rc;
   VFT_REQUIRE(r == 0 || dt_save != nullptr, "dt_save is required when r > 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (r > 0) {
+  bool tc = false;
+  if (dx != nullptr) {
+    tc = use_tc(a, true, &rc);
+    if (rc != VFT_OK) return rc;
+  }
+  // dt_save = s * dy . B: inside the GEMM launch when the persistent tcgen05 kernel takes the call unsplit and the
+  // forward left bt_save, else a kernel of its own in front of it
+  if (r > 0 && !(tc && tc_fuses_side(a, true))) {
     rc = (forced_path() == VFT_PATH_SIMT) ? simt_lora_dt(dy, lora_b, T, N, r, scale, act_dtype, dt_save, st)
                                           : side_mma() ? mma_lora_dt(dy, lora_b, T, N, r, scale, act_dtype, dt_save, st)
                                                        : tc_lora_dt(dy, lora_b, T, N, r, scale, act_dtype, dt_save, st);
@@ -255,8 +268,6 @@ int vft_qlora_bwd_dx(const void* dy, int64_t T, const uint8_t* packed, const flo
     set_path(VFT_PATH_SIMT);
     return VFT_OK;
   }
-  const bool tc = use_tc(a, true, &rc);
-  if (rc != VFT_OK) return rc;
   set_path(tc ? VFT_PATH_TCGEN05 : VFT_PATH_SIMT);
   return tc ? tc_bwd_dx(a, dy, dx, dt_save, st) : simt_bwd_dx(a, dy, dx, dt_save, st);
 }

@@ -167,6 +167,7 @@ int simt_lora_down(const void* x, const void* a, int64_t T, int64_t K, int r, in
                    cudaStream_t st);
 int simt_lora_dt(const void* dy, const void* b, int64_t T, int64_t N, int r, float scale, int act_dtype, void* dt_save,
                  cudaStream_t st);
+int simt_lora_bt(const void* b, int64_t N, int r, float scale, int act_dtype, void* bt, cudaStream_t st);
 int simt_fwd(const LayerArgs& a, const void* x, void* y, const void* t_save, cudaStream_t st);
 int simt_bwd_dx(const LayerArgs& a, const void* dy, void* dx, const void* dt_save, cudaStream_t st);
 int simt_dab(const void* dy, const void* x, const void* t_save, const void* dt_save, int64_t T, int64_t N, int64_t K,
