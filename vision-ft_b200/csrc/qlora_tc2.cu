@@ -129,6 +129,7 @@ struct Tc2Params {
 // Timeline of the leader CTA of pair 0 for performance triage (VFT_TC_DEBUG & 16): SM clock per event.
 constexpr int kTlRows = 7, kTlCols = 256;
 __device__ unsigned long long g_tc2_timeline[kTlRows * kTlCols];
+__device__ float g_tc2_p0dump[2 * 128 * 32];  // VFT_TC_DEBUG & 512: raw side-product accumulator lanes of pair 0
 __device__ __forceinline__ void tl_mark(const Tc2Params& p, int row, int col) {
   if ((p.debug & 16) && blockIdx.x == 0 && col < kTlCols) g_tc2_timeline[row * kTlCols + col] = (unsigned long long)clock64();
 }
@@ -203,6 +204,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   // or, with one accumulator, the tail of the second pitch
   const uint32_t p0_col = (uint32_t)((p.n_acc == 2 ? 1 : 2) * kAccCols - p.r_pad);
   const int n_p0 = kSide ? n_main : 0;  // side-product steps: one per 64 contraction elements
+  const bool p0_m128 = p.p0_rows <= 64;
   // grid-wide counter: generation before anybody of this launch can have arrived (read by the one thread that waits)
   const int n_ctas = (int)gridDim.x;
   // accumulators of a tile that hold at least one real token (all roles derive it the same way)
@@ -328,7 +330,10 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     // polls both of its duties so that neither can block the other.
     if (ptx::elect_one()) {
       ptx::griddep_wait();
-      const uint32_t idesc_p0 = ptx::make_idesc_f16(std::is_same<ActT, __nv_bfloat16>::value, false, false, 2 * kBM, p.r_pad);
+      // M = 128 over the pair (64 rows per CTA) whenever the CTA's token rows fit: the MMA reads M/2 rows of 32 bytes
+      // per CTA from shared memory whatever number of them is real, and that read is what the side product costs
+      const uint32_t idesc_p0 = ptx::make_idesc_f16(std::is_same<ActT, __nv_bfloat16>::value, false, false,
+                                                    p0_m128 ? kBM : 2 * kBM, p.r_pad);
       int ld = 0, ld_s = 0, mm = 0, mm_s = 0;
       uint32_t ld_par = 1, mm_par = 0;
       while (ld < n_p0 || (rank == 0 && mm < n_p0)) {
@@ -504,13 +509,27 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       ptx::mbar_wait(bar_p0_done, 0);
       ptx::tc_fence_after();
       if (et == 0) tl_mark(p, 6, 250);
-      if (quad * 32 < p.p0_rows) {
-        const int row = quad * 32 + lane;
+      // M = 256: lane = row, r_pad columns.  M = 128 (measured with tools/p0_layout_probe.py: tcgen05.mma
+      // cta_group::2 with M = 128 stores a CTA's 64 rows x N as 128 lanes x N/2 columns): lanes 0..63 hold columns
+      // [0, N/2) of rows 0..63, lanes 64..127 columns [N/2, N) of the same rows.
+      if ((p.debug & 512) && blockIdx.x < 2) {  // layout probe (tools/p0_layout_probe.py): every lane's 32 columns
+        uint32_t v[16];
+        for (int c16 = 0; c16 < 32; c16 += 16) {
+          ptx::tmem_ld_32x32b_x16(lane_base + p0_col + (uint32_t)c16, v);
+          ptx::tmem_ld_wait();
+          for (int e = 0; e < 16; ++e)
+            g_tc2_p0dump[(blockIdx.x * 128 + quad * 32 + lane) * 32 + c16 + e] = __uint_as_float(v[e]);
+        }
+      }
+      const int half = p0_m128 ? (quad >> 1) : 0;                     // which half of the r_pad columns this warp holds
+      const int row = (p0_m128 ? (quad & 1) : quad) * 32 + lane;      // token row of this CTA's slice
+      const int n_col = p0_m128 ? (p.r_pad >> 1) : p.r_pad;           // accumulator columns per lane: 8, 16 or 32
+      if (row - lane < p.p0_rows) {
         const int64_t tok = (int64_t)blockIdx.x * p.p0_rows + row;
         uint32_t pk[kMaxSideRP / 2];
 #pragma unroll
         for (int c16 = 0; c16 < kMaxSideRP; c16 += 16) {
-          if (c16 < p.r_pad) {
+          if (c16 < n_col) {  // (a 16-column load of an 8-column half reads 8 columns nobody wrote: unused)
             uint32_t v[16];
             ptx::tmem_ld_32x32b_x16(lane_base + p0_col + (uint32_t)c16, v);
             ptx::tmem_ld_wait();
@@ -520,10 +539,10 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
           }
         }
         if (row < p.p0_rows && tok < p.T) {
-          uint4* orow = reinterpret_cast<uint4*>(static_cast<ActT*>(p.save) + tok * VFT_LORA_LD);
+          uint4* orow = reinterpret_cast<uint4*>(static_cast<ActT*>(p.save) + tok * VFT_LORA_LD) + half * (n_col >> 3);
 #pragma unroll
           for (int c = 0; c < kMaxSideRP / 8; ++c)
-            if (c < (p.r_pad >> 3)) orow[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            if (c < (n_col >> 3)) orow[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         }
       }
       __threadfence();
@@ -1181,6 +1200,11 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
 
 }  // namespace
 }  // namespace vft
+
+extern "C" int vft_debug_tc2_p0dump(float* out, int n) {
+  if (n > 2 * 128 * 32) n = 2 * 128 * 32;
+  return cudaMemcpyFromSymbol(out, vft::g_tc2_p0dump, sizeof(float) * n) == cudaSuccess ? 0 : -3;
+}
 
 // Debug export (not part of the public ABI): timeline of the last VFT_TC_DEBUG&16 launch of the pair kernel.
 extern "C" int vft_debug_tc2_timeline(unsigned long long* out, int n) {
