@@ -25,11 +25,12 @@ def main():
     ts = torch.empty(T, 64, device=dev, dtype=torch.bfloat16)
     bt = torch.empty(16 * ((max(r, 1) + 15) // 16), N, device=dev, dtype=torch.bfloat16)
     AP, BP, TS, BT = (A.data_ptr(), B.data_ptr(), ts.data_ptr(), bt.data_ptr()) if r else (None, None, None, None)
+    BT_F = None if os.environ.get("VFT_NO_BT") else BT  # forward: do not ask for bt_save (the backward still reads the buffer)
     WFB = _cabi.lib.vft_workspace_bytes(0, T, N, K, 0); WBB = _cabi.lib.vft_workspace_bytes(1, T, N, K, 0)
     wf_t = torch.empty(max(WFB, 4), dtype=torch.uint8, device=dev); wb_t = torch.empty(max(WBB, 4), dtype=torch.uint8, device=dev)
     WF = wf_t.data_ptr() if WFB else None; WB = wb_t.data_ptr() if WBB else None
     def fwd(i):
-        _cabi.check(_cabi.lib.vft_qlora_fwd(xs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, AP, BP, r, 1.0 / max(r, 1), y.data_ptr(), TS, BT, WF, WFB, TC, TA, st))
+        _cabi.check(_cabi.lib.vft_qlora_fwd(xs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, AP, BP, r, 1.0 / max(r, 1), y.data_ptr(), TS, BT_F, WF, WFB, TC, TA, st))
     def bwd(i):
         _cabi.check(_cabi.lib.vft_qlora_bwd_dx(gs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, AP, BP, r, 1.0 / max(r, 1), dx.data_ptr(), TS, BT, WB, WBB, TC, TA, st))
     res = {}

@@ -322,49 +322,33 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       }
     }
   } else if (kSide && warp == kAllocWarp) {
-    // ------------------------------------------------------------- side product: its own producer + issuer
-    // A thread of its own (the TMEM-allocation warp has nothing else to do): with the side-product steps interleaved
-    // into the main producer and issuer loops, every main ring step of the first tile took 1500-2200 cycles instead
-    // of 712 -- an MMA costs the issuing thread ~40 cycles whatever its size, and barrier waits come on top.
-    // Loads of step i go to slot i % p0_slots once the MMAs of step i - p0_slots have read it; the leader's thread
-    // polls both of its duties so that neither can block the other.
-    if (ptx::elect_one()) {
-      ptx::griddep_wait();
+    // ------------------------------------------------------------- side product: its own issuer (leader CTA)
+    // Threads of their own -- this warp (the TMEM-allocation warp has nothing else to do) issues the MMAs, the store
+    // warp issues the loads before its first output tile exists.  With the side-product steps interleaved into the
+    // main producer and issuer loops every main ring step of the first tile took 1500-2200 cycles instead of 712
+    // (an MMA costs the issuing thread ~40 cycles whatever its size, barrier waits come on top); with ONE thread
+    // polling both duties a step took ~900 cycles and the slowest CTA of the grid published its rows 43 k cycles
+    // into the launch, after the first tile's contraction had ended everywhere.
+    if (rank == 0 && ptx::elect_one()) {
       // M = 128 over the pair (64 rows per CTA) whenever the CTA's token rows fit: the MMA reads M/2 rows of 32 bytes
-      // per CTA from shared memory whatever number of them is real, and that read is what the side product costs
+      // per CTA from shared memory whatever number of them is real
       const uint32_t idesc_p0 = ptx::make_idesc_f16(std::is_same<ActT, __nv_bfloat16>::value, false, false,
                                                     p0_m128 ? kBM : 2 * kBM, p.r_pad);
-      int ld = 0, ld_s = 0, mm = 0, mm_s = 0;
-      uint32_t ld_par = 1, mm_par = 0;
-      while (ld < n_p0 || (rank == 0 && mm < n_p0)) {
-        if (ld < n_p0 && ptx::mbar_try_wait(bar_p0_empty(ld_s), ld_par)) {
-          const uint32_t dst = p0_slot(ld_s);
-          if (rank == 0) ptx::mbar_arrive_expect_tx(bar_p0_full(ld_s), (uint32_t)(2 * p.p0_slot_bytes));
-          const uint32_t leader_bar = ptx::mapa(bar_p0_full(ld_s), 0);
-          ptx::tma_load_2d_pair(&map_p0a, dst, leader_bar, ld * kBK, (int)blockIdx.x * p.p0_rows);
-          ptx::tma_load_2d_pair(&map_p0w, dst + (uint32_t)(p.p0_rows * 128), leader_bar, ld * kBK,
-                                (int)rank * (p.r_pad >> 1));
-          ++ld;
-          if (++ld_s == p.p0_slots) {
-            ld_s = 0;
-            ld_par ^= 1u;
-          }
-        }
-        if (rank == 0 && mm < n_p0 && ptx::mbar_try_wait(bar_p0_full(mm_s), mm_par)) {
-          ptx::tc_fence_after();
-          // M = 256 (128 rows per CTA from the start of the slot, p0_rows of them real), N = r_pad, K-major operands
-          const uint64_t xa = ptx::make_smem_desc_sw128(p0_slot(mm_s), 16, 1024);
-          const uint64_t wa = ptx::make_smem_desc_sw128(p0_slot(mm_s) + (uint32_t)(p.p0_rows * 128), 16, 1024);
+      int mm_s = 0;
+      uint32_t mm_par = 0;
+      for (int mm = 0; mm < n_p0; ++mm) {
+        ptx::mbar_wait(bar_p0_full(mm_s), mm_par);
+        ptx::tc_fence_after();
+        const uint64_t xa = ptx::make_smem_desc_sw128(p0_slot(mm_s), 16, 1024);
+        const uint64_t wa = ptx::make_smem_desc_sw128(p0_slot(mm_s) + (uint32_t)(p.p0_rows * 128), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)
-            ptx::umma_ss_pair(tmem_d + p0_col, xa + k * (32u >> 4), wa + k * (32u >> 4), idesc_p0, (mm | k) != 0 ? 1u : 0u);
-          ptx::umma_commit_pair(bar_p0_empty(mm_s));
-          if (mm == n_p0 - 1) ptx::umma_commit_pair(bar_p0_done);  // -> epilogue warps, both CTAs
-          ++mm;
-          if (++mm_s == p.p0_slots) {
-            mm_s = 0;
-            mm_par ^= 1u;
-          }
+        for (int k = 0; k < kBK / 16; ++k)
+          ptx::umma_ss_pair(tmem_d + p0_col, xa + k * (32u >> 4), wa + k * (32u >> 4), idesc_p0, (mm | k) != 0 ? 1u : 0u);
+        ptx::umma_commit_pair(bar_p0_empty(mm_s));
+        if (mm == n_p0 - 1) ptx::umma_commit_pair(bar_p0_done);  // -> epilogue warps, both CTAs
+        if (++mm_s == p.p0_slots) {
+          mm_s = 0;
+          mm_par ^= 1u;
         }
       }
     }
@@ -446,6 +430,26 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     // tile, hand it to the TMA engine and release it once the engine has read it.
     if (p.n_split == 1 && ptx::elect_one()) {
       ptx::griddep_wait();  // the output buffer may still be read by the previous kernel
+      if (kSide) {
+        // side product: this thread is free until the first output tile is staged -- it issues all the loads (step i
+        // goes to slot i % p0_slots once the MMAs of step i - p0_slots have read it; bytes of both CTAs are counted
+        // on the leader's barrier, as in the main ring)
+        int ld_s = 0;
+        uint32_t ld_par = 1;
+        for (int ld = 0; ld < n_p0; ++ld) {
+          ptx::mbar_wait(bar_p0_empty(ld_s), ld_par);
+          const uint32_t dst = p0_slot(ld_s);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(bar_p0_full(ld_s), (uint32_t)(2 * p.p0_slot_bytes));
+          const uint32_t leader_bar = ptx::mapa(bar_p0_full(ld_s), 0);
+          ptx::tma_load_2d_pair(&map_p0a, dst, leader_bar, ld * kBK, (int)blockIdx.x * p.p0_rows);
+          ptx::tma_load_2d_pair(&map_p0w, dst + (uint32_t)(p.p0_rows * 128), leader_bar, ld * kBK,
+                                (int)rank * (p.r_pad >> 1));
+          if (++ld_s == p.p0_slots) {
+            ld_s = 0;
+            ld_par ^= 1u;
+          }
+        }
+      }
       const uint32_t stg = bar_base - (uint32_t)epi_bytes;
       uint32_t chunk = 0, sb = 0, sphase = 0;  // staging tile of this chunk and its use parity
       for (int item = pair; item < n_items; item += n_pairs) {
@@ -570,6 +574,20 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         for (int u = 0; u < 4; ++u) {
           const int64_t f = feat0 + quad * 32 + (lane >> 2) + 8 * u;
           if (f < OUT) bias_v[u] = to_f32<ActT>(static_cast<const ActT*>(p.bias)[f]);
+        }
+      }
+      if (!kBackward && p.bt_out != nullptr && tile / p.n_fblk == 0) {
+        // bt = s * B^T [16 * ceil(r / 16), N], the K-major form of the adapter's up-projection that the backward launch
+        // reads for its side product: the tiles of token block 0 cover every out-feature exactly once, and this warp
+        // has nothing to do until the tile's contraction ends.  (Written by the decode warps on their way through the
+        // adapter step, the 16 two-byte stores per thread cost the tiles of token block 0 ~6 k cycles.)
+        const int64_t n = feat0 + quad * 32 + lane;
+        if (n < p.N) {
+          const ActT* brow = static_cast<const ActT*>(p.lora_w) + n * p.r;
+          ActT* bt = static_cast<ActT*>(p.bt_out) + n;
+          const int bt_rows = ((p.r + 15) >> 4) << 4;
+          for (int j = 0; j < bt_rows; ++j)
+            bt[(int64_t)j * p.N] = from_f32<ActT>(j < p.r ? p.scale * to_f32<ActT>(brow[j]) : 0.0f);
         }
       }
       ptx::mbar_wait(bar_acc_full, it & 1u);
@@ -789,32 +807,23 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             }
           } else {
             const int64_t n = f0 + row;
-            if (n < p.N) {
+            if (n < p.N && (p.r & 7) == 0 && (reinterpret_cast<uintptr_t>(lw) & 15u) == 0) {
+              // ranks that are multiples of 8 (16 in every shipped config but one): one 16-byte load per 8 columns
+              // instead of eight 2-byte loads in the path of the tile's last ring step
+              if (c * 8 < p.r) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(lw + n * p.r + c * 8));
+                const ActT* e8 = reinterpret_cast<const ActT*>(&q);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  v[c][e] = pack2<ActT>(p.scale * to_f32<ActT>(e8[2 * e]), p.scale * to_f32<ActT>(e8[2 * e + 1]));
+              }
+            } else if (n < p.N) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int j = c * 8 + 2 * e;
                 const float b0 = (j < p.r) ? p.scale * to_f32<ActT>(lw[n * p.r + j]) : 0.0f;
                 const float b1 = (j + 1 < p.r) ? p.scale * to_f32<ActT>(lw[n * p.r + j + 1]) : 0.0f;
                 v[c][e] = pack2<ActT>(b0, b1);
-              }
-            }
-          }
-        }
-        if (!kBackward && p.bt_out != nullptr && item_tile(cur.item) / p.n_fblk == 0 && cur.f0 + row < p.N) {
-          // The scaled rows this thread has just built, once more as columns of bt = s * B^T [16 * ceil(r / 16), N]
-          // (K-major for the backward launch, which computes dt = dy . bt^T itself): the tiles of token block 0 cover
-          // every out-feature exactly once; per j the warp writes 32 consecutive elements.
-          ActT* bt = static_cast<ActT*>(p.bt_out) + (cur.f0 + row);
-          const int bt_rows = ((p.r + 15) >> 4) << 4;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = c * 8 + 2 * e;
-              if (j < bt_rows) {
-                const uint32_t w2 = v[c][e];
-                reinterpret_cast<uint16_t*>(bt)[(int64_t)j * p.N] = (uint16_t)(w2 & 0xffffu);
-                reinterpret_cast<uint16_t*>(bt)[(int64_t)(j + 1) * p.N] = (uint16_t)(w2 >> 16);
               }
             }
           }
