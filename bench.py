@@ -466,7 +466,7 @@ def run_gpu_arm(args):
 
         def k_fwd(i):
             _cabi.check(_cabi.lib.vft_qlora_fwd(xk[i % n_sets].data_ptr(), T, w.data_ptr(), absmax.data_ptr(), N_FEAT, K_FEAT, 64,
-                                                _cabi.BF16, _cabi.BF16, None, None, None, 0, 0.0, yk.data_ptr(), None, None, None, 0, tc_ptr, ta_ptr, st))
+                                                _cabi.BF16, _cabi.BF16, None, None, None, 0, 0.0, yk.data_ptr(), None, None, None, None, 0, tc_ptr, ta_ptr, st))
 
         def k_bwd(i):
             _cabi.check(_cabi.lib.vft_qlora_bwd_dx(gk[i % n_sets].data_ptr(), T, w.data_ptr(), absmax.data_ptr(), N_FEAT, K_FEAT, 64,

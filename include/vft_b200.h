@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VFT_ABI_VERSION 5
+#define VFT_ABI_VERSION 6
 #define VFT_LORA_LD 64 /* leading dimension (elements) of the saved LoRA activations t_save / dt_save */
 
 enum vft_dtype { VFT_F32 = 0, VFT_F16 = 1, VFT_BF16 = 2 };
@@ -58,7 +58,7 @@ enum vft_path {
   VFT_PATH_GEMV = 3     /* few-token forward (T <= 8): packed-weight streaming kernel, HBM/decode bound */
 };
 
-enum vft_op { VFT_OP_FWD = 0, VFT_OP_BWD_DX = 1, VFT_OP_BWD_DAB = 2, VFT_OP_ABSMAX_NEST = 3 };
+enum vft_op { VFT_OP_FWD = 0, VFT_OP_BWD_DX = 1, VFT_OP_BWD_DAB = 2, VFT_OP_ABSMAX_NEST = 3, VFT_OP_BWD = 4 };
 
 int vft_abi_version(void);
 const char* vft_last_error(void);
@@ -142,10 +142,12 @@ int64_t vft_workspace_bytes(int op, int64_t T, int64_t N, int64_t K, int r);
  *   backward reads it).
  *   bt_save [16*ceil(r/16), N] out, optional (NULL: not wanted): scale * lora_b^T rounded to act_dtype, rows >= r
  *   zero -- the K-major form of the adapter's up-projection that lets vft_qlora_bwd_dx compute dt inside its launch.
+ *   tt_save [16*ceil(r/16), T] out, optional: t_save transposed (rows >= r zero) -- with it vft_qlora_bwd computes
+ *   the adapter's weight gradients inside its launch; 16-byte aligned, T % 8 == 0 for that to apply.
  *   codes_t / absmax_t: the micro-tiled copy of the same weight, or both NULL. */
 int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
                   int blocksize, int act_dtype, int qdtype, const void* bias, const void* lora_a, const void* lora_b,
-                  int r, float scale, void* y, void* t_save, void* bt_save, void* ws, int64_t ws_bytes,
+                  int r, float scale, void* y, void* t_save, void* bt_save, void* tt_save, void* ws, int64_t ws_bytes,
                   const uint8_t* codes_t, const float* absmax_t, void* stream);
 
 /* Fused backward w.r.t. the input.  Replaces MatMul4Bit.backward (second dequant +
@@ -159,6 +161,16 @@ int vft_qlora_bwd_dx(const void* dy, int64_t T, const uint8_t* packed, const flo
                      int blocksize, int act_dtype, int qdtype, const void* lora_a, const void* lora_b, int r,
                      float scale, void* dx, void* dt_save, const void* bt_save, void* ws, int64_t ws_bytes,
                      const uint8_t* codes_t, const float* absmax_t, void* stream);
+
+/* The whole backward of the layer in one call -- MatMul4Bit.backward plus the autograd of lora.py:100-104:
+ *     dt_save = scale * dy . B;  dx = dy . W~ + dt . A;  dA = dt^T . x;  dB = scale * dy^T . t
+ * With bt_save and tt_save from the forward call (and a shape the persistent tcgen05 kernel takes unsplit) this is ONE
+ * launch: the side product and the two token contractions ride the GEMM (csrc/qlora_tc2.cu).  Otherwise it is the two
+ * calls below, in order.  ws: vft_workspace_bytes(VFT_OP_BWD, T, N, K, r) bytes, 256-byte aligned.  dx may be NULL. */
+int vft_qlora_bwd(const void* dy, const void* x, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
+                  int blocksize, int act_dtype, int qdtype, const void* lora_a, const void* lora_b, int r, float scale,
+                  const void* t_save, const void* tt_save, const void* bt_save, void* dx, void* dA, void* dB,
+                  void* dt_save, void* ws, int64_t ws_bytes, const uint8_t* codes_t, const float* absmax_t, void* stream);
 
 /* Adapter weight gradients (autograd of lora.py:100-104):
  *     dA[r,K] = dt^T . x        dB[N,r] = scale * dy^T . t

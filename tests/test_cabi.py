@@ -35,7 +35,7 @@ def test_header_symbols_are_exported(cabi):
 
 
 def test_abi_version(cabi):
-    assert cabi.lib.vft_abi_version() == cabi.ABI_VERSION == 5
+    assert cabi.lib.vft_abi_version() == cabi.ABI_VERSION == 6
 
 
 def test_argument_validation_needs_no_gpu(cabi):
@@ -47,12 +47,12 @@ def test_argument_validation_needs_no_gpu(cabi):
     # n == 0 is a no-op
     assert lib.vft_nf4_quantize(None, cabi.BF16, 0, 64, None, None, None) == 0
     # LoRA rank out of range / missing adapter pointers
-    rc = lib.vft_qlora_fwd(1, 4, 1, 1, 64, 64, 64, cabi.BF16, cabi.BF16, None, None, None, 65, 1.0, 1, 1, None, None, 0, None, None, None)
+    rc = lib.vft_qlora_fwd(1, 4, 1, 1, 64, 64, 64, cabi.BF16, cabi.BF16, None, None, None, 65, 1.0, 1, 1, None, None, None, 0, None, None, None)
     assert rc == -1 and b"rank" in lib.vft_last_error()
-    rc = lib.vft_qlora_fwd(1, 4, 1, 1, 64, 64, 64, cabi.BF16, cabi.BF16, None, None, None, 16, 1.0, 1, 1, None, None, 0, None, None, None)
+    rc = lib.vft_qlora_fwd(1, 4, 1, 1, 64, 64, 64, cabi.BF16, cabi.BF16, None, None, None, 16, 1.0, 1, 1, None, None, None, 0, None, None, None)
     assert rc == -1
     # the micro-tiled copy comes as a pair
-    rc = lib.vft_qlora_fwd(1, 4, 1, 1, 64, 64, 64, cabi.BF16, cabi.BF16, None, None, None, 0, 1.0, 1, None, None, None, 0, 1, None, None)
+    rc = lib.vft_qlora_fwd(1, 4, 1, 1, 64, 64, 64, cabi.BF16, cabi.BF16, None, None, None, 0, 1.0, 1, None, None, None, None, 0, 1, None, None)
     assert rc == -1 and b"together" in lib.vft_last_error()
     assert lib.vft_nf4_tiled_bytes(100, 128, 0) == 128 * 128 // 2 and lib.vft_nf4_tiled_bytes(100, 128, 1) == 128 * 2 * 4
     assert lib.vft_nf4_tiled_bytes(100, 100, 0) == 0

@@ -319,7 +319,7 @@ def test_pair_kernel_fused_down_projection(ops, vft_env, nacc, T, K, N, r, bias)
         from vft_b200 import _cabi
         _cabi.check(_cabi.lib.vft_qlora_fwd(xc.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, _cabi.BF16,
                                             _cabi.BF16, None, ac.data_ptr(), bc.data_ptr(), r, 1.0 / r, y.data_ptr(),
-                                            t_save.data_ptr(), None, None, 0, tiles[0].data_ptr(), tiles[1].data_ptr(),
+                                            t_save.data_ptr(), None, None, None, 0, tiles[0].data_ptr(), tiles[1].data_ptr(),
                                             torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
         ops.force_path(0)

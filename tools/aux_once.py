@@ -19,7 +19,7 @@ ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 L = _cabi.lib
 for _ in range(3):
-    _cabi.check(L.vft_qlora_fwd(x.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, A.data_ptr(), B.data_ptr(), r, 1.0 / r, y.data_ptr(), ts.data_ptr(), None, None, 0, None, None, st))
+    _cabi.check(L.vft_qlora_fwd(x.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, A.data_ptr(), B.data_ptr(), r, 1.0 / r, y.data_ptr(), ts.data_ptr(), None, None, None, 0, None, None, st))
     _cabi.check(L.vft_qlora_bwd_dx(g.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, A.data_ptr(), B.data_ptr(), r, 1.0 / r, None, dts.data_ptr(), None, None, 0, None, None, st))
     _cabi.check(L.vft_lora_bwd_dab(g.data_ptr(), x.data_ptr(), ts.data_ptr(), dts.data_ptr(), T, N, K, r, 2, 1.0 / r, dA.data_ptr(), dB.data_ptr(), ws.data_ptr(), wsb, st))
 torch.cuda.synchronize()

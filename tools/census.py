@@ -69,7 +69,7 @@ def time_layer(N, K, T, lora, bias, dev):
     P = lambda t: None if t is None else t.data_ptr()
     side = torch.cuda.Stream()
     def fwd(i, st):
-        _cabi.check(L.vft_qlora_fwd(xs[i % nset].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, P(bv), P(A), P(B_), r, 1.0 / R, y.data_ptr(), P(ts) if lora else None, P(bt) if lora else None, wf.data_ptr() if wf_b else None, wf_b, TC, TA, st))
+        _cabi.check(L.vft_qlora_fwd(xs[i % nset].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, P(bv), P(A), P(B_), r, 1.0 / R, y.data_ptr(), P(ts) if lora else None, P(bt) if lora else None, None, wf.data_ptr() if wf_b else None, wf_b, TC, TA, st))
     def bwd(i, st):
         _cabi.check(L.vft_qlora_bwd_dx(gs[i % nset].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, P(A), P(B_), r, 1.0 / R, dx.data_ptr(), P(dts) if lora else None, P(bt) if lora else None, wb.data_ptr() if wb_b else None, wb_b, TC, TA, st))
         if lora:

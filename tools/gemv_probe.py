@@ -30,7 +30,7 @@ def probe(N, K, T, path, bias=False, dev="cuda"):
     def call(i, st):
         tl = tiles[i % copies]
         _cabi.check(_cabi.lib.vft_qlora_fwd(x.data_ptr(), T, packs[i % copies].data_ptr(), ams[i % copies].data_ptr(), N, K, 64, 2, 2,
-                                            None if bv is None else bv.data_ptr(), None, None, 0, 0.0, y.data_ptr(), None, None,
+                                            None if bv is None else bv.data_ptr(), None, None, 0, 0.0, y.data_ptr(), None, None, None,
                                             ws.data_ptr() if wsb else None, wsb, tl[0].data_ptr() if tl else None,
                                             tl[1].data_ptr() if tl else None, st))
     g = torch.cuda.CUDAGraph()

@@ -21,7 +21,7 @@ y = torch.empty(T, N, device=dev, dtype=torch.bfloat16)
 ts = torch.zeros(T, 64, device=dev, dtype=torch.bfloat16)
 st = torch.cuda.current_stream().cuda_stream
 _cabi.check(_cabi.lib.vft_qlora_fwd(x.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, A.data_ptr(), B.data_ptr(),
-                                    r, 1.0 / r, y.data_ptr(), ts.data_ptr(), None, None, 0, tiles[0].data_ptr(), tiles[1].data_ptr(), st))
+                                    r, 1.0 / r, y.data_ptr(), ts.data_ptr(), None, None, None, 0, tiles[0].data_ptr(), tiles[1].data_ptr(), st))
 torch.cuda.synchronize()
 buf = (ctypes.c_float * (2 * 128 * 32))()
 fn = _cabi.lib.vft_debug_tc2_p0dump

@@ -26,17 +26,22 @@ def main():
     ts = torch.empty(T, 64, device=dev, dtype=bf); dts = torch.empty(T, 64, device=dev, dtype=bf)
     bt = torch.empty(16 * ((r + 15) // 16), N, device=dev, dtype=bf)
     BT = None if os.environ.get("VFT_NO_BT") else bt.data_ptr()
+    tt = torch.empty(16 * ((r + 15) // 16), T, device=dev, dtype=bf)
+    TT = None if os.environ.get("VFT_NO_BT") else tt.data_ptr()
+    wsb2 = _cabi.lib.vft_workspace_bytes(_cabi.OP_BWD, T, N, K, r)
+    ws2 = torch.empty(max(wsb2, 4), dtype=torch.uint8, device=dev)
     dA = torch.empty_like(A); dB = torch.empty_like(B)
     wsb = _cabi.lib.vft_workspace_bytes(_cabi.OP_BWD_DAB, T, N, K, r)
     ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     L = _cabi.lib
     calls = {
-        "fwd  (NF4 only)": lambda i: L.vft_qlora_fwd(xs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, None, 0, 0.0, y.data_ptr(), None, None, None, 0, TC, TA, st),
-        "fwd  (+LoRA)   ": lambda i: L.vft_qlora_fwd(xs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, A.data_ptr(), B.data_ptr(), r, 1.0 / r, y.data_ptr(), ts.data_ptr(), BT, None, 0, TC, TA, st),
+        "fwd  (NF4 only)": lambda i: L.vft_qlora_fwd(xs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, None, 0, 0.0, y.data_ptr(), None, None, None, None, 0, TC, TA, st),
+        "fwd  (+LoRA)   ": lambda i: L.vft_qlora_fwd(xs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, A.data_ptr(), B.data_ptr(), r, 1.0 / r, y.data_ptr(), ts.data_ptr(), BT, TT, None, 0, TC, TA, st),
         "bwd  (NF4 only)": lambda i: L.vft_qlora_bwd_dx(gs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, 0, 0.0, dx.data_ptr(), None, None, None, 0, TC, TA, st),
         "bwd  (+LoRA)   ": lambda i: L.vft_qlora_bwd_dx(gs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, A.data_ptr(), B.data_ptr(), r, 1.0 / r, dx.data_ptr(), dts.data_ptr(), BT, None, 0, TC, TA, st),
         "dt only        ": lambda i: L.vft_qlora_bwd_dx(gs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, A.data_ptr(), B.data_ptr(), r, 1.0 / r, None, dts.data_ptr(), None, None, 0, TC, TA, st),
+        "bwd  (one call)": lambda i: L.vft_qlora_bwd(gs[i % NSET].data_ptr(), xs[i % NSET].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, A.data_ptr(), B.data_ptr(), r, 1.0 / r, ts.data_ptr(), TT, BT, dx.data_ptr(), dA.data_ptr(), dB.data_ptr(), dts.data_ptr(), ws2.data_ptr(), wsb2, TC, TA, st),
         "dA/dB          ": lambda i: L.vft_lora_bwd_dab(gs[i % NSET].data_ptr(), xs[i % NSET].data_ptr(), ts.data_ptr(), dts.data_ptr(), T, N, K, r, 2, 1.0 / r, dA.data_ptr(), dB.data_ptr(), ws.data_ptr(), wsb, st),
     }
     tot = {}
@@ -69,6 +74,7 @@ def main():
             buf = (ctypes.c_ulonglong * 16)()
             L.vft_debug_side_timeline(buf, 16)
             print(f"  side-kernel timeline [{nm.strip()}] (ns since entry): " + ", ".join(f"{n} {buf[i]-buf[0]}" for i, n in enumerate(names)))
+    print(f"  step with the one-call backward: {tot['fwd  (+LoRA)   '] + tot['bwd  (one call)']:.1f} us")
     step = tot["fwd  (+LoRA)   "] + tot["bwd  (+LoRA)   "] + tot["dA/dB          "]
     fl = 4 * T * N * K + 6 * T * r * (N + K)
     print(f"T={T} N={N} K={K} r={r}: step (3 calls, CUDA-graph replay) {step:.1f} us -> {fl / step / 1e6:.0f} TF/s; "

@@ -19,7 +19,7 @@ y = torch.empty(T, N, device=dev, dtype=torch.bfloat16)
 dx = torch.empty(T, K, device=dev, dtype=torch.bfloat16)
 st = torch.cuda.current_stream().cuda_stream
 for _ in range(reps):
-    _cabi.check(_cabi.lib.vft_qlora_fwd(x.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, None, 0, 0.0, y.data_ptr(), None, None, None, 0, TC, TA, st))
+    _cabi.check(_cabi.lib.vft_qlora_fwd(x.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, None, 0, 0.0, y.data_ptr(), None, None, None, None, 0, TC, TA, st))
     _cabi.check(_cabi.lib.vft_qlora_bwd_dx(g.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, 0, 0.0, dx.data_ptr(), None, None, None, 0, TC, TA, st))
 torch.cuda.synchronize()
 print("ok")

@@ -30,7 +30,7 @@ def main():
     wf_t = torch.empty(max(WFB, 4), dtype=torch.uint8, device=dev); wb_t = torch.empty(max(WBB, 4), dtype=torch.uint8, device=dev)
     WF = wf_t.data_ptr() if WFB else None; WB = wb_t.data_ptr() if WBB else None
     def fwd(i):
-        _cabi.check(_cabi.lib.vft_qlora_fwd(xs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, AP, BP, r, 1.0 / max(r, 1), y.data_ptr(), TS, BT_F, WF, WFB, TC, TA, st))
+        _cabi.check(_cabi.lib.vft_qlora_fwd(xs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, AP, BP, r, 1.0 / max(r, 1), y.data_ptr(), TS, BT_F, None, WF, WFB, TC, TA, st))
     def bwd(i):
         _cabi.check(_cabi.lib.vft_qlora_bwd_dx(gs[i % 4].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, AP, BP, r, 1.0 / max(r, 1), dx.data_ptr(), TS, BT, WB, WBB, TC, TA, st))
     res = {}

@@ -211,6 +211,28 @@ int simt_lora_bt(const void* b, int64_t N, int r, float scale, int act_dtype, vo
   return VFT_OK;
 }
 
+// tt[j, t] = t_save[t, j] for j < 16 * ceil(r / 16): the transposed copy the backward's dA/dB job reads; written by the
+// persistent tcgen05 forward on its way when it computes t itself, by this kernel otherwise
+template <typename ActT>
+__global__ void lora_tt_kernel(const ActT* __restrict__ t_save, int64_t T, int rows, ActT* __restrict__ tt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * rows) return;
+  const int64_t j = i / T, t = i % T;
+  tt[i] = t_save[t * VFT_LORA_LD + j];
+}
+
+int simt_lora_tt(const void* t_save, int64_t T, int r, int act_dtype, void* tt, cudaStream_t st) {
+  const int rows = ((r + 15) / 16) * 16;
+  if (T == 0) return VFT_OK;
+  const unsigned grid = (unsigned)ceil_div64(T * rows, 256);
+  if (act_dtype == VFT_F32)
+    lora_tt_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(t_save), T, rows, static_cast<float*>(tt));
+  else  // 16-bit types: a plain copy of two-byte elements
+    lora_tt_kernel<<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(t_save), T, rows, static_cast<uint16_t*>(tt));
+  VFT_CUDA_OK(cudaGetLastError());
+  return VFT_OK;
+}
+
 int simt_lora_down(const void* x, const void* a, int64_t T, int64_t K, int r, int act_dtype, void* t_save,
                    cudaStream_t st) {
   if (T == 0) return VFT_OK;

@@ -75,7 +75,8 @@ struct AccLayout {
 constexpr int kTmemCols = 512;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kMaxStg = 16;  // output staging tiles
-constexpr int kBarBytes = (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg + 2 * kMaxP0 + 1) * 8 + 16;
+constexpr int kBarBytes = (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg + 2 * kMaxP0 + 2) * 8 + 16;
+constexpr int kJobBox = 64 * 128;  // dA/dB job: one [64 tokens x 64 columns] box of x / dy per CTA and ring step
 constexpr int kStgBytes = 32 * kBM * 2;  // one staging tile [32 tokens][128 features] of 16-bit outputs (8 KB)
 constexpr int kEpiBytes = 2 * kStgBytes;  // the minimum: two tiles
 
@@ -124,6 +125,18 @@ struct Tc2Params {
   void* save;         // t_save / dt_save [T, VFT_LORA_LD] (written when side != 0; the adapter step reads it)
   unsigned* sync;     // {arrivals, generation} of the grid-wide counter (self-resetting; csrc pool, one pair per launch)
   void* bt_out;       // forward, optional: s * lora_up.weight^T as [16 * ceil(r / 16), N] for the backward's side product
+  void* save_t;       // optional: the side product once more, transposed [r_pad, T] (K-major operand of the dA/dB job)
+  // dA/dB job (backward launch with its side product inside): the adapter's weight gradients dA = dt^T . x [r, K] and
+  // dB = s * dy^T . t [N, r] are contractions over the TOKENS -- one pass over x and one over dy, a kernel of its own
+  // until now (12.9 us + a launch gap at config #1).  Here pair u < job_units takes 128 columns of x (dA) or dy (dB):
+  // after the side product, the same two threads stream [64 tokens x 64 columns] boxes (MN-major A operand) and
+  // [r_pad/2 x 64 tokens] boxes of dt^T / t^T (K-major B operand) through the side product's ring and accumulate
+  // M = 128, N = r_pad MMAs in spare TMEM columns; the epilogue warps write the result before the last tile's drain.
+  int job;            // 0: adapter gradients by vft_lora_bwd_dab after this launch
+  int job_units_a;    // units [0, job_units_a): dA column tiles; [job_units_a, job_units): dB column tiles
+  int job_units;
+  void* job_da;       // dA [r, K]
+  void* job_db;       // dB [N, r]
 };
 
 // Timeline of the leader CTA of pair 0 for performance triage (VFT_TC_DEBUG & 16): SM clock per event.
@@ -150,12 +163,17 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
   return v;
 }
 
-template <typename ActT, bool kBackward, bool kSide>
+struct JobMaps {  // dA/dB job: x / dy in [64 columns x 64 tokens] boxes, dt^T / t^T in [64 tokens x r_pad/2 rows] boxes
+  CUtensorMap m_a, m_b, v_a, v_b;
+};
+
+template <typename ActT, bool kBackward, bool kSide, bool kJob = false>
 __global__ void __launch_bounds__(kThreads, 1)
 qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_lora,
                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out16,
                  const __grid_constant__ CUtensorMap map_p0a, const __grid_constant__ CUtensorMap map_p0w,
-                 const Tc2Params p) {
+                 const __grid_constant__ JobMaps jm, const Tc2Params p) {
+  static_assert(!kJob || (kBackward && kSide), "the dA/dB job rides the backward launch's side-product machinery");
   constexpr bool kTmemA = !kBackward;  // forward: decoded weights go to tensor memory, backward: shared memory
   constexpr int kAccCols = AccLayout<kTmemA>::pitch;
   constexpr int kAOff = kTmemA ? 0 : kATileBytes;  // offset of the activation boxes inside a stage
@@ -195,7 +213,8 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   auto bar_p0_full = [&](int i) { return bar_base + 8u * (kBarP0 + i); };
   auto bar_p0_empty = [&](int i) { return bar_base + 8u * (kBarP0 + kMaxP0 + i); };
   const uint32_t bar_p0_done = bar_base + 8u * (kBarP0 + 2 * kMaxP0);
-  const uint32_t tmem_slot = bar_base + 8u * (kBarP0 + 2 * kMaxP0 + 1);
+  const uint32_t bar_job_done = bar_base + 8u * (kBarP0 + 2 * kMaxP0 + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (kBarP0 + 2 * kMaxP0 + 2);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
   auto stage_a = [&](int s) { return smem_base + (uint32_t)(s * p.stage_bytes); };
   auto stage_b = [&](int s, int a) { return smem_base + (uint32_t)(s * p.stage_bytes + kAOff + a * p.b_bytes); };
@@ -205,6 +224,12 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   const uint32_t p0_col = (uint32_t)((p.n_acc == 2 ? 1 : 2) * kAccCols - p.r_pad);
   const int n_p0 = kSide ? n_main : 0;  // side-product steps: one per 64 contraction elements
   const bool p0_m128 = p.p0_rows <= 64;
+  // dA/dB job of this pair (kJob): unit, whether it is a dA unit, first column of this CTA's 64, contraction steps
+  const bool job_on = kJob && pair < p.job_units;
+  const bool job_is_a = pair < p.job_units_a;
+  const int job_col0 = (job_is_a ? pair : pair - p.job_units_a) * kBM + (int)rank * 64;
+  const int job_steps = (int)((p.T + 63) / 64);
+  const uint32_t job_col = p0_col - (uint32_t)p.r_pad;  // TMEM columns [job_col, job_col + r_pad / 2)
   // grid-wide counter: generation before anybody of this launch can have arrived (read by the one thread that waits)
   const int n_ctas = (int)gridDim.x;
   // accumulators of a tile that hold at least one real token (all roles derive it the same way)
@@ -228,6 +253,10 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       ptx::tma_prefetch_desc(&map_p0a);
       ptx::tma_prefetch_desc(&map_p0w);
     }
+    if (kJob) {
+      ptx::tma_prefetch_desc(job_is_a ? &jm.m_a : &jm.m_b);
+      ptx::tma_prefetch_desc(job_is_a ? &jm.v_a : &jm.v_b);
+    }
     ptx::tma_prefetch_desc(&map_act);
     if (p.r > 0) ptx::tma_prefetch_desc(&map_lora);
     ptx::tma_prefetch_desc(&map_out);
@@ -245,6 +274,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         ptx::mbar_init(bar_p0_empty(i), 1);  // multicast tcgen05.commit
       }
       ptx::mbar_init(bar_p0_done, 1);
+      ptx::mbar_init(bar_job_done, 1);
     }
     for (int a = 0; a < kMaxAcc; ++a) ptx::mbar_init(bar_acc_empty(a), 2 * 4);  // epilogue warps of both CTAs
     for (int b = 0; b < p.n_stg; ++b) {
@@ -329,26 +359,85 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     // (an MMA costs the issuing thread ~40 cycles whatever its size, barrier waits come on top); with ONE thread
     // polling both duties a step took ~900 cycles and the slowest CTA of the grid published its rows 43 k cycles
     // into the launch, after the first tile's contraction had ended everywhere.
-    if (rank == 0 && ptx::elect_one()) {
-      // M = 128 over the pair (64 rows per CTA) whenever the CTA's token rows fit: the MMA reads M/2 rows of 32 bytes
-      // per CTA from shared memory whatever number of them is real
-      const uint32_t idesc_p0 = ptx::make_idesc_f16(std::is_same<ActT, __nv_bfloat16>::value, false, false,
-                                                    p0_m128 ? kBM : 2 * kBM, p.r_pad);
+    if ((rank == 0 || job_on) && ptx::elect_one()) {
+      unsigned gen0 = 0;  // generation of the grid-wide counter before anybody of this launch can have arrived
+      if (kJob) gen0 = *reinterpret_cast<volatile unsigned*>(p.sync + 1);
       int mm_s = 0;
       uint32_t mm_par = 0;
-      for (int mm = 0; mm < n_p0; ++mm) {
-        ptx::mbar_wait(bar_p0_full(mm_s), mm_par);
-        ptx::tc_fence_after();
-        const uint64_t xa = ptx::make_smem_desc_sw128(p0_slot(mm_s), 16, 1024);
-        const uint64_t wa = ptx::make_smem_desc_sw128(p0_slot(mm_s) + (uint32_t)(p.p0_rows * 128), 16, 1024);
+      if (rank == 0) {
+        // M = 128 over the pair (64 rows per CTA) whenever the CTA's token rows fit: the MMA reads M/2 rows of 32
+        // bytes per CTA from shared memory whatever number of them is real
+        const uint32_t idesc_p0 = ptx::make_idesc_f16(std::is_same<ActT, __nv_bfloat16>::value, false, false,
+                                                      p0_m128 ? kBM : 2 * kBM, p.r_pad);
+        for (int mm = 0; mm < n_p0; ++mm) {
+          ptx::mbar_wait(bar_p0_full(mm_s), mm_par);
+          ptx::tc_fence_after();
+          const uint64_t xa = ptx::make_smem_desc_sw128(p0_slot(mm_s), 16, 1024);
+          const uint64_t wa = ptx::make_smem_desc_sw128(p0_slot(mm_s) + (uint32_t)(p.p0_rows * 128), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k)
-          ptx::umma_ss_pair(tmem_d + p0_col, xa + k * (32u >> 4), wa + k * (32u >> 4), idesc_p0, (mm | k) != 0 ? 1u : 0u);
-        ptx::umma_commit_pair(bar_p0_empty(mm_s));
-        if (mm == n_p0 - 1) ptx::umma_commit_pair(bar_p0_done);  // -> epilogue warps, both CTAs
-        if (++mm_s == p.p0_slots) {
-          mm_s = 0;
-          mm_par ^= 1u;
+          for (int k = 0; k < kBK / 16; ++k)
+            ptx::umma_ss_pair(tmem_d + p0_col, xa + k * (32u >> 4), wa + k * (32u >> 4), idesc_p0, (mm | k) != 0 ? 1u : 0u);
+          ptx::umma_commit_pair(bar_p0_empty(mm_s));
+          if (mm == n_p0 - 1) ptx::umma_commit_pair(bar_p0_done);  // -> epilogue warps, both CTAs
+          if (++mm_s == p.p0_slots) {
+            mm_s = 0;
+            mm_par ^= 1u;
+          }
+        }
+      }
+      if (job_on) {
+        // ---- dA/dB job: this thread issues the loads of its CTA and (leader) the MMAs, polling both duties.  The
+        // ring continues where the side product left it: slot and parity after n_p0 steps.
+        ptx::griddep_wait();
+        // (the peer CTA's thread has issued nothing so far: the ring is the side product's until its last MMA is done)
+        if (rank != 0) ptx::mbar_wait(bar_p0_done, 0);
+        const CUtensorMap* map_m = job_is_a ? &jm.m_a : &jm.m_b;
+        const CUtensorMap* map_v = job_is_a ? &jm.v_a : &jm.v_b;
+        if (job_is_a) {  // dt^T is being written by every CTA of the grid in this very launch
+          const long long t_start = clock64();
+          unsigned gen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(p.sync + 1) : "memory");
+            if (clock64() - t_start > 4000000000LL) __trap();
+          } while (gen == gen0);
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        int ld_s = n_p0 % p.p0_slots;
+        uint32_t ld_par = 1u ^ (uint32_t)((n_p0 / p.p0_slots) & 1);
+        mm_s = ld_s;
+        mm_par = (uint32_t)((n_p0 / p.p0_slots) & 1);
+        // M = 128 over the pair: 64 columns per CTA = one MN-major atom [64 tokens x 128 bytes]; N = r_pad; K = tokens
+        const uint32_t idesc_job = ptx::make_idesc_f16(std::is_same<ActT, __nv_bfloat16>::value, /*a_mn_major=*/true,
+                                                       /*b_mn_major=*/false, kBM, p.r_pad);
+        int ld = 0, mm = 0;
+        while (ld < job_steps || (rank == 0 && mm < job_steps)) {
+          if (ld < job_steps && ptx::mbar_try_wait(bar_p0_empty(ld_s), ld_par)) {
+            const uint32_t dst = p0_slot(ld_s);
+            if (rank == 0) ptx::mbar_arrive_expect_tx(bar_p0_full(ld_s), (uint32_t)(2 * (kJobBox + p.la_bytes)));
+            const uint32_t leader_bar = ptx::mapa(bar_p0_full(ld_s), 0);
+            ptx::tma_load_2d_pair(map_m, dst, leader_bar, job_col0, ld * 64);
+            ptx::tma_load_2d_pair(map_v, dst + (uint32_t)kJobBox, leader_bar, ld * 64, (int)rank * (p.r_pad >> 1));
+            ++ld;
+            if (++ld_s == p.p0_slots) {
+              ld_s = 0;
+              ld_par ^= 1u;
+            }
+          }
+          if (rank == 0 && mm < job_steps && ptx::mbar_try_wait(bar_p0_full(mm_s), mm_par)) {
+            ptx::tc_fence_after();
+            const uint64_t ma = ptx::make_smem_desc_sw128(p0_slot(mm_s), 8192, 1024);
+            const uint64_t va = ptx::make_smem_desc_sw128(p0_slot(mm_s) + (uint32_t)kJobBox, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // 16 tokens: 16 rows of 128 bytes (A), 32 bytes inside a row (B)
+              ptx::umma_ss_pair(tmem_d + job_col, ma + k * (2048u >> 4), va + k * (32u >> 4), idesc_job, (mm | k) != 0 ? 1u : 0u);
+            ptx::umma_commit_pair(bar_p0_empty(mm_s));
+            if (mm == job_steps - 1) ptx::umma_commit_pair(bar_job_done);  // -> epilogue warps, both CTAs
+            ++mm;
+            if (++mm_s == p.p0_slots) {
+              mm_s = 0;
+              mm_par ^= 1u;
+            }
+          }
         }
       }
     }
@@ -439,7 +528,8 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         for (int ld = 0; ld < n_p0; ++ld) {
           ptx::mbar_wait(bar_p0_empty(ld_s), ld_par);
           const uint32_t dst = p0_slot(ld_s);
-          if (rank == 0) ptx::mbar_arrive_expect_tx(bar_p0_full(ld_s), (uint32_t)(2 * p.p0_slot_bytes));
+          // (bytes of the two boxes, not the slot pitch: the dA/dB job's larger boxes can widen the slots)
+          if (rank == 0) ptx::mbar_arrive_expect_tx(bar_p0_full(ld_s), (uint32_t)(2 * (p.p0_rows * 128 + p.la_bytes)));
           const uint32_t leader_bar = ptx::mapa(bar_p0_full(ld_s), 0);
           ptx::tma_load_2d_pair(&map_p0a, dst, leader_bar, ld * kBK, (int)blockIdx.x * p.p0_rows);
           ptx::tma_load_2d_pair(&map_p0w, dst + (uint32_t)(p.p0_rows * 128), leader_bar, ld * kBK,
@@ -547,6 +637,16 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
 #pragma unroll
           for (int c = 0; c < kMaxSideRP / 8; ++c)
             if (c < (n_col >> 3)) orow[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          if (p.save_t != nullptr) {  // the same values as rows [r_pad, T] (K-major operand of the dA/dB job)
+            uint16_t* tcol = static_cast<uint16_t*>(p.save_t) + (int64_t)(half * n_col) * p.T + tok;
+#pragma unroll
+            for (int c = 0; c < kMaxSideRP / 2; ++c) {
+              if (2 * c < n_col) {
+                tcol[(int64_t)(2 * c) * p.T] = (uint16_t)(pk[c] & 0xffffu);
+                tcol[(int64_t)(2 * c + 1) * p.T] = (uint16_t)(pk[c] >> 16);
+              }
+            }
+          }
         }
       }
       __threadfence();
@@ -574,6 +674,32 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         for (int u = 0; u < 4; ++u) {
           const int64_t f = feat0 + quad * 32 + (lane >> 2) + 8 * u;
           if (f < OUT) bias_v[u] = to_f32<ActT>(static_cast<const ActT*>(p.bias)[f]);
+        }
+      }
+      if (kJob && job_on && item + n_pairs >= n_items) {
+        // dA/dB job of this pair: its 64 columns x r_pad accumulator (M = 128 layout: lanes 0..63 hold the first half
+        // of the r_pad columns of rows 0..63, lanes 64..127 the second half) -- written while the last tile's MMAs run
+        ptx::mbar_wait(bar_job_done, 0);
+        ptx::tc_fence_after();
+        const int L = quad * 32 + lane;
+        const int64_t col = job_col0 + (L & 63);
+        const int jh = (L >> 6) * (p.r_pad >> 1);
+        const int64_t C = job_is_a ? p.K : p.N;
+        uint32_t v[16];
+        ptx::tmem_ld_32x32b_x16(lane_base + job_col, v);
+        ptx::tmem_ld_wait();
+        if (col < C) {
+          if (job_is_a) {  // dA[j, col]: per j the warp writes 32 consecutive elements
+            ActT* o = static_cast<ActT*>(p.job_da) + col;
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (e < (p.r_pad >> 1) && jh + e < p.r) o[(int64_t)(jh + e) * p.K] = from_f32<ActT>(__uint_as_float(v[e]));
+          } else {         // dB[col, j]: this thread's half row
+            ActT* o = static_cast<ActT*>(p.job_db) + col * p.r + jh;
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (e < (p.r_pad >> 1) && jh + e < p.r) o[e] = from_f32<ActT>(p.scale * __uint_as_float(v[e]));
+          }
         }
       }
       if (!kBackward && p.bt_out != nullptr && tile / p.n_fblk == 0) {
@@ -1011,6 +1137,7 @@ static int side_rank(const LayerArgs& a, bool backward) {
 
 struct Tc2Choice {
   Tc2Plan plan;
+  bool job;     // backward: dA / dB inside the launch too
   int rp;       // > 0: side product inside the launch
   int pairs;    // CTA pairs launched
   int p0_rows;  // token rows per CTA of the side product
@@ -1034,6 +1161,7 @@ static Tc2Choice choose_tc2(const LayerArgs& a, bool backward, int n_pairs) {
   const VftEnv& ev = env();
   Tc2Choice c;
   c.p0_rows = 0;
+  c.job = false;
   // triage override VFT_TC2_NACC="<n_acc>x<N_acc>" (clamped to what the path allows): forces the shape, never splits
   auto forced = [&](int rp) -> bool {
     if (ev.tc2_force_na <= 0) return false;
@@ -1052,13 +1180,24 @@ static Tc2Choice choose_tc2(const LayerArgs& a, bool backward, int n_pairs) {
     // the plan the launch would take without it decides: a problem small enough to be split along the contraction
     // keeps its side kernel (which is then tiny), so does one with more tokens than one pass of 128 rows per CTA holds
     const Tc2Plan base = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs);
-    c.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs, /*allow_split=*/false, c.rp);
-    forced(c.rp);
-    c.pairs = pairs_for(c.plan, n_pairs);
-    const int64_t rows = ceil_div64(ceil_div64(a.T, 2 * c.pairs), 8) * 8;
-    if ((base.n_split == 1 || ev.tc2_fuse == 1) && c.plan.cfg.N_acc > 0 && rows <= kBM) {
-      c.p0_rows = (int)rows;
-      return c;
+    // dA/dB job: everything it reads and writes is there, TMA can address the transposed side products (row stride
+    // T * 2 bytes), and a second block of r_pad accumulator columns is free
+    const bool job_ok = backward && ev.tc2_job != 0 && a.job_x && a.tt_save && a.job_dtt && a.job_da && a.job_db &&
+                        a.T % 8 == 0 && ((reinterpret_cast<uintptr_t>(a.job_x) | reinterpret_cast<uintptr_t>(a.tt_save) |
+                                          reinterpret_cast<uintptr_t>(a.job_dtt)) & 15u) == 0;
+    for (int with_job = job_ok ? 1 : 0; with_job >= 0; --with_job) {
+      const int cols = c.rp * (1 + with_job);  // accumulator columns set aside
+      c.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs, /*allow_split=*/false, cols);
+      forced(cols);
+      c.pairs = pairs_for(c.plan, n_pairs);
+      const int64_t rows = ceil_div64(ceil_div64(a.T, 2 * c.pairs), 8) * 8;
+      const int64_t units = ceil_div64(a.K, kBM) + ceil_div64(a.N, kBM);
+      if (with_job && (units > c.pairs || c.plan.cfg.N_acc <= 0)) continue;
+      if ((base.n_split == 1 || ev.tc2_fuse == 1) && c.plan.cfg.N_acc > 0 && rows <= kBM) {
+        c.p0_rows = (int)rows;
+        c.job = with_job != 0;
+        return c;
+      }
     }
     c.rp = 0;
   }
@@ -1117,6 +1256,17 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   p.p0_per_step = 2;
   p.save = lora_act;
   p.bt_out = kBackward ? nullptr : a.bt_save;
+  p.save_t = rp > 0 ? (kBackward ? (choice.job ? a.job_dtt : nullptr) : a.tt_save) : nullptr;
+  p.job = choice.job ? 1 : 0;
+  p.job_units_a = (int)ceil_div64(a.K, kBM);
+  p.job_units = choice.job ? p.job_units_a + (int)ceil_div64(a.N, kBM) : 0;
+  p.job_da = a.job_da;
+  p.job_db = a.job_db;
+  if (choice.job && p.p0_slot_bytes < kJobBox + p.la_bytes) {  // the job's boxes ride the side product's ring
+    p.p0_slot_bytes = kJobBox + p.la_bytes;
+    p.p0_slots = kP0Budget / p.p0_slot_bytes;
+    if (p.p0_slots > kMaxP0) p.p0_slots = kMaxP0;
+  }
   p.sync = nullptr;
   if (rp > 0) {
     p.sync = next_sync_pair();
@@ -1143,6 +1293,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   const CUtensorMapDataType dt =
       std::is_same<ActT, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap map_act, map_lora, map_out, map_out16, map_p0a, map_p0w;
+  JobMaps jm;
   int rc = make_map_2d(&map_act, dt, act, (uint64_t)RED, (uint64_t)a.T, (uint64_t)RED * 2, kBK, cfg.N_acc / 2,
                        CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != VFT_OK) return rc;
@@ -1162,6 +1313,19 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
                      (uint64_t)RED * 2, kBK, (uint32_t)(rp / 2), CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != VFT_OK) return rc;
   }
+  jm.m_a = jm.m_b = jm.v_a = jm.v_b = map_act;
+  if (choice.job) {
+    rc = make_map_2d(&jm.m_a, dt, a.job_x, (uint64_t)a.K, (uint64_t)a.T, (uint64_t)a.K * 2, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != VFT_OK) return rc;
+    rc = make_map_2d(&jm.m_b, dt, act, (uint64_t)a.N, (uint64_t)a.T, (uint64_t)a.N * 2, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != VFT_OK) return rc;
+    rc = make_map_2d(&jm.v_a, dt, a.job_dtt, (uint64_t)a.T, (uint64_t)rp, (uint64_t)a.T * 2, 64, (uint32_t)(rp / 2),
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != VFT_OK) return rc;
+    rc = make_map_2d(&jm.v_b, dt, a.tt_save, (uint64_t)a.T, (uint64_t)rp, (uint64_t)a.T * 2, 64, (uint32_t)(rp / 2),
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != VFT_OK) return rc;
+  }
   if (a.r > 0) {
     rc = make_map_2d(&map_lora, dt, lora_act, VFT_LORA_LD, (uint64_t)a.T, VFT_LORA_LD * 2, kBK, cfg.N_acc / 2,
                      CU_TENSOR_MAP_SWIZZLE_128B);
@@ -1176,11 +1340,13 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   if (p.n_stg > kMaxStg) p.n_stg = kMaxStg;
   if (ev.tc2_n_stg >= 2 && ev.tc2_n_stg <= p.n_stg) p.n_stg = ev.tc2_n_stg;
   const int dyn_bytes = cfg.stages * p.stage_bytes + p0_bytes + p.n_stg * kStgBytes + kBarBytes + 1024;  // + 1024-B alignment slack
-  auto kern_plain = qlora_tc2_kernel<ActT, kBackward, false>;
-  auto kern_side = qlora_tc2_kernel<ActT, kBackward, true>;
+  auto kern_plain = qlora_tc2_kernel<ActT, kBackward, false, false>;
+  auto kern_side = qlora_tc2_kernel<ActT, kBackward, true, false>;
+  auto kern_job = qlora_tc2_kernel<ActT, kBackward, true, kBackward>;  // (forward: the same function as kern_side)
   VFT_OPT_IN_SMEM_ONCE(kern_plain, VFT_MAX_DYN_SMEM);  // dyn_bytes depends on the plan: opt in to the limit
   VFT_OPT_IN_SMEM_ONCE(kern_side, VFT_MAX_DYN_SMEM);
-  auto kern = rp > 0 ? kern_side : kern_plain;
+  VFT_OPT_IN_SMEM_ONCE(kern_job, VFT_MAX_DYN_SMEM);
+  auto kern = rp > 0 ? (choice.job ? kern_job : kern_side) : kern_plain;
   const int pairs = choice.pairs;
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)(2 * pairs));
@@ -1196,7 +1362,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
   lc.numAttrs = pdl_enabled() ? 2 : 1;
-  VFT_CUDA_OK(cudaLaunchKernelEx(&lc, kern, map_act, map_lora, map_out, map_out16, map_p0a, map_p0w, p));
+  VFT_CUDA_OK(cudaLaunchKernelEx(&lc, kern, map_act, map_lora, map_out, map_out16, map_p0a, map_p0w, jm, p));
   VFT_CUDA_OK(cudaGetLastError());
   if (p.n_split > 1) {
     const int64_t total8 = a.T * OUT / 8;
@@ -1243,6 +1409,12 @@ int64_t tc2_workspace_bytes(int64_t T, int64_t N, int64_t K, int r, bool backwar
 bool tc2_fuses_side(const LayerArgs& a, bool backward) {
   if (a.T <= 0 || !tc2_preferred(a, backward)) return false;
   return choose_tc2(a, backward, device_pairs()).rp > 0;
+}
+
+// True when the backward launch also computes the adapter's weight gradients (no vft_lora_bwd_dab afterwards)
+bool tc2_fuses_dab(const LayerArgs& a) {
+  if (a.T <= 0 || !tc2_preferred(a, true)) return false;
+  return choose_tc2(a, true, device_pairs()).job;
 }
 
 int tc2_fwd(const LayerArgs& a, const void* x, void* y, void* t_save, cudaStream_t st) {

@@ -76,6 +76,7 @@ void VftEnv::load() {
   }
   tc2_nosplit = is("VFT_TC2_NOSPLIT", '1');
   tc2_fuse = num("VFT_TC2_FUSE", -1);
+  tc2_job = num("VFT_TC2_JOB", -1);
 }
 static VftEnv& env_mut() {
   static VftEnv e = [] { VftEnv v; v.load(); return v; }();
@@ -188,21 +189,31 @@ int vft_absmax_denest(const uint8_t* absmax8, const float* absmax2, const float*
                               static_cast<cudaStream_t>(stream));
 }
 
+static int64_t bwd_dtt_bytes(int64_t T, int r) {
+  const int64_t rows = ((r > 0 ? r : 0) + 15) / 16 * 16;
+  return (rows * T * 2 + 255) / 256 * 256;
+}
+
 int64_t vft_workspace_bytes(int op, int64_t T, int64_t N, int64_t K, int r) {
   if (op == VFT_OP_ABSMAX_NEST) return absmax_nest_workspace_bytes();
   if (op == VFT_OP_BWD_DAB) return (int64_t)sizeof(float) * (N + K) * (r > 0 ? r : 0);
   if (op == VFT_OP_FWD) return tc2_workspace_bytes(T, N, K, r, false);
   if (op == VFT_OP_BWD_DX) return tc2_workspace_bytes(T, N, K, r, true);
+  if (op == VFT_OP_BWD) {  // [dt^T scratch, 256-byte aligned][the larger of the two-call workspaces]
+    const int64_t dx = tc2_workspace_bytes(T, N, K, r, true), dab = (int64_t)sizeof(float) * (N + K) * (r > 0 ? r : 0);
+    return bwd_dtt_bytes(T, r) + (dx > dab ? dx : dab);
+  }
   return 0;
 }
 
 int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
                   int blocksize, int act_dtype, int qdtype, const void* bias, const void* lora_a, const void* lora_b,
-                  int r, float scale, void* y, void* t_save, void* bt_save, void* ws, int64_t ws_bytes,
+                  int r, float scale, void* y, void* t_save, void* bt_save, void* tt_save, void* ws, int64_t ws_bytes,
                   const uint8_t* codes_t, const float* absmax_t, void* stream) {
   VFT_REQUIRE((codes_t == nullptr) == (absmax_t == nullptr), "codes_t / absmax_t must be given together");
   LayerArgs a{T, N, K, blocksize, act_dtype, qdtype, r, scale, packed, absmax, bias, lora_a, lora_b, codes_t, absmax_t,
               ws, ws_bytes, r > 0 ? bt_save : nullptr};
+  a.tt_save = r > 0 ? tt_save : nullptr;
   int rc = check_layer(a, x, y);
   if (rc != VFT_OK) return rc;
   VFT_REQUIRE(r == 0 || t_save != nullptr, "t_save is required when r > 0");
@@ -225,6 +236,10 @@ int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* 
                                           : side_mma() ? mma_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st)
                                                        : tc_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st);
     if (rc != VFT_OK) return rc;
+    if (a.tt_save != nullptr) {  // t^T for the backward's dA/dB job: the fused launch writes it itself
+      rc = simt_lora_tt(t_save, T, r, act_dtype, a.tt_save, st);
+      if (rc != VFT_OK) return rc;
+    }
   }
   // bt_save = s * B^T for the backward call: the persistent tcgen05 forward writes it on its way, every other path
   // gets a small kernel
@@ -270,6 +285,48 @@ int vft_qlora_bwd_dx(const void* dy, int64_t T, const uint8_t* packed, const flo
   }
   set_path(tc ? VFT_PATH_TCGEN05 : VFT_PATH_SIMT);
   return tc ? tc_bwd_dx(a, dy, dx, dt_save, st) : simt_bwd_dx(a, dy, dx, dt_save, st);
+}
+
+int vft_qlora_bwd(const void* dy, const void* x, int64_t T, const uint8_t* packed, const float* absmax, int64_t N, int64_t K,
+                  int blocksize, int act_dtype, int qdtype, const void* lora_a, const void* lora_b, int r, float scale,
+                  const void* t_save, const void* tt_save, const void* bt_save, void* dx, void* dA, void* dB,
+                  void* dt_save, void* ws, int64_t ws_bytes, const uint8_t* codes_t, const float* absmax_t, void* stream) {
+  VFT_REQUIRE(r > 0 && r <= VFT_LORA_LD, "LoRA rank %d outside [1, %d]", r, VFT_LORA_LD);
+  VFT_REQUIRE(dA && dB && dt_save && (T == 0 || (dy && x && t_save)), "null pointer");
+  const int64_t need = vft_workspace_bytes(VFT_OP_BWD, T, N, K, r);
+  if (ws == nullptr || ws_bytes < need) {
+    set_error("workspace too small: need %lld bytes, got %lld", (long long)need, (long long)ws_bytes);
+    return VFT_ERR_WORKSPACE;
+  }
+  const int64_t dtt_bytes = bwd_dtt_bytes(T, r);
+  void* ws_rest = static_cast<char*>(ws) + dtt_bytes;
+  const int64_t rest_bytes = ws_bytes - dtt_bytes;
+  if (T > 0 && dx != nullptr) {
+    // one launch: dx, dt (side product) and dA / dB (column-tile job) inside the persistent tcgen05 kernel
+    LayerArgs a{T, N, K, blocksize, act_dtype, qdtype, r, scale, packed, absmax, nullptr, lora_a, lora_b, codes_t, absmax_t,
+                ws_rest, rest_bytes, const_cast<void*>(bt_save)};
+    a.tt_save = const_cast<void*>(tt_save);
+    a.job_x = x;
+    a.job_dtt = ws;
+    a.job_da = dA;
+    a.job_db = dB;
+    int rc = check_layer(a, dy, dx);
+    if (rc != VFT_OK) return rc;
+    const bool tc = use_tc(a, true, &rc);
+    if (rc != VFT_OK) return rc;
+    if (tc && tc_fuses_side(a, true) && tc2_fuses_dab(a)) {
+      set_path(VFT_PATH_TCGEN05);
+      return tc_bwd_dx(a, dy, dx, dt_save, static_cast<cudaStream_t>(stream));
+    }
+  }
+  // two calls: input gradient (+ dt), then the adapter's weight gradients
+  int rc = vft_qlora_bwd_dx(dy, T, packed, absmax, N, K, blocksize, act_dtype, qdtype, lora_a, lora_b, r, scale, dx, dt_save,
+                            bt_save, ws_rest, rest_bytes, codes_t, absmax_t, stream);
+  if (rc != VFT_OK) return rc;
+  const int path = g_path;
+  rc = vft_lora_bwd_dab(dy, x, t_save, dt_save, T, N, K, r, act_dtype, scale, dA, dB, ws_rest, rest_bytes, stream);
+  set_path(path);
+  return rc;
 }
 
 int vft_lora_bwd_dab(const void* dy, const void* x, const void* t_save, const void* dt_save, int64_t T, int64_t N,

@@ -118,6 +118,7 @@ struct VftEnv {
   int tc2_max_stages = 0, tc2_stages = 0, tc2_n_stg = 0;   // VFT_TC2_MAXSTAGES / _STAGES / _NSTG
   int tc2_force_na = 0, tc2_force_nn = 0;                   // VFT_TC2_NACC="<n_acc>x<N_acc>"
   bool tc2_nosplit = false;                                 // VFT_TC2_NOSPLIT=1
+  int tc2_job = -1;   // VFT_TC2_JOB=0: adapter weight gradients by vft_lora_bwd_dab's kernel, not inside the backward launch
   int tc2_fuse = -1;  // VFT_TC2_FUSE=1: adapter down-projection fused into the forward launch whenever the shape
                       // allows it (never splits the contraction); otherwise a side kernel (see fuse_rank())
   void load();
@@ -160,6 +161,13 @@ struct LayerArgs {
   // s * lora_up.weight^T as a K-major [16 * ceil(r / 16), N] matrix: written by the forward call (when asked for), read
   // by the backward call, which can then compute dt = s * dy . B inside its launch; nullptr = not available
   void* bt_save = nullptr;
+  // t^T [16 * ceil(r / 16), T]: forward output (optional), backward input -- with it, x, a dt^T scratch of the same
+  // size and the two gradient buffers, the backward launch also computes dA = dt^T . x and dB = s * dy^T . t itself
+  void* tt_save = nullptr;
+  const void* job_x = nullptr;
+  void* job_dtt = nullptr;
+  void* job_da = nullptr;
+  void* job_db = nullptr;
 };
 
 // generic CUDA-core family
@@ -203,6 +211,8 @@ bool tc2_preferred(const LayerArgs& a, bool backward);
 int64_t tc2_workspace_bytes(int64_t T, int64_t N, int64_t K, int r, bool backward);
 int tc2_fwd(const LayerArgs& a, const void* x, void* y, void* t_save, cudaStream_t st);
 bool tc2_fuses_side(const LayerArgs& a, bool backward);  // the launch computes t_save / dt_save itself (no side kernel)
+bool tc2_fuses_dab(const LayerArgs& a);                  // the backward launch also computes dA, dB (no vft_lora_bwd_dab)
+int simt_lora_tt(const void* t_save, int64_t T, int r, int act_dtype, void* tt, cudaStream_t st);
 int tc2_bwd_dx(const LayerArgs& a, const void* dy, void* dx, const void* dt_save, cudaStream_t st);
 
 }  // namespace vft

@@ -15,11 +15,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ALT_LIB = os.environ.get("VFT_LIB")
 LIB_PATH = _ALT_LIB if _ALT_LIB else os.path.join(_HERE, "libvft_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 LORA_LD = 64
 F32, F16, BF16 = 0, 1, 2
 PATH_NONE, PATH_TCGEN05, PATH_SIMT, PATH_GEMV = 0, 1, 2, 3
-OP_FWD, OP_BWD_DX, OP_BWD_DAB, OP_ABSMAX_NEST = 0, 1, 2, 3
+OP_FWD, OP_BWD_DX, OP_BWD_DAB, OP_ABSMAX_NEST, OP_BWD = 0, 1, 2, 3, 4
 
 # every symbol include/vft_b200.h declares: (restype, argtypes)
 _c = ctypes
@@ -41,7 +41,9 @@ SYMBOLS = {
     "vft_absmax_nest_at": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p]),
     "vft_absmax_denest": (_i, [_p, _p, _p, _f, _i64, _i, _p, _p]),
     "vft_workspace_bytes": (_i64, [_i, _i64, _i64, _i64, _i]),
-    "vft_qlora_fwd": (_i, [_p, _i64, _p, _p, _i64, _i64, _i, _i, _i, _p, _p, _p, _i, _f, _p, _p, _p, _p, _i64, _p, _p, _p]),
+    "vft_qlora_fwd": (_i, [_p, _i64, _p, _p, _i64, _i64, _i, _i, _i, _p, _p, _p, _i, _f, _p, _p, _p, _p, _p, _i64, _p, _p, _p]),
+    "vft_qlora_bwd": (_i, [_p, _p, _i64, _p, _p, _i64, _i64, _i, _i, _i, _p, _p, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _i64,
+                           _p, _p, _p]),
     "vft_qlora_bwd_dx": (_i, [_p, _i64, _p, _p, _i64, _i64, _i, _i, _i, _p, _p, _i, _f, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "vft_lora_bwd_dab": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i, _i, _f, _p, _p, _p, _i64, _p]),
 }

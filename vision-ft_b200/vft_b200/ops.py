@@ -238,6 +238,8 @@ class QLoRALinearFunction(torch.autograd.Function):
         t_save = torch.empty((T, LORA_LD), dtype=x.dtype, device=dev) if r else None
         # s * B^T, K-major: lets the backward launch compute dt = s * dy . B itself (include/vft_b200.h)
         bt_save = torch.empty((bt_rows(r), N), dtype=x.dtype, device=dev) if r and T > 0 else None
+        # t^T: with it the backward launch computes dA, dB as well (one launch for the whole backward)
+        tt_save = torch.empty((bt_rows(r), T), dtype=x.dtype, device=dev) if r and T > 0 else None
         ws, ws_bytes = _workspace(_cabi.OP_FWD, T, N, K, r, dev)
         with _on_device(dev):
             if T > 0:  # an empty batch (ragged bucket on one rank) launches nothing
@@ -245,11 +247,11 @@ class QLoRALinearFunction(torch.autograd.Function):
                     lib.vft_qlora_fwd(
                         x2.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, blocksize, act, dtype_code(qdtype),
                         _ptr(bias), _ptr(lora_a), _ptr(lora_b), r, float(scale), y.data_ptr(), _ptr(t_save), _ptr(bt_save),
-                        _ptr(ws), ws_bytes, _ptr(codes_t), _ptr(absmax_t), _stream(),
+                        _ptr(tt_save), _ptr(ws), ws_bytes, _ptr(codes_t), _ptr(absmax_t), _stream(),
                     )
                 )
         ctx.meta = (N, K, blocksize, act, dtype_code(qdtype), r, float(scale), x.shape)
-        ctx.tiled = (codes_t, absmax_t, bt_save)  # frozen derived buffers, not autograd-tracked
+        ctx.tiled = (codes_t, absmax_t, bt_save, tt_save)  # frozen derived buffers, not autograd-tracked
         ctx.save_for_backward(x2 if r else None, packed, absmax, lora_a, lora_b, t_save)
         return y
 
@@ -257,7 +259,7 @@ class QLoRALinearFunction(torch.autograd.Function):
     def backward(ctx, dy):
         N, K, blocksize, act, qd, r, scale, x_shape = ctx.meta
         x2, packed, absmax, lora_a, lora_b, t_save = ctx.saved_tensors
-        codes_t, absmax_t, bt_save = ctx.tiled
+        codes_t, absmax_t, bt_save, tt_save = ctx.tiled
         dev = dy.device
         dy2 = dy.reshape(-1, N)
         if dy2.dtype != _TORCH_DT[act]:
@@ -274,6 +276,21 @@ class QLoRALinearFunction(torch.autograd.Function):
         if T == 0:  # empty batch: no launches; the adapter gradients of an empty sum are zeros
             if need_ab:
                 da, db = torch.zeros_like(lora_a), torch.zeros_like(lora_b)
+            return dx, None, None, None, da, db, None, None, None, None, None, None
+        if need_dx and need_ab:
+            # the whole backward in one C-ABI call (one launch when the persistent tcgen05 kernel takes it)
+            da = torch.empty_like(lora_a)
+            db = torch.empty_like(lora_b)
+            ws, ws_bytes = _workspace(_cabi.OP_BWD, T, N, K, r, dev)
+            with _on_device(dev):
+                check(
+                    lib.vft_qlora_bwd(
+                        dy2.data_ptr(), x2.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, blocksize, act, qd,
+                        _ptr(lora_a), _ptr(lora_b), r, scale, t_save.data_ptr(), _ptr(tt_save), _ptr(bt_save), _ptr(dx),
+                        da.data_ptr(), db.data_ptr(), dt_save.data_ptr(), _ptr(ws), ws_bytes, _ptr(codes_t), _ptr(absmax_t),
+                        _stream(),
+                    )
+                )
             return dx, None, None, None, da, db, None, None, None, None, None, None
         with _on_device(dev):
             if need_dx or need_ab:
@@ -313,7 +330,7 @@ def _empty(like: torch.Tensor) -> torch.Tensor:
 def _qlora_fwd_op(x: torch.Tensor, packed: torch.Tensor, absmax: torch.Tensor, bias: torch.Tensor | None,
                   lora_a: torch.Tensor | None, lora_b: torch.Tensor | None, scale: float, out_features: int,
                   in_features: int, blocksize: int, qdtype: int, codes_t: torch.Tensor | None,
-                  absmax_t: torch.Tensor | None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                  absmax_t: torch.Tensor | None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     dev = _require_cuda(x, packed, absmax, bias, lora_a, lora_b)
     N, K = out_features, in_features
     if x.shape[-1] != K:
@@ -331,14 +348,16 @@ def _qlora_fwd_op(x: torch.Tensor, packed: torch.Tensor, absmax: torch.Tensor, b
     # (zeros: the kernels write the first 16 * ceil(r / 16) columns only, and an operator's outputs must be reproducible)
     t_save = torch.zeros((T, LORA_LD), dtype=x.dtype, device=dev) if r else _empty(x)
     bt_save = torch.empty((bt_rows(r), N), dtype=x.dtype, device=dev) if r else _empty(x)
+    tt_save = torch.empty((bt_rows(r), T), dtype=x.dtype, device=dev) if r else _empty(x)
     ws, ws_bytes = _workspace(_cabi.OP_FWD, T, N, K, r, dev)
     with _on_device(dev):
         if T > 0:
             check(lib.vft_qlora_fwd(x2.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, blocksize, dtype_code(x.dtype),
                                     qdtype, _ptr(bias), _ptr(la), _ptr(lb), r, float(scale), y.data_ptr(),
-                                    t_save.data_ptr() if r else None, bt_save.data_ptr() if r else None, _ptr(ws), ws_bytes,
+                                    t_save.data_ptr() if r else None, bt_save.data_ptr() if r else None,
+                                    tt_save.data_ptr() if r else None, _ptr(ws), ws_bytes,
                                     _ptr(codes_t), _ptr(absmax_t), _stream()))
-    return y, t_save, bt_save
+    return y, t_save, bt_save, tt_save
 
 
 @_qlora_fwd_op.register_fake
@@ -347,13 +366,14 @@ def _(x, packed, absmax, bias, lora_a, lora_b, scale, out_features, in_features,
     y = x.new_empty((*x.shape[:-1], out_features))
     t_save = x.new_empty((T, LORA_LD)) if lora_a is not None else x.new_empty((0,))
     bt_save = x.new_empty((bt_rows(lora_a.shape[0]), out_features)) if lora_a is not None else x.new_empty((0,))
-    return y, t_save, bt_save
+    tt_save = x.new_empty((bt_rows(lora_a.shape[0]), T)) if lora_a is not None else x.new_empty((0,))
+    return y, t_save, bt_save, tt_save
 
 
 @torch.library.custom_op("vft_b200::qlora_bwd", mutates_args=())
 def _qlora_bwd_op(dy: torch.Tensor, x: torch.Tensor, packed: torch.Tensor, absmax: torch.Tensor,
                   lora_a: torch.Tensor | None, lora_b: torch.Tensor | None, t_save: torch.Tensor, bt_save: torch.Tensor,
-                  scale: float, out_features: int, in_features: int, blocksize: int, qdtype: int, codes_t: torch.Tensor | None,
+                  tt_save: torch.Tensor, scale: float, out_features: int, in_features: int, blocksize: int, qdtype: int, codes_t: torch.Tensor | None,
                   absmax_t: torch.Tensor | None, need_dx: bool, need_ab: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     dev = dy.device
     N, K = out_features, in_features
@@ -371,6 +391,14 @@ def _qlora_bwd_op(dy: torch.Tensor, x: torch.Tensor, packed: torch.Tensor, absma
         return dx, da, db
     dt_save = torch.empty((T, LORA_LD), dtype=x.dtype, device=dev) if r else None
     act = dtype_code(x.dtype)
+    if need_dx and need_ab:
+        ws, ws_bytes = _workspace(_cabi.OP_BWD, T, N, K, r, dev)
+        with _on_device(dev):
+            check(lib.vft_qlora_bwd(dy2.data_ptr(), x2.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, blocksize, act,
+                                    qdtype, _ptr(la), _ptr(lb), r, float(scale), t_save.data_ptr(), tt_save.data_ptr(),
+                                    bt_save.data_ptr(), dx.data_ptr(), da.data_ptr(), db.data_ptr(), dt_save.data_ptr(),
+                                    _ptr(ws), ws_bytes, _ptr(codes_t), _ptr(absmax_t), _stream()))
+        return dx, da, db
     with _on_device(dev):
         ws, ws_bytes = _workspace(_cabi.OP_BWD_DX, T, N, K, r, dev) if need_dx else (None, 0)
         check(lib.vft_qlora_bwd_dx(dy2.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, blocksize, act, qdtype,
@@ -385,8 +413,8 @@ def _qlora_bwd_op(dy: torch.Tensor, x: torch.Tensor, packed: torch.Tensor, absma
 
 
 @_qlora_bwd_op.register_fake
-def _(dy, x, packed, absmax, lora_a, lora_b, t_save, bt_save, scale, out_features, in_features, blocksize, qdtype, codes_t,
-      absmax_t, need_dx, need_ab):
+def _(dy, x, packed, absmax, lora_a, lora_b, t_save, bt_save, tt_save, scale, out_features, in_features, blocksize, qdtype,
+      codes_t, absmax_t, need_dx, need_ab):
     dx = x.new_empty(x.shape) if need_dx else x.new_empty((0,))
     ab = need_ab and lora_a is not None
     da = lora_a.new_empty(lora_a.shape) if ab else x.new_empty((0,))
@@ -396,17 +424,17 @@ def _(dy, x, packed, absmax, lora_a, lora_b, t_save, bt_save, scale, out_feature
 
 def _op_setup_context(ctx, inputs, output):
     x, packed, absmax, bias, lora_a, lora_b, scale, N, K, blocksize, qdtype, codes_t, absmax_t = inputs
-    _, t_save, bt_save = output
+    _, t_save, bt_save, tt_save = output
     ctx.meta = (float(scale), N, K, blocksize, qdtype)
-    ctx.save_for_backward(x, packed, absmax, lora_a, lora_b, t_save, bt_save, codes_t, absmax_t)
+    ctx.save_for_backward(x, packed, absmax, lora_a, lora_b, t_save, bt_save, tt_save, codes_t, absmax_t)
 
 
-def _op_backward(ctx, dy, _dt_save, _dbt_save):
+def _op_backward(ctx, dy, _dt_save, _dbt_save, _dtt_save):
     scale, N, K, blocksize, qdtype = ctx.meta
-    x, packed, absmax, lora_a, lora_b, t_save, bt_save, codes_t, absmax_t = ctx.saved_tensors
+    x, packed, absmax, lora_a, lora_b, t_save, bt_save, tt_save, codes_t, absmax_t = ctx.saved_tensors
     need_dx = ctx.needs_input_grad[0]
     need_ab = lora_a is not None and (ctx.needs_input_grad[4] or ctx.needs_input_grad[5])
-    dx, da, db = _qlora_bwd_op(dy, x, packed, absmax, lora_a, lora_b, t_save, bt_save, scale, N, K, blocksize, qdtype,
+    dx, da, db = _qlora_bwd_op(dy, x, packed, absmax, lora_a, lora_b, t_save, bt_save, tt_save, scale, N, K, blocksize, qdtype,
                                codes_t, absmax_t, need_dx, need_ab)
     return (dx if need_dx else None, None, None, None, da if need_ab else None, db if need_ab else None,
             None, None, None, None, None, None, None)
@@ -420,7 +448,7 @@ def qlora_linear(x, packed, absmax, bias, lora_a, lora_b, scale, out_features, i
     """``tiled``: optional (codes_t, absmax_t) from :func:`nf4_tile_weight` for the same weight."""
     if torch.compiler.is_compiling():  # traced by torch.compile: the registered operator (no graph break)
         codes_t, absmax_t = tiled if tiled is not None else (None, None)
-        y, _, _ = _qlora_fwd_op(x, packed, absmax, bias, lora_a, lora_b, float(scale), int(out_features), int(in_features),
+        y, _, _, _ = _qlora_fwd_op(x, packed, absmax, bias, lora_a, lora_b, float(scale), int(out_features), int(in_features),
                              int(blocksize), dtype_code(qdtype), codes_t, absmax_t)
         return y
     return QLoRALinearFunction.apply(x, packed, absmax, bias, lora_a, lora_b, scale, out_features, in_features,
