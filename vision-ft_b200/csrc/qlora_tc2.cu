@@ -388,6 +388,15 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       if (job_on) {
         // ---- dA/dB job: this thread issues the loads of its CTA and (leader) the MMAs, polling both duties.  The
         // ring continues where the side product left it: slot and parity after n_p0 steps.
+        // One slow thread (~900 cycles per step) is the schedule that measured best (config #1 step through the module
+        // API, us): this form 134.3; loads and MMAs on threads of their own, as fast as the data arrives, 145.7 (the
+        // backward's main loop is bound by shared-memory bandwidth: every byte the job's MMAs read while it runs is
+        // taken from it, and a job that runs early competes with the side product and the cold start); the peer CTA's
+        // thread loading for both CTAs through the leader's cluster address 158.8 (that traffic shares the SM-to-SM
+        // path with the operand exchange of the cta_group::2 MMAs); MMAs issued by the main issuer thread while it
+        // waits for the accumulators to drain, the rest behind its last MMA, 143.0 (an MMA costs the issuing thread
+        // ~40 cycles: the job's 256 do not fit into the drain bubbles, and what is left becomes the launch's tail).
+        // A smaller ring (28 KB instead of 40: three slots) costs 5 us: the job must not fall behind.
         ptx::griddep_wait();
         // (the peer CTA's thread has issued nothing so far: the ring is the side product's until its last MMA is done)
         if (rank != 0) ptx::mbar_wait(bar_p0_done, 0);
@@ -1033,12 +1042,12 @@ struct Tc2Config {
 // K = 64), decode ~600 ALU-pipe cycles per 128 x 64 weight tile, shared memory 128 B/clk over the activation
 // boxes (written by TMA, read by the MMA) and -- backward only -- the decoded tile (written once, read once per
 // accumulator).
-// `rp`: padded rank of a side product computed inside the launch (0: none) -- costs its ring (kP0Budget bytes of
+// `rp`: padded rank of a side product computed inside the launch (0: none) -- costs its ring (p0_budget() bytes of
 // shared memory) and the last rp columns of an accumulator pitch.
-constexpr int kP0Budget = 40 * 1024;
+static int p0_budget() { return (env().tc2_p0kb >= 10 && env().tc2_p0kb <= 64 ? env().tc2_p0kb : 40) * 1024; }
 static int max_stages(bool tmem_a, int n_acc, int N_acc, int rp) {
   const int stage_bytes = (tmem_a ? 0 : kATileBytes) + n_acc * (N_acc / 2) * 128;
-  int stages = (kSmemLimit - kBarBytes - kEpiBytes - 1024 - (rp > 0 ? kP0Budget : 0)) / stage_bytes;
+  int stages = (kSmemLimit - kBarBytes - kEpiBytes - 1024 - (rp > 0 ? p0_budget() : 0)) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (tmem_a && stages > kTmemAStages) stages = kTmemAStages;  // the weight ring in tensor memory has 4 slots
   // four stages (one per decode group) keep the tensor pipe fed; shared memory beyond that is worth more as output
@@ -1251,7 +1260,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   p.la_bytes = (p.r_pad / 2) * 128;
   p.p0_rows = rp > 0 ? choice.p0_rows : 8;
   p.p0_slot_bytes = p.p0_rows * 128 + p.la_bytes;
-  p.p0_slots = rp > 0 ? kP0Budget / p.p0_slot_bytes : 0;
+  p.p0_slots = rp > 0 ? p0_budget() / p.p0_slot_bytes : 0;
   if (p.p0_slots > kMaxP0) p.p0_slots = kMaxP0;
   p.p0_per_step = 2;
   p.save = lora_act;
@@ -1264,7 +1273,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   p.job_db = a.job_db;
   if (choice.job && p.p0_slot_bytes < kJobBox + p.la_bytes) {  // the job's boxes ride the side product's ring
     p.p0_slot_bytes = kJobBox + p.la_bytes;
-    p.p0_slots = kP0Budget / p.p0_slot_bytes;
+    p.p0_slots = p0_budget() / p.p0_slot_bytes;
     if (p.p0_slots > kMaxP0) p.p0_slots = kMaxP0;
   }
   p.sync = nullptr;
