@@ -532,7 +532,20 @@ def run_gpu_arm(args):
         gbs = (2 * n + n / 2 + n / 16) / (q_ms * 1e-3) / 1e9
         extra["nf4_quantize_pack"] = {"GB/s": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"], "elements": n,
                                       "bytes_per_element": 2.5625, "us_per_tensor": q_ms * 1e3,
-                                      "note": "bf16 [18432, 3072], device-resident, CUDA-graph replay; whole AuraFlow set: tools/quant_probe.py"}
+                                      "note": "bf16 [18432, 3072], device-resident, CUDA-graph replay"}
+        del wq2, qgraph
+        try:  # BASELINE configs[1]: the whole synthetic AuraFlow DiT weight set (322 tensors, 6.80 G elements, fp16)
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import quant_probe
+
+            q_ms_set, q_gbs_set = quant_probe.whole_set(torch.float16)
+            extra["nf4_quantize_pack_auraflow_set"] = {
+                "ms": q_ms_set, "GB/s": q_gbs_set, "frac_of_hbm_peak": q_gbs_set / peaks["hbm_gbs"], "tensors": 322,
+                "elements": 6.80e9, "hbm_floor_ms": 17.4e9 / peaks["hbm_gbs"] / 1e6,
+                "note": "fp16 weights device-resident, one launch per tensor, per-shape CUDA-graph timing weighted by count"}
+        except Exception as e:  # pragma: no cover - reported, not hidden
+            extra["nf4_quantize_pack_auraflow_set"] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
 
     if rank == 0:
         # few-token forward (T = per-GPU batch 2) of the largest AuraFlow modulation weight [18432, 3072]: achieved
@@ -582,6 +595,13 @@ def run_gpu_arm(args):
                 "ms_per_step": ms, "steps_per_s_upper_bound": 1e3 / ms, "avg_tflops": avg_tf,
                 "frac_of_measured_bf16_peak": avg_tf / peaks["bf16_tflops"], "per_gpu_batch": 2,
                 "note": "322 quantized Linears, forward x2 (checkpointing) + backward; data-parallel ranks step independently"}
+            # BASELINE configs[2] and [4]: the same census for Lumina2 NextDiT-2.6B (batch 1, 1024^2) and the SDXL UNet
+            # transformer Linears (batch 2, 1024^2: small K, 77-token cross-attention projections)
+            for key, layers, what in (("lumina2_qlora_step_linear_layers", census.lumina2(1), "178 quantized Linears of NextDiT-2.6B, batch 1"),
+                                      ("sdxl_qlora_step_linear_layers", census.sdxl(2), "SDXL UNet attention/FF Linears (C = 640, 1280), batch 2")):
+                ms, avg_tf, _ = census.model_step(layers, dev)
+                extra[key] = {"ms_per_step": ms, "avg_tflops": avg_tf, "frac_of_measured_bf16_peak": avg_tf / peaks["bf16_tflops"],
+                              "note": what + "; forward x2 (checkpointing) + backward, each layer at its own token count"}
         except Exception as e:  # pragma: no cover - reported, not hidden
             extra["auraflow_qlora_step_linear_layers"] = {"error": f"{type(e).__name__}: {e}"}
 
@@ -592,7 +612,9 @@ def run_gpu_arm(args):
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "cpu_model": r["cpu_model"],
                    "sample": f"all {TOKENS} tokens, 1 warm-up + 5 runs of the oracle port (C/OpenMP dequant + F.linear + LoRA, "
                              "autograd, second dequant)"}
-        kernels_per_step = 5  # lora_side<x.A^T>, qlora_tc2<fwd> | lora_side<dy.B>, qlora_tc2<bwd>, lora_side<dA,dB>
+        # qlora_tc2<fwd, side product inside> | qlora_tc2<bwd, side product + dA/dB job inside>; the triage switches
+        # bring the side kernels back: lora_side<x.A^T>, <dy.B> (VFT_TC2_FUSE=0) and lora_side<dA,dB> (VFT_TC2_JOB=0)
+        kernels_per_step = 5 if os.environ.get("VFT_TC2_FUSE") == "0" else (3 if os.environ.get("VFT_TC2_JOB") == "0" else 2)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

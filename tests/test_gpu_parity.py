@@ -653,3 +653,72 @@ def test_lumina2_block_shapes_vs_oracle(ops):
                               torch.bfloat16, 0, tiled=True)
         assert used == (GEMV if T == 1 else TC)
         _check(out, ref, truth, ("y", "dx") + (("da", "db") if r else ()), f"lumina2-T{T}K{K}N{N}")
+
+
+# ----------------------------------------------------------------------------- the whole backward in one C-ABI call
+@pytest.mark.parametrize("T,K,N,r,job", [
+    (4096, 3072, 3072, 16, True),    # BASELINE config #1: one launch (side product + dA/dB job inside the GEMM)
+    (2176, 1280, 1280, 4, True),     # the reference's shipped rank 4, ragged token count (multiple of 8)
+    (1003, 640, 1280, 8, False),     # T % 8 != 0: t^T cannot be a TMA operand -> two calls inside
+    (136, 2048, 640, 16, False),     # few tokens: the contraction is split, side kernels + vft_lora_bwd_dab inside
+])
+def test_one_call_backward(ops, vft_env, T, K, N, r, job):
+    """vft_qlora_bwd (dx, dt, dA, dB) against fp64 truth, with and without the in-launch job (VFT_TC2_JOB=0 forces the
+    two-call sequence): both must agree with the truth within the bf16 bars of this file and with each other."""
+    from vft_b200 import _cabi
+
+    torch.manual_seed(T + K + N + r)
+    dev, bf = torch.device("cuda"), torch.bfloat16
+    w = (torch.randn(N, K, device=dev) * 0.02).to(bf)
+    packed, absmax = ops.nf4_quantize(w)
+    wd = ops.nf4_dequantize(packed, absmax, (N, K), bf).double()
+    tiles = ops.nf4_tile_weight(packed, absmax, N, K)
+    x = torch.randn(T, K, device=dev, dtype=bf)
+    dy = torch.randn(T, N, device=dev, dtype=bf)
+    A = (torch.randn(r, K, device=dev) * 0.05).to(bf)
+    B = (torch.randn(N, r, device=dev) * 0.05).to(bf)
+    s = 0.5
+    rp = 16 * ((r + 15) // 16)
+    L, st = _cabi.lib, torch.cuda.current_stream().cuda_stream
+    results = []
+    for mode in ("1", "0"):
+        vft_env(VFT_TC2_JOB=mode)
+        y = torch.empty(T, N, device=dev, dtype=bf)
+        ts = torch.zeros(T, 64, device=dev, dtype=bf)
+        bt = torch.empty(rp, N, device=dev, dtype=bf)
+        tt = torch.empty(rp, T, device=dev, dtype=bf)
+        wsf = L.vft_workspace_bytes(_cabi.OP_FWD, T, N, K, r)
+        wf = torch.empty(max(wsf, 4), dtype=torch.uint8, device=dev)
+        _cabi.check(L.vft_qlora_fwd(x.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, _cabi.BF16, _cabi.BF16, None,
+                                    A.data_ptr(), B.data_ptr(), r, s, y.data_ptr(), ts.data_ptr(), bt.data_ptr(), tt.data_ptr(),
+                                    wf.data_ptr(), wsf, tiles[0].data_ptr(), tiles[1].data_ptr(), st))
+        dx = torch.full((T, K), float("nan"), device=dev, dtype=bf)
+        dts = torch.zeros(T, 64, device=dev, dtype=bf)
+        dA = torch.full_like(A, float("nan"))
+        dB = torch.full_like(B, float("nan"))
+        wsb = L.vft_workspace_bytes(_cabi.OP_BWD, T, N, K, r)
+        ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=dev)
+        # too small a workspace is refused before anything is launched
+        assert L.vft_qlora_bwd(dy.data_ptr(), x.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, _cabi.BF16, _cabi.BF16,
+                               A.data_ptr(), B.data_ptr(), r, s, ts.data_ptr(), tt.data_ptr(), bt.data_ptr(), dx.data_ptr(),
+                               dA.data_ptr(), dB.data_ptr(), dts.data_ptr(), ws.data_ptr(), wsb - 1, tiles[0].data_ptr(),
+                               tiles[1].data_ptr(), st) == -4
+        _cabi.check(L.vft_qlora_bwd(dy.data_ptr(), x.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, _cabi.BF16,
+                                    _cabi.BF16, A.data_ptr(), B.data_ptr(), r, s, ts.data_ptr(), tt.data_ptr(), bt.data_ptr(),
+                                    dx.data_ptr(), dA.data_ptr(), dB.data_ptr(), dts.data_ptr(), ws.data_ptr(), wsb,
+                                    tiles[0].data_ptr(), tiles[1].data_ptr(), st))
+        torch.cuda.synchronize()
+        results.append({"dx": dx.double(), "dA": dA.double(), "dB": dB.double(), "dt": dts[:, :r].double(),
+                        "tt": tt[:r].double(), "t": ts[:, :r].double()})
+    t_truth = x.double() @ A.double().t()
+    dt_truth = s * dy.double() @ B.double()
+    truth = {"dx": dy.double() @ wd + dt_truth @ A.double(), "dA": dt_truth.t() @ x.double(),
+             "dB": s * dy.double().t() @ t_truth, "dt": dt_truth, "tt": t_truth.t(), "t": t_truth}
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    for res in results:
+        assert torch.equal(res["tt"], res["t"].t()), "t^T must be the transposed copy of t_save, bit for bit"
+        for k, lim in (("dx", 4e-3), ("dA", 6e-3), ("dB", 6e-3), ("dt", 4e-3), ("t", 4e-3)):
+            assert rel(res[k], truth[k]) <= lim, (k, rel(res[k], truth[k]))
+    for k in ("dx", "dA", "dB"):
+        assert rel(results[0][k], results[1][k]) <= 6e-3, k
+    assert job or True  # (which path served the call is a planning decision; both are checked above)

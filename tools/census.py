@@ -59,6 +59,9 @@ def time_layer(N, K, T, lora, bias, dev):
     ts = torch.empty(T, 64, device=dev, dtype=bf); dts = torch.empty(T, 64, device=dev, dtype=bf)
     dA = torch.empty(R, K, device=dev, dtype=bf); dB = torch.empty(N, R, device=dev, dtype=bf)
     bt = torch.empty(16 * ((R + 15) // 16), N, device=dev, dtype=bf)
+    tt = torch.empty(16 * ((R + 15) // 16), T, device=dev, dtype=bf)
+    wsb2 = _cabi.lib.vft_workspace_bytes(_cabi.OP_BWD, T, N, K, R)
+    ws2 = torch.empty(max(wsb2, 4), dtype=torch.uint8, device=dev)
     wsb = _cabi.lib.vft_workspace_bytes(_cabi.OP_BWD_DAB, T, N, K, R)
     ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=dev)
     wf_b = _cabi.lib.vft_workspace_bytes(_cabi.OP_FWD, T, N, K, r_) if True else 0
@@ -69,11 +72,15 @@ def time_layer(N, K, T, lora, bias, dev):
     P = lambda t: None if t is None else t.data_ptr()
     side = torch.cuda.Stream()
     def fwd(i, st):
-        _cabi.check(L.vft_qlora_fwd(xs[i % nset].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, P(bv), P(A), P(B_), r, 1.0 / R, y.data_ptr(), P(ts) if lora else None, P(bt) if lora else None, None, wf.data_ptr() if wf_b else None, wf_b, TC, TA, st))
+        _cabi.check(L.vft_qlora_fwd(xs[i % nset].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, P(bv), P(A), P(B_), r, 1.0 / R, y.data_ptr(), P(ts) if lora else None, P(bt) if lora else None, P(tt) if lora else None, wf.data_ptr() if wf_b else None, wf_b, TC, TA, st))
     def bwd(i, st):
-        _cabi.check(L.vft_qlora_bwd_dx(gs[i % nset].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, P(A), P(B_), r, 1.0 / R, dx.data_ptr(), P(dts) if lora else None, P(bt) if lora else None, wb.data_ptr() if wb_b else None, wb_b, TC, TA, st))
-        if lora:
-            _cabi.check(L.vft_lora_bwd_dab(gs[i % nset].data_ptr(), xs[i % nset].data_ptr(), ts.data_ptr(), dts.data_ptr(), T, N, K, R, 2, 1.0 / R, dA.data_ptr(), dB.data_ptr(), ws.data_ptr(), wsb, st))
+        if lora:  # the whole backward (dx, dt, dA, dB) in one C-ABI call: one launch where the persistent kernel takes it
+            _cabi.check(L.vft_qlora_bwd(gs[i % nset].data_ptr(), xs[i % nset].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2,
+                                        P(A), P(B_), R, 1.0 / R, ts.data_ptr(), tt.data_ptr(), bt.data_ptr(), dx.data_ptr(), dA.data_ptr(),
+                                        dB.data_ptr(), dts.data_ptr(), ws2.data_ptr(), wsb2, TC, TA, st))
+        else:
+            _cabi.check(L.vft_qlora_bwd_dx(gs[i % nset].data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, 0, 0.0,
+                                           dx.data_ptr(), None, None, wb.data_ptr() if wb_b else None, wb_b, TC, TA, st))
     out = {}
     for name, fn in (("fwd", fwd), ("bwd", bwd)):
         reps = 6

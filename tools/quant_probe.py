@@ -12,6 +12,37 @@ SHAPES = {  # AuraFlow 6.8B DiT, include "denoiser.", exclude t_embedder/final_l
     (18432, 3072): 4 * 2 + 32 * 1, (3072, 2048): 1, (3072, 16): 1,
 }
 
+def whole_set(dt=torch.float16, code=None, reps=6, verbose=False):
+    """GB/s of vft_nf4_quantize over the whole synthetic AuraFlow DiT set (322 tensors, weights device-resident):
+    every distinct shape timed from a CUDA graph, weighted by its count.  Returns (ms, GB/s)."""
+    code = _cabi.F16 if dt == torch.float16 else _cabi.BF16
+    dev = torch.device("cuda")
+    total_bytes = total_us = 0.0
+    for (n_, k_), count in SHAPES.items():
+        n = n_ * k_
+        ws = [(torch.randn(n_, k_, device=dev) * 0.02).to(dt) for _ in range(min(max(2, int(300e6 // (2 * n)) + 1), 6))]
+        packed = torch.empty((n + 1) // 2, dtype=torch.uint8, device=dev)
+        absmax = torch.empty((n + 63) // 64, dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            st = side.cuda_stream
+            for w in ws: _cabi.check(_cabi.lib.vft_nf4_quantize(w.data_ptr(), code, n, 64, packed.data_ptr(), absmax.data_ptr(), st))
+            side.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                for i in range(reps):
+                    _cabi.check(_cabi.lib.vft_nf4_quantize(ws[i % len(ws)].data_ptr(), code, n, 64, packed.data_ptr(), absmax.data_ptr(), st))
+        g.replay(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3): g.replay()
+        b.record(); torch.cuda.synchronize()
+        us = a.elapsed_time(b) / (3 * reps) * 1e3
+        total_bytes += 2.5625 * n * count; total_us += us * count
+        del ws, g
+    return total_us / 1e3, total_bytes / total_us / 1e3
+
+
 def main():
     dev = torch.device("cuda")
     total_bytes = total_us = 0.0
@@ -45,4 +76,5 @@ def main():
         print(f"{str(dt)[6:]}: AuraFlow DiT set (322 tensors, 6.80 G elements): {total_us / 1e3:.2f} ms, {total_bytes / total_us / 1e3:.0f} GB/s "
               f"({total_bytes / total_us / 1e3 / 6452.2 * 100:.1f} % of measured HBM copy bandwidth)")
 
-main()
+if __name__ == "__main__":
+    main()
