@@ -25,6 +25,7 @@ from safetensors.torch import save_file
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
 sys.path.insert(0, ROOT)
 
 from oracle import nf4_oracle  # noqa: E402
@@ -147,7 +148,27 @@ def lora_vectors() -> dict:
     return out
 
 
+def auraflow_keys() -> list:
+    """Outputs of the reference's own three rename functions (/root/reference/src/models/auraflow/pipeline.py:35-54),
+    exec'd from the source text so that the model's heavy imports are not needed."""
+    src = open(os.path.join(REF, "src/models/auraflow/pipeline.py")).read()
+    ns = {"DENOISER_TENSOR_PREFIX": "model.", "VAE_TENSOR_PREFIX": "vae.",
+          "TEXT_ENCODER_TENSOR_PREFIX": "text_encoders.pile_t5xl.transformer."}  # denoiser.py:32, vae.py:36, text_encoder.py:50
+    exec(src[src.index("def convert_to_original_key"):src.index("class AuraFlowModel")], ns)
+    keys = ["denoiser.double_layers.0.attn.w1q.lora_down.weight", "denoiser.single_layers.31.mlp.c_fc1.lora_up.weight",
+            "denoiser.single_layers.3.modCX.1.lora_up.bias", "vae.decoder.conv_in.weight", "text_encoder.model.shared.weight",
+            "denoiser.cond_seq_linear.weight", "text_encoder.model.encoder.block.0.layer.0.SelfAttention.q.weight"]
+    rows = []
+    for k in keys:
+        o, c = ns["convert_to_original_key"](k), ns["convert_to_comfy_key"](k)
+        rows.append({"key": k, "original": o, "comfy": c, "from_original": ns["convert_from_original_key"](o),
+                     "from_comfy": ns["convert_from_original_key"](c)})
+    return rows
+
+
 if __name__ == "__main__":
+    with open(os.path.join(HERE, "auraflow_keys.json"), "w") as f:
+        json.dump(auraflow_keys(), f, indent=1)
     save_file({k: v.contiguous() for k, v in nf4_vectors().items()}, os.path.join(HERE, "nf4_vectors.safetensors"))
     with open(os.path.join(HERE, "nf4_hashes.json"), "w") as f:
         json.dump(nf4_hashes(), f, indent=1)
