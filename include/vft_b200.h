@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VFT_ABI_VERSION 6
+#define VFT_ABI_VERSION 7
 #define VFT_LORA_LD 64 /* leading dimension (elements) of the saved LoRA activations t_save / dt_save */
 
 enum vft_dtype { VFT_F32 = 0, VFT_F16 = 1, VFT_BF16 = 2 };
@@ -79,6 +79,14 @@ int vft_debug_side_timeline(unsigned long long* out, int n);
  * Bit-exact contract: absmax = max|float(w)| per block; code = number of NF4
  * thresholds strictly below float(w) * (1.0f/absmax) (IEEE fp32). */
 int vft_nf4_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t* packed, float* absmax, void* stream);
+
+/* The same for a batch of tensors of one dtype in as few launches as possible (the tables are HOST arrays of `count`
+ * device pointers / element counts; 96 tensors ride one launch).  This is the loop of quantize_state_dict()
+ * (/root/reference/src/modules/quant/functional.py:342-371) and of tools/quantize_model.py:33-54 over a checkpoint:
+ * per-tensor launches leave an HBM-bound kernel waiting on launch latency for the small weights.  Results are
+ * bit-identical to `count` calls of vft_nf4_quantize. */
+int vft_nf4_quantize_many(int count, const void* const* w, int dtype, const int64_t* n, int blocksize,
+                          uint8_t* const* packed, float* const* absmax, void* stream);
 
 /* NF4 dequantize (debug / checker entry; the fused kernels never materialise W).
  * Replaces bitsandbytes.functional.dequantize_4bit.  out[n] in `dtype`. */

@@ -35,7 +35,7 @@ def test_header_symbols_are_exported(cabi):
 
 
 def test_abi_version(cabi):
-    assert cabi.lib.vft_abi_version() == cabi.ABI_VERSION == 6
+    assert cabi.lib.vft_abi_version() == cabi.ABI_VERSION == 7
 
 
 def test_argument_validation_needs_no_gpu(cabi):

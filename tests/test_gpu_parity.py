@@ -722,3 +722,60 @@ def test_one_call_backward(ops, vft_env, T, K, N, r, job):
     for k in ("dx", "dA", "dB"):
         assert rel(results[0][k], results[1][k]) <= 6e-3, k
     assert job or True  # (which path served the call is a planning decision; both are checked above)
+
+
+# ----------------------------------------------------------------------------- split contraction: one launch, reproducible
+@pytest.mark.parametrize("T,K,N,r,bias", [
+    (2, 3072, 18432, 0, True),      # AuraFlow modulation layer, T = batch (backward of the few-token path)
+    (154, 2048, 1280, 8, False),    # SDXL attn2.to_k/v on 2 x 77 text tokens, with an adapter
+    (264, 3072, 3072, 0, False),    # AuraFlow condition tokens
+    (528, 3072, 3072, 16, True),    # two ragged token tiles, bias added in the reduction
+    (1000, 1280, 1280, 4, False),   # T % 16 != 0, shipped rank 4
+])
+def test_split_contraction_is_reproducible_and_matches_unsplit(ops, vft_env, T, K, N, r, bias):
+    """Small problems divide the contraction of every tile over several work items (csrc/qlora_tc2.cu: per-item fp32
+    slices, summed in split order inside the same launch).  Twice the same call -> bit-identical y and dx (no atomics);
+    against the unsplit schedule (VFT_TC2_NOSPLIT=1) and the fp64 truth within the bf16 bars of this file."""
+    w, x, dy, a, b, bv = _make_case(T, K, N, r, seed=T + r, bias=bias)
+    packed, absmax = ops.nf4_quantize(w.cuda())
+    wd = ops.nf4_dequantize(packed, absmax, (N, K), torch.bfloat16).double().cpu()
+    runs = []
+    for mode in (None, None, "1"):
+        vft_env(VFT_TC2_NOSPLIT=mode)
+        out, used = _run_cuda(ops, packed, absmax, x, dy, a, b, bv, 1.0, N, K, torch.bfloat16, TC, tiled=True)
+        assert used == TC
+        runs.append(out)
+    for k in ("y", "dx"):
+        assert torch.equal(runs[0][k], runs[1][k]), f"{k}: two identical calls differ"
+    xd, dyd = x.double(), dy.double()
+    s = 1.0 / r if r else 0.0
+    y_t = xd @ wd.t() + (bv.double() if bias else 0.0)
+    dx_t = dyd @ wd
+    if r:
+        y_t = y_t + s * (xd @ a.double().t()) @ b.double().t()
+        dx_t = dx_t + s * (dyd @ b.double()) @ a.double()
+    for out in (runs[0], runs[2]):
+        assert qlora_oracle.rel_l2(out["y"], y_t) <= 4e-3
+        assert qlora_oracle.rel_l2(out["dx"], dx_t) <= 4e-3
+    assert qlora_oracle.rel_l2(runs[0]["y"], runs[2]["y"].double()) <= 4e-3
+
+
+# ----------------------------------------------------------------------------- a checkpoint's worth of tensors per launch
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16, torch.float32])
+def test_quantize_many_is_bit_identical_to_per_tensor_calls(ops, dt):
+    """vft_nf4_quantize_many: 96 tensors per launch, chunk index space across tensors; ragged / tiny / empty tensors take
+    the generic tail.  Codes and absmax must equal the per-tensor entry bit for bit (and through it the oracle)."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    shapes = [(3072, 16), (64, 64), (1, 1), (0,), (1000, 3), (256, 1024), (2048, 640), (33, 64)] + [(128, 8 * (i % 5 + 1)) for i in range(100)]
+    ws = [(torch.randn(*s, generator=g, device="cuda") * 0.02).to(dt) if len(s) > 1 or s[0] else torch.empty(0, device="cuda", dtype=dt)
+          for s in shapes]
+    ws[5][:64].zero_()  # all-zero blocks
+    many = ops.nf4_quantize_many(ws)
+    assert len(many) == len(ws)
+    for w, (p, a) in zip(ws, many):
+        p1, a1 = ops.nf4_quantize(w)
+        assert torch.equal(p, p1) and torch.equal(a, a1), tuple(w.shape)
+    # and against the oracle for a few
+    for i in (0, 4, 6):
+        po, ao = nf4_oracle.nf4_quantize(ws[i].cpu())
+        assert np.array_equal(many[i][0].cpu().numpy().reshape(-1), po.reshape(-1)) and np.array_equal(many[i][1].cpu().numpy(), ao)

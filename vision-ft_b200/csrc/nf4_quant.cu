@@ -112,10 +112,23 @@ constexpr int kChunkElems = kWarpElems * kQuantUnroll;  // 1024
 // lane ([cell][lane], 8 bytes each: conflict-free), and the cell index sits at bits [8, 14) of the FFMA result.
 constexpr int kTabBytes = kCells * 32 * 8;  // 16 KB
 
+// One launch quantizes a BATCH of tensors (vft_nf4_quantize_many: a checkpoint is hundreds of weights, and a launch per
+// tensor costs ~2 us of an HBM-bound kernel that needs 4-30 us for one -- the 322-tensor AuraFlow set ran at 57 % of
+// HBM bandwidth against 73 % for its largest tensor).  The chunks (1024 elements) of all tensors form one index space;
+// a warp walks it with the grid stride and steps through the table as it crosses tensor boundaries.  The table rides in
+// the kernel parameters (constant bank: no workspace, capturable), kQuantBatch tensors per launch.
+constexpr int kQuantBatch = 96;
+struct QuantBatch {
+  const void* w[kQuantBatch];
+  uint32_t* packed[kQuantBatch];
+  float* absmax[kQuantBatch];
+  int64_t chunk_end[kQuantBatch];  // exclusive prefix ends in the batch's chunk index space
+  int n;
+};
+
 template <typename T>
 __global__ void __launch_bounds__(kQuantThreads)
-nf4_quantize64_kernel(const T* __restrict__ w, int64_t n_chunks, uint32_t* __restrict__ packed_words,
-                      float* __restrict__ absmax, const CellTable table) {
+nf4_quantize64_kernel(const __grid_constant__ QuantBatch batch, const __grid_constant__ CellTable table) {
   extern __shared__ uint8_t q_smem[];
   const uint32_t raw = static_cast<uint32_t>(__cvta_generic_to_shared(q_smem));
   const uint32_t tab_base = (raw + (uint32_t)kTabBytes - 1u) & ~((uint32_t)kTabBytes - 1u);
@@ -130,19 +143,33 @@ nf4_quantize64_kernel(const T* __restrict__ w, int64_t n_chunks, uint32_t* __res
   const int64_t warp_global = (int64_t)blockIdx.x * (kQuantThreads / 32) + (threadIdx.x >> 5);
   const int64_t warp_stride = (int64_t)gridDim.x * (kQuantThreads / 32);
 
+  const int64_t n_chunks = batch.chunk_end[batch.n - 1];
+  // tensor of a chunk: the table index only moves forward along a warp's walk
+  int t_cur = 0, t_nxt = 0;
+  auto locate = [&](int64_t chunk, int& t) -> int64_t {  // -> first element of the chunk inside its tensor
+    while (chunk >= batch.chunk_end[t]) ++t;
+    return (chunk - (t > 0 ? batch.chunk_end[t - 1] : 0)) * kChunkElems + lane * 8;
+  };
+
   // register double buffering: the loads of the warp's NEXT chunk are in flight while this one is encoded
   Vec8<T> v[kQuantUnroll], nxt[kQuantUnroll];
+  int64_t base = 0, base_nxt = 0;
   if (warp_global < n_chunks) {
+    base = locate(warp_global, t_cur);
+    t_nxt = t_cur;
+    const T* w = static_cast<const T*>(batch.w[t_cur]);
 #pragma unroll
-    for (int u = 0; u < kQuantUnroll; ++u) v[u].load(w + warp_global * kChunkElems + lane * 8 + u * kWarpElems);
+    for (int u = 0; u < kQuantUnroll; ++u) v[u].load(w + base + u * kWarpElems);
   }
   for (int64_t chunk = warp_global; chunk < n_chunks; chunk += warp_stride) {
-    const int64_t base = chunk * kChunkElems + lane * 8;
     if (chunk + warp_stride < n_chunks) {
+      base_nxt = locate(chunk + warp_stride, t_nxt);
+      const T* w = static_cast<const T*>(batch.w[t_nxt]);
 #pragma unroll
-      for (int u = 0; u < kQuantUnroll; ++u)
-        nxt[u].load(w + (chunk + warp_stride) * kChunkElems + lane * 8 + u * kWarpElems);
+      for (int u = 0; u < kQuantUnroll; ++u) nxt[u].load(w + base_nxt + u * kWarpElems);
     }
+    uint32_t* packed_words = batch.packed[t_cur];
+    float* absmax = batch.absmax[t_cur];
 #pragma unroll
     for (int u = 0; u < kQuantUnroll; ++u) {
       float f[8];
@@ -176,6 +203,8 @@ nf4_quantize64_kernel(const T* __restrict__ w, int64_t n_chunks, uint32_t* __res
     }
 #pragma unroll
     for (int u = 0; u < kQuantUnroll; ++u) v[u] = nxt[u];
+    t_cur = t_nxt;
+    base = base_nxt;
   }
 }
 
@@ -210,42 +239,92 @@ __global__ void nf4_quantize_generic_kernel(const T* __restrict__ w, int64_t sta
 }
 
 template <typename T>
-static int quantize_typed(const T* w, int64_t n, int blocksize, uint8_t* packed, float* absmax, cudaStream_t st) {
-  int64_t n_main = 0;
-  const bool aligned = (reinterpret_cast<uintptr_t>(w) % 16 == 0) && (reinterpret_cast<uintptr_t>(packed) % 4 == 0);
-  if (blocksize == 64 && aligned) n_main = (n / kChunkElems) * kChunkElems;
-  if (n_main > 0) {
-    static const CellTable table = make_cell_table();
-    const int64_t n_chunks = n_main / kChunkElems;
-    const int warps_per_block = kQuantThreads / 32;
-    int64_t blocks = ceil_div64(n_chunks, warps_per_block);
-    const int64_t max_blocks = 148 * 6;  // 6 resident CTAs of 256 threads per SM (32 KB of shared memory each)
-    if (blocks > max_blocks) blocks = max_blocks;
-    nf4_quantize64_kernel<T><<<(unsigned)blocks, kQuantThreads, 2 * kTabBytes, st>>>(
-        w, n_chunks, reinterpret_cast<uint32_t*>(packed), absmax, table);
-    VFT_CUDA_OK(cudaGetLastError());
-  }
-  if (n_main < n) {
-    const int64_t rest_blocks = ceil_div64(n - n_main, blocksize);
-    const int warps = 4;
-    nf4_quantize_generic_kernel<T><<<(unsigned)ceil_div64(rest_blocks, warps), warps * 32, 0, st>>>(
-        w, n_main, n, blocksize, packed, absmax);
-    VFT_CUDA_OK(cudaGetLastError());
-  }
+static int launch_quant_batch(const QuantBatch& b, cudaStream_t st) {
+  static const CellTable table = make_cell_table();
+  const int64_t n_chunks = b.chunk_end[b.n - 1];
+  const int warps_per_block = kQuantThreads / 32;
+  int64_t blocks = ceil_div64(n_chunks, warps_per_block);
+  const int64_t max_blocks = 148 * 6;  // 6 resident CTAs of 256 threads per SM (32 KB of shared memory each)
+  if (blocks > max_blocks) blocks = max_blocks;
+  nf4_quantize64_kernel<T><<<(unsigned)blocks, kQuantThreads, 2 * kTabBytes, st>>>(b, table);
+  VFT_CUDA_OK(cudaGetLastError());
   return VFT_OK;
+}
+
+// tail of a tensor the fast path cannot take (blocksize != 64, n % 1024, misaligned pointers): one warp per block
+template <typename T>
+static int quantize_rest(const T* w, int64_t n_main, int64_t n, int blocksize, uint8_t* packed, float* absmax,
+                         cudaStream_t st) {
+  if (n_main >= n) return VFT_OK;
+  const int64_t rest_blocks = ceil_div64(n - n_main, blocksize);
+  const int warps = 4;
+  nf4_quantize_generic_kernel<T><<<(unsigned)ceil_div64(rest_blocks, warps), warps * 32, 0, st>>>(
+      w, n_main, n, blocksize, packed, absmax);
+  VFT_CUDA_OK(cudaGetLastError());
+  return VFT_OK;
+}
+
+static int64_t fast_elems(const void* w, int64_t n, int blocksize, const uint8_t* packed) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(w) % 16 == 0) && (reinterpret_cast<uintptr_t>(packed) % 4 == 0);
+  return (blocksize == 64 && aligned) ? (n / kChunkElems) * kChunkElems : 0;
+}
+
+template <typename T>
+static int quantize_many_typed(int count, const void* const* ws, const int64_t* ns, int blocksize, uint8_t* const* packed,
+                               float* const* absmax, cudaStream_t st) {
+  QuantBatch b;
+  b.n = 0;
+  int64_t chunks = 0;
+  auto flush = [&]() -> int {
+    if (b.n == 0) return VFT_OK;
+    const int rc = launch_quant_batch<T>(b, st);
+    b.n = 0;
+    chunks = 0;
+    return rc;
+  };
+  for (int i = 0; i < count; ++i) {
+    if (ns[i] == 0) continue;
+    const int64_t n_main = fast_elems(ws[i], ns[i], blocksize, packed[i]);
+    if (n_main > 0) {
+      chunks += n_main / kChunkElems;
+      b.w[b.n] = ws[i];
+      b.packed[b.n] = reinterpret_cast<uint32_t*>(packed[i]);
+      b.absmax[b.n] = absmax[i];
+      b.chunk_end[b.n] = chunks;
+      if (++b.n == kQuantBatch) {
+        const int rc = flush();
+        if (rc != VFT_OK) return rc;
+      }
+    }
+    const int rc = quantize_rest(static_cast<const T*>(ws[i]), n_main, ns[i], blocksize, packed[i], absmax[i], st);
+    if (rc != VFT_OK) return rc;
+  }
+  return flush();
+}
+
+int launch_quantize_many(int count, const void* const* w, int dtype, const int64_t* n, int blocksize,
+                         uint8_t* const* packed, float* const* absmax, cudaStream_t st) {
+  VFT_REQUIRE(blocksize >= 2 && blocksize % 2 == 0 && blocksize <= 4096, "blocksize %d must be even and in [2, 4096]",
+              blocksize);
+  VFT_REQUIRE(count >= 0 && (count == 0 || (w && n && packed && absmax)), "null table");
+  for (int i = 0; i < count; ++i)
+    VFT_REQUIRE(n[i] >= 0 && (n[i] == 0 || (w[i] && packed[i] && absmax[i])), "tensor %d: null pointer or negative size", i);
+  switch (dtype) {
+    case VFT_F32: return quantize_many_typed<float>(count, w, n, blocksize, packed, absmax, st);
+    case VFT_F16: return quantize_many_typed<__half>(count, w, n, blocksize, packed, absmax, st);
+    case VFT_BF16: return quantize_many_typed<__nv_bfloat16>(count, w, n, blocksize, packed, absmax, st);
+    default: set_error("unknown dtype %d", dtype); return VFT_ERR_INVALID;
+  }
 }
 
 int launch_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t* packed, float* absmax,
                     cudaStream_t st) {
-  VFT_REQUIRE(blocksize >= 2 && blocksize % 2 == 0 && blocksize <= 4096, "blocksize %d must be even and in [2, 4096]",
-              blocksize);
-  if (n == 0) return VFT_OK;
-  switch (dtype) {
-    case VFT_F32: return quantize_typed(static_cast<const float*>(w), n, blocksize, packed, absmax, st);
-    case VFT_F16: return quantize_typed(static_cast<const __half*>(w), n, blocksize, packed, absmax, st);
-    case VFT_BF16: return quantize_typed(static_cast<const __nv_bfloat16*>(w), n, blocksize, packed, absmax, st);
-    default: set_error("unknown dtype %d", dtype); return VFT_ERR_INVALID;
+  if (n == 0) {
+    VFT_REQUIRE(blocksize >= 2 && blocksize % 2 == 0 && blocksize <= 4096, "blocksize %d must be even and in [2, 4096]",
+                blocksize);
+    return VFT_OK;
   }
+  return launch_quantize_many(1, &w, dtype, &n, blocksize, &packed, &absmax, st);
 }
 
 // ---------------------------------------------------------------------------

@@ -99,9 +99,12 @@ struct Tc2Params {
   int stage_bytes;  // (backward: kATileBytes +) n_acc * b_bytes
   int n_fblk;       // feature blocks of 256
   int n_tiles;      // n_fblk * token blocks
-  // split-K (small problems: fewer tiles than SM pairs): a work item is (tile, split); split i reduces ring steps
-  // [i * k_per, (i + 1) * k_per) of the contraction (the adapter step belongs to the last split) and ADDS its fp32
-  // partial tile into `partial` [T, OUT] (zeroed by the host; converted by qlora_tc2_finalize_kernel afterwards)
+  // split-K (small problems: fewer tiles than SM pairs; all work items resident at once): a work item is
+  // (tile, split); split i reduces ring steps [i * k_per, (i + 1) * k_per) of the contraction (the adapter step belongs
+  // to the last split), writes its fp32 partial tile to ITS slice of `partial` [item][token of the tile][256 features],
+  // counts itself in on the tile's {arrivals, generation} pair (`sync` + 2 * tile) and, once all n_split items of the
+  // tile are there, sums every n_split-th token row over the slices IN SPLIT ORDER, adds the bias, converts and writes
+  // the output rows.  One launch, no memset, no atomics on data: the sums are reproducible run to run.
   int n_split, k_per;
   float* partial;
   int debug;        // VFT_TC_DEBUG triage mask (results are garbage when non-zero): 1 = no decode stores,
@@ -729,38 +732,76 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       ptx::tc_fence_after();
       if (et == 0) tl_mark(p, 4, 4 * (int)it + 2);
       if (p.n_split > 1) {
-        // split-K: the fp32 partial tile is ADDED to the workspace (few-token problems only)
+        // split-K: this item's fp32 partial tile goes to its own slice of the workspace, rows = tokens of the tile,
+        // 256 features per row (a warp's 32 lanes = 32 consecutive features: 128-byte stores)
+        const int sp = item % p.n_split;
+        unsigned* tile_sync = p.sync + 2 * tile;
+        unsigned gen0 = 0;  // (this CTA has not arrived yet, so the generation cannot have moved on)
+        if (lane == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen0) : "l"(tile_sync + 1) : "memory");
+        float* slice = p.partial + (int64_t)item * tok_tile * (2 * kBM) + (int)rank * kBM + quad * 32 + lane;
         for (int a = 0; a < na; ++a) {
           const int64_t ta = t0 + (int64_t)a * p.N_acc;
 #pragma unroll 1
-          for (int c0 = 0; c0 < p.N_acc; c0 += 32) {
+          for (int c0 = 0; c0 < p.N_acc; c0 += 16) {  // (N_acc is a multiple of 16)
             const bool live = ta + c0 < p.T;  // warp-uniform; dead chunks still release the accumulator below
-            // 16x256b: mma-style fragments -- r[4q], r[4q+1] = (lane t/4, tokens 8q + 2(t%4), +1); r[4q+2], r[4q+3] = lane + 8
-            uint32_t v0[16], v1[16];  // lanes 0..15 / 16..31 of the quadrant, 32 token columns
+            uint32_t v0[16];  // lane = feature, registers = 16 consecutive token columns
             if (live) {
-              ptx::tmem_ld_16x256b_x4(lane_base + (uint32_t)(a * kAccCols + c0), v0);
-              ptx::tmem_ld_16x256b_x4(lane_base + (16u << 16) + (uint32_t)(a * kAccCols + c0), v1);
+              ptx::tmem_ld_32x32b_x16(lane_base + (uint32_t)(a * kAccCols + c0), v0);
               ptx::tmem_ld_wait();
             }
-            if (c0 + 32 >= p.N_acc) {  // accumulator a is in registers / not needed: the issuer may overwrite it
+            if (c0 + 16 >= p.N_acc) {  // accumulator a is in registers / not needed: the issuer may overwrite it
               ptx::tc_fence_before();
               __syncwarp();
               if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar_acc_empty(a), 0));
             }
             if (!live || (p.debug & 4)) continue;
+            float* row = slice + (int64_t)(a * p.N_acc + c0) * (2 * kBM);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int e = 0; e < 16; ++e)
+              if (ta + c0 + e < p.T) __stcg(row + e * (2 * kBM), __uint_as_float(v0[e]));
+          }
+        }
+        // count this warp in (4 warps x 2 CTAs x n_split items per tile); the warp that completes the count resets it
+        // for the next launch that is handed this pair and bumps the generation everybody else is watching
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          const unsigned total = 8u * (unsigned)p.n_split;
+          if (atomicAdd(tile_sync, 1u) == total - 1u) {
+            atomicExch(tile_sync, 0u);
+            __threadfence();
+            atomicAdd(tile_sync + 1, 1u);
+          }
+          const long long t_start = clock64();
+          unsigned gen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(tile_sync + 1) : "memory");
+            if (clock64() - t_start > 4000000000LL) __trap();
+          } while (gen == gen0);
+        }
+        __syncwarp();
+        // reduction: token rows sp, sp + n_split, ... of the tile belong to this item; its four epilogue warps take
+        // them in turn, a lane holds 4 consecutive features of the CTA's 128
+        const int64_t left = p.T - t0;
+        const int tok_live = left < tok_tile ? (int)left : tok_tile;
+        const int64_t f = feat0 + 4 * lane;
+        if (f < OUT && !(p.debug & 4)) {
+          float bias4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          if (has_bias) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int64_t t = ta + c0 + 8 * q + 2 * (lane & 3) + (e & 1);
-                const int col = c0 + 8 * q + 2 * (lane & 3) + (e & 1);
-                const int64_t f_lo = feat0 + quad * 32 + (lane >> 2) + ((e >> 1) ? 8 : 0);
-                if (col < p.N_acc && t < p.T) {
-                  if (f_lo < OUT) atomicAdd(p.partial + t * OUT + f_lo, __uint_as_float(v0[4 * q + e]));
-                  if (f_lo + 16 < OUT) atomicAdd(p.partial + t * OUT + f_lo + 16, __uint_as_float(v1[4 * q + e]));
-                }
-              }
+            for (int u = 0; u < 4; ++u) bias4[u] = to_f32<ActT>(static_cast<const ActT*>(p.bias)[f + u]);
+          }
+          const float* tile_part = p.partial + (int64_t)tile * p.n_split * tok_tile * (2 * kBM) + (int)rank * kBM + 4 * lane;
+          for (int row = sp + p.n_split * (warp - kEpiWarp0); row < tok_live; row += 4 * p.n_split) {
+            float4 acc = make_float4(bias4[0], bias4[1], bias4[2], bias4[3]);
+            for (int s2 = 0; s2 < p.n_split; ++s2) {
+              const float4 q = __ldcg(reinterpret_cast<const float4*>(tile_part + ((int64_t)s2 * tok_tile + row) * (2 * kBM)));
+              acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
             }
+            uint2 o;
+            o.x = pack2<ActT>(acc.x, acc.y);
+            o.y = pack2<ActT>(acc.z, acc.w);
+            *reinterpret_cast<uint2*>(static_cast<ActT*>(p.out) + (t0 + row) * OUT + f) = o;
           }
         }
       } else {
@@ -1007,29 +1048,6 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   }
 }
 
-// split-K epilogue: out[t, f] = ActT(partial[t, f] + bias[f]); 8 outputs per thread (OUT % 8 == 0)
-template <typename ActT>
-__global__ void qlora_tc2_finalize_kernel(const float* __restrict__ partial, const ActT* __restrict__ bias, int64_t total8,
-                                          int64_t OUT, ActT* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
-  const int64_t e = i * 8;
-  const int64_t f = e % OUT;
-  const float4 a = __ldcs(reinterpret_cast<const float4*>(partial + e));
-  const float4 b = __ldcs(reinterpret_cast<const float4*>(partial + e) + 1);
-  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  if (bias != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] += to_f32<ActT>(bias[f + j]);
-  }
-  uint4 q;
-  q.x = pack2<ActT>(v[0], v[1]);
-  q.y = pack2<ActT>(v[2], v[3]);
-  q.z = pack2<ActT>(v[4], v[5]);
-  q.w = pack2<ActT>(v[6], v[7]);
-  *reinterpret_cast<uint4*>(out + e) = q;
-}
-
 // ---------------------------------------------------------------------------
 // host side: tile shape selection + launch
 // ---------------------------------------------------------------------------
@@ -1068,7 +1086,8 @@ static bool config_ok(bool tmem_a, int n_acc, int N_acc, int rp) {
 }
 
 // Split-K plan: with fewer tiles than half the SM pairs, the contraction of every tile is divided over n_split work
-// items so that about one item per pair exists; their fp32 partial tiles are summed in a caller-provided workspace.
+// items so that about one item per pair exists (never more items than pairs: the items of a tile wait for each other
+// inside the launch); their fp32 partial tiles meet in a caller-provided workspace, one slice per item.
 struct Tc2Plan {
   Tc2Config cfg;
   int n_tiles, n_split, k_per;
@@ -1079,15 +1098,14 @@ struct Tc2Plan {
 // 2*N_acc cycles per accumulator (M = 256 over the pair, K = 64), decode ~620 ALU-pipe cycles per 128 x 64 weight
 // tile, shared memory 128 B/clk over the activation boxes (TMA write + MMA read) and -- backward only -- the decoded
 // tile (written once, read once per accumulator); per work item ~2500 cycles of fill + ~20 cycles per token of
-// epilogue (128 per token when the partial tile leaves through fp32 atomics); a split adds a memset and a finalize
-// launch (~6000 cycles).  In practice the split wins only for a few tokens (adaLN / modulation layers, T = batch).
+// epilogue; a split item instead writes its fp32 partial tile (one 128-byte store per token and warp), meets the other
+// items of its tile (~2000 cycles) and reduces its share of the rows (~12 cycles per token of the tile in all).
 static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a, int n_pairs, bool allow_split = true,
                         int rp = 0) {
   Tc2Plan best = {};
   double best_cost = 1e300;
   const int n_main = (int)ceil_div64(RED, kBK);
   const int64_t n_f = ceil_div64(OUT, 2 * kBM);
-  const int64_t ws = T * OUT * (int64_t)sizeof(float);
   for (int n_acc = 1; n_acc <= kMaxAcc; ++n_acc) {
     for (int N_acc = 32; N_acc <= 256; N_acc += 16) {
       if (!config_ok(tmem_a, n_acc, N_acc, rp)) continue;
@@ -1099,7 +1117,7 @@ static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a,
       double step = mma > smem ? mma : smem;
       if (step < 620.0) step = 620.0;
       int split = 1, k_per = n_main;
-      if (allow_split && tiles * 2 <= n_pairs && n_main >= 4 && ws <= (64ll << 20)) {
+      if (allow_split && tiles * 2 <= n_pairs && n_main >= 4) {
         int want = (int)(n_pairs / tiles);
         if (want > n_main / 2) want = n_main / 2;  // at least two ring steps per item
         if (want > 1) {
@@ -1108,11 +1126,12 @@ static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a,
           if (split <= 1) { split = 1; k_per = n_main; }
         }
       }
+      const int64_t ws = tiles * split * tok * (2 * kBM) * (int64_t)sizeof(float);  // one slice per work item
+      if (split > 1 && (ws > (64ll << 20) || tiles * split > n_pairs)) { split = 1; k_per = n_main; }
       const double waves = (double)ceil_div64(tiles * split, n_pairs);
-      // split epilogue: one fp32 atomic per (feature lane, token), ~1 cycle per lane-atomic on the SM's path to L2
       const double tok_live = (double)(tok < T ? tok : T);
-      const double epi = split > 1 ? 128.0 * tok_live : 20.0 * tok;
-      const double cost = waves * ((k_per + (r > 0 ? 1 : 0)) * step + 2500.0 + epi) + (split > 1 ? 6000.0 : 0.0);
+      const double epi = split > 1 ? 12.0 * tok_live + 2000.0 : 20.0 * tok;
+      const double cost = waves * ((k_per + (r > 0 ? 1 : 0)) * step + 2500.0 + epi);
       if (cost < best_cost * 0.999 || (cost < best_cost * 1.001 && N_acc > best.cfg.N_acc)) {
         best_cost = cost;
         best.cfg = {n_acc, N_acc, max_stages(tmem_a, n_acc, N_acc, rp), cost};
@@ -1172,48 +1191,71 @@ static Tc2Choice choose_tc2(const LayerArgs& a, bool backward, int n_pairs) {
   c.p0_rows = 0;
   c.job = false;
   // triage override VFT_TC2_NACC="<n_acc>x<N_acc>" (clamped to what the path allows): forces the shape, never splits
-  auto forced = [&](int rp) -> bool {
+  auto forced = [&](int rp, Tc2Plan& plan) -> bool {
     if (ev.tc2_force_na <= 0) return false;
     int na = ev.tc2_force_na, nn = ev.tc2_force_nn;
     if (tmem_a && na == 2 && nn > AccLayout<true>::pitch) nn = AccLayout<true>::pitch;
     if (!config_ok(tmem_a, na, nn, rp)) return false;
-    c.plan.cfg = {na, nn, max_stages(tmem_a, na, nn, rp), 0.0};
-    c.plan.n_tiles = (int)(ceil_div64(OUT, 2 * kBM) * ceil_div64(a.T, (int64_t)na * nn));
-    c.plan.n_split = 1;
-    c.plan.k_per = (int)ceil_div64(RED, kBK);
-    c.plan.ws_bytes = 0;
+    plan.cfg = {na, nn, max_stages(tmem_a, na, nn, rp), plan.cfg.cost};
+    plan.n_tiles = (int)(ceil_div64(OUT, 2 * kBM) * ceil_div64(a.T, (int64_t)na * nn));
+    plan.n_split = 1;
+    plan.k_per = (int)ceil_div64(RED, kBK);
+    plan.ws_bytes = 0;
     return true;
   };
   c.rp = side_rank(a, backward);
+  const bool ws_ok = a.ws != nullptr && (reinterpret_cast<uintptr_t>(a.ws) & 15u) == 0 && !ev.tc2_nosplit;
   if (c.rp > 0) {
-    // the plan the launch would take without it decides: a problem small enough to be split along the contraction
-    // keeps its side kernel (which is then tiny), so does one with more tokens than one pass of 128 rows per CTA holds
-    const Tc2Plan base = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs);
+    // Inside the launch or next to it?  Compared on the cycle model, with the side kernels of lora_tc.cu at what they
+    // measured (3.5 us + bytes at 3.2 TB/s for t / dt, 4 us + bytes at 3.9 TB/s for dA/dB: 7.9 / 8.5 / 12.9 us at
+    // config #1) and the fused launch at 1.08 x its plan (the side product shares the tensor pipe, the TMA queue and
+    // 40 KB of the staging tiles' shared memory with the main loop).  What decides in practice is the wave count:
+    // setting the side product's columns aside caps the forward's accumulators at 2 x 176 tokens instead of 2 x 192,
+    // and at T = 8720 (AuraFlow, batch 2) that is 300 tiles = 5 waves instead of 276 = 4 (measured, 3072 x 3072:
+    // 139.5 us fused against 131.8 us with the side kernel; at T = 4096 and 8192 the fused launch wins).
+    const double cyc_per_us = 1900.0;
+    const double side_cyc = cyc_per_us * (3.5 + (double)a.T * (double)RED * 2.0 / 3.2e6);
+    const double dab_cyc = backward ? cyc_per_us * (4.0 + (double)a.T * (double)(a.N + a.K) * 2.0 / 3.9e6) : 0.0;
+    Tc2Plan base = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs);
+    if (base.n_split > 1 && (!ws_ok || a.ws_bytes < base.ws_bytes))
+      base = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs, /*allow_split=*/false);
+    const double base_cost = base.cfg.cost + side_cyc + dab_cyc;
     // dA/dB job: everything it reads and writes is there, TMA can address the transposed side products (row stride
     // T * 2 bytes), and a second block of r_pad accumulator columns is free
     const bool job_ok = backward && ev.tc2_job != 0 && a.job_x && a.tt_save && a.job_dtt && a.job_da && a.job_db &&
                         a.T % 8 == 0 && ((reinterpret_cast<uintptr_t>(a.job_x) | reinterpret_cast<uintptr_t>(a.tt_save) |
                                           reinterpret_cast<uintptr_t>(a.job_dtt)) & 15u) == 0;
+    Tc2Choice best_c = c;
+    double best_cost = 1e300;
     for (int with_job = job_ok ? 1 : 0; with_job >= 0; --with_job) {
+      Tc2Choice k = c;
       const int cols = c.rp * (1 + with_job);  // accumulator columns set aside
-      c.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs, /*allow_split=*/false, cols);
-      forced(cols);
-      c.pairs = pairs_for(c.plan, n_pairs);
-      const int64_t rows = ceil_div64(ceil_div64(a.T, 2 * c.pairs), 8) * 8;
+      k.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs, /*allow_split=*/false, cols);
+      forced(cols, k.plan);
+      if (k.plan.cfg.N_acc <= 0) continue;
+      k.pairs = pairs_for(k.plan, n_pairs);
+      const int64_t rows = ceil_div64(ceil_div64(a.T, 2 * k.pairs), 8) * 8;
+      if (rows > kBM) continue;  // more tokens than one pass of 128 rows per CTA holds
       const int64_t units = ceil_div64(a.K, kBM) + ceil_div64(a.N, kBM);
-      if (with_job && (units > c.pairs || c.plan.cfg.N_acc <= 0)) continue;
-      if ((base.n_split == 1 || ev.tc2_fuse == 1) && c.plan.cfg.N_acc > 0 && rows <= kBM) {
-        c.p0_rows = (int)rows;
-        c.job = with_job != 0;
-        return c;
+      // the job streams all T tokens through ONE pair per 128 columns at ~900 cycles per 64 tokens: it has to end
+      // before the pair's last tile does (C640 at T = 8192: 115 k cycles of job against 21 k of GEMM -- 50 us, measured)
+      const double job_cyc = 900.0 * (double)ceil_div64(a.T, 64);
+      if (with_job && (units > k.pairs || job_cyc > 0.85 * k.plan.cfg.cost)) continue;
+      k.p0_rows = (int)rows;
+      k.job = with_job != 0;
+      const double cost = 1.08 * k.plan.cfg.cost + (with_job ? 0.0 : dab_cyc);
+      if (cost < best_cost) {
+        best_cost = cost;
+        best_c = k;
       }
     }
+    if (best_cost < 1e300 && (ev.tc2_fuse == 1 || best_cost <= base_cost)) return best_c;
     c.rp = 0;
   }
   c.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs);
-  if (c.plan.n_split > 1 && (a.ws == nullptr || a.ws_bytes < c.plan.ws_bytes || ev.tc2_nosplit))
+  if (c.plan.n_split > 1 && (!ws_ok || a.ws_bytes < c.plan.ws_bytes))
     c.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs, /*allow_split=*/false);  // no workspace: unsplit shape
-  forced(0);
+  forced(0, c.plan);
   c.pairs = pairs_for(c.plan, n_pairs);
   return c;
 }
@@ -1224,11 +1266,17 @@ static Tc2Choice choose_tc2(const LayerArgs& a, bool backward, int n_pairs) {
 // to avoid is replaying ONE captured graph concurrently with itself on two streams.
 constexpr int kSyncSlots = 4096;
 __device__ unsigned g_tc2_sync[2 * kSyncSlots];
-static unsigned* next_sync_pair() {
+static unsigned* next_sync_pair(unsigned n = 1) {  // n consecutive pairs (split-K: one per tile, n <= SM pairs)
   static std::atomic<unsigned> next{0};
-  unsigned* base = nullptr;
-  if (cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_tc2_sync) != cudaSuccess) return nullptr;
-  return base + 2 * (next.fetch_add(1, std::memory_order_relaxed) % kSyncSlots);
+  static unsigned* base = nullptr;  // (the symbol's address does not change; a failed lookup is retried)
+  if (base == nullptr && cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_tc2_sync) != cudaSuccess) {
+    base = nullptr;
+    return nullptr;
+  }
+  unsigned first = next.fetch_add(n, std::memory_order_relaxed) % kSyncSlots;
+  if (first + n > kSyncSlots) first = next.fetch_add(n, std::memory_order_relaxed) % kSyncSlots;  // no wrap inside a run
+  if (first + n > kSyncSlots) first = 0;
+  return base + 2 * first;
 }
 
 template <typename ActT, bool kBackward>
@@ -1295,7 +1343,11 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
     p.n_split = plan.n_split;
     p.k_per = plan.k_per;
     p.partial = static_cast<float*>(a.ws);
-    VFT_CUDA_OK(cudaMemsetAsync(a.ws, 0, (size_t)plan.ws_bytes, st));
+    p.sync = next_sync_pair((unsigned)p.n_tiles);
+    if (p.sync == nullptr) {
+      set_error("cudaGetSymbolAddress(g_tc2_sync) failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return VFT_ERR_CUDA;
+    }
   }
   p.debug = ev.tc_debug;
 
@@ -1373,12 +1425,6 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   lc.numAttrs = pdl_enabled() ? 2 : 1;
   VFT_CUDA_OK(cudaLaunchKernelEx(&lc, kern, map_act, map_lora, map_out, map_out16, map_p0a, map_p0w, jm, p));
   VFT_CUDA_OK(cudaGetLastError());
-  if (p.n_split > 1) {
-    const int64_t total8 = a.T * OUT / 8;
-    qlora_tc2_finalize_kernel<ActT><<<(unsigned)ceil_div64(total8, 256), 256, 0, st>>>(
-        p.partial, static_cast<const ActT*>(p.bias), total8, OUT, static_cast<ActT*>(out));
-    VFT_CUDA_OK(cudaGetLastError());
-  }
   return VFT_OK;
 }
 

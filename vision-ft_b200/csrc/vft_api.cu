@@ -106,6 +106,11 @@ int vft_nf4_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t
   return launch_quantize(w, dtype, n, blocksize, packed, absmax, static_cast<cudaStream_t>(stream));
 }
 
+int vft_nf4_quantize_many(int count, const void* const* w, int dtype, const int64_t* n, int blocksize,
+                          uint8_t* const* packed, float* const* absmax, void* stream) {
+  return launch_quantize_many(count, w, dtype, n, blocksize, packed, absmax, static_cast<cudaStream_t>(stream));
+}
+
 int vft_nf4_dequantize(const uint8_t* packed, const float* absmax, int64_t n, int blocksize, void* out, int dtype,
                        void* stream) {
   VFT_REQUIRE(n >= 0, "n must be >= 0");

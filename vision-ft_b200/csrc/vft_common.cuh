@@ -131,6 +131,8 @@ inline bool pdl_enabled() { return env().pdl; }
 // ---------------------------------------------------------------------------
 // launchers implemented across the .cu files (all return vft_status)
 // ---------------------------------------------------------------------------
+int launch_quantize_many(int count, const void* const* w, int dtype, const int64_t* n, int blocksize,
+                         uint8_t* const* packed, float* const* absmax, cudaStream_t st);
 int launch_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t* packed, float* absmax,
                     cudaStream_t st);
 int launch_dequantize(const uint8_t* packed, const float* absmax, int64_t n, int blocksize, void* out, int dtype,

@@ -16,7 +16,8 @@ from typing import Callable, Literal, get_args
 import torch
 import torch.nn as nn
 
-from vft_b200.nn import quantize_4bit
+from vft_b200 import ops
+from vft_b200.nn import QuantState
 
 from ...utils.state_dict import get_target_keys
 from .bnb import BnbLinear4bit
@@ -158,11 +159,31 @@ def quantize_state_dict(
         raise NotImplementedError("Only bitsandbytes 4bit quantization is supported")
     _require_implemented(quant_type)
     targets = set(get_target_keys(include_keys, exclude_keys, list(state_dict.keys())))
-    for key in list(state_dict.keys()):
-        if key not in targets:
-            continue
-        packed, state = quantize_4bit(state_dict[key].cuda(), quant_type="nf4")
-        state_dict[key] = packed.cpu()
-        for state_key, state_value in state.as_dict(packed=True).items():
-            state_dict[f"{key}.{state_key}"] = state_value.cpu()
+    keys = [k for k in list(state_dict.keys()) if k in targets]
+    # The reference quantizes tensor by tensor (.cuda() -> quantize_4bit -> .cpu()).  Here the uploads of a group of
+    # tensors of one dtype (at most ~2 GB of weights) are followed by ONE batched launch (vft_nf4_quantize_many, 96
+    # tensors per kernel, bit-identical to the per-tensor calls): a checkpoint is mostly small weights, and per-tensor
+    # launches leave the HBM-bound kernel waiting on launch latency.
+    group: list[str] = []
+    group_bytes = 0
+
+    def flush() -> None:
+        nonlocal group, group_bytes
+        if not group:
+            return
+        dev_w = [state_dict[k].cuda() for k in group]
+        for k, w, (packed, absmax) in zip(group, dev_w, ops.nf4_quantize_many(dev_w)):
+            state = QuantState(absmax=absmax, shape=w.shape, dtype=w.dtype, blocksize=64, quant_type="nf4")
+            state_dict[k] = packed.cpu()
+            for state_key, state_value in state.as_dict(packed=True).items():
+                state_dict[f"{k}.{state_key}"] = state_value.cpu()
+        group, group_bytes = [], 0
+
+    for key in keys:
+        w = state_dict[key]
+        if group and (w.dtype != state_dict[group[0]].dtype or group_bytes + w.numel() * w.element_size() > (2 << 30)):
+            flush()
+        group.append(key)
+        group_bytes += w.numel() * w.element_size()
+    flush()
     return state_dict

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ALT_LIB = os.environ.get("VFT_LIB")
 LIB_PATH = _ALT_LIB if _ALT_LIB else os.path.join(_HERE, "libvft_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 LORA_LD = 64
 F32, F16, BF16 = 0, 1, 2
 PATH_NONE, PATH_TCGEN05, PATH_SIMT, PATH_GEMV = 0, 1, 2, 3
@@ -33,6 +33,7 @@ SYMBOLS = {
     "vft_debug_tc2_timeline": (_i, [_p, _i]),
     "vft_debug_side_timeline": (_i, [_p, _i]),
     "vft_nf4_quantize": (_i, [_p, _i, _i64, _i, _p, _p, _p]),
+    "vft_nf4_quantize_many": (_i, [_i, _p, _i, _p, _i, _p, _p, _p]),
     "vft_nf4_dequantize": (_i, [_p, _p, _i64, _i, _p, _i, _p]),
     "vft_nf4_quantize_host": (_i, [_p, _i, _i64, _i, _p, _p]),
     "vft_nf4_tiled_bytes": (_i64, [_i64, _i64, _i]),
