@@ -69,6 +69,7 @@ def main():
             for i in list(range(0, 6)) + list(range(10, 14)):
                 print(f"   {4*i:4d}: {rel(rows[2][i]):10d} {rel(rows[6][i]):10d} {rel(rows[3][i]):10d}")
             print("   epilogue per tile (t_full seen, t box written, acc_full seen, drained):", [rel(v) for v in rows[4][:12]])
+            print("   split exchange: stores issued, fenced, all items arrived, reduced:", [rel(v) for v in rows[6][240:244]])
             print("   side product: done seen by epilogue, published, generation seen by producer:", [rel(v) for v in rows[6][250:253]])
             steps = [v for v in rows[0] if v]
             if len(steps) > 20:

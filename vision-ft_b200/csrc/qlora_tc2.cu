@@ -101,10 +101,12 @@ struct Tc2Params {
   int n_tiles;      // n_fblk * token blocks
   // split-K (small problems: fewer tiles than SM pairs; all work items resident at once): a work item is
   // (tile, split); split i reduces ring steps [i * k_per, (i + 1) * k_per) of the contraction (the adapter step belongs
-  // to the last split), writes its fp32 partial tile to ITS slice of `partial` [item][token of the tile][256 features],
-  // counts itself in on the tile's {arrivals, generation} pair (`sync` + 2 * tile) and, once all n_split items of the
-  // tile are there, sums every n_split-th token row over the slices IN SPLIT ORDER, adds the bias, converts and writes
-  // the output rows.  One launch, no memset, no atomics on data: the sums are reproducible run to run.
+  // to the last split) and writes its fp32 partial tile to ITS slice of `partial` [item][token of the tile][256
+  // features]; qlora_tc2_finalize_kernel (launched behind this kernel, programmatic dependent launch) adds the slices
+  // of every output element IN SPLIT ORDER, adds the bias and converts.  No memset, no atomics: reproducible sums.
+  // (Measured alternatives: fp32 atomicAdd into one [T, OUT] buffer + memset + finalize -- three launches, sums that
+  // change from run to run; meeting inside the launch on a per-tile counter and reducing there -- the items of a tile
+  // finish up to 15 k cycles apart, and the store -> fence -> atomic -> poll -> load chain cost 20 us at T = 528.)
   int n_split, k_per;
   float* partial;
   int debug;        // VFT_TC_DEBUG triage mask (results are garbage when non-zero): 1 = no decode stores,
@@ -734,10 +736,6 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       if (p.n_split > 1) {
         // split-K: this item's fp32 partial tile goes to its own slice of the workspace, rows = tokens of the tile,
         // 256 features per row (a warp's 32 lanes = 32 consecutive features: 128-byte stores)
-        const int sp = item % p.n_split;
-        unsigned* tile_sync = p.sync + 2 * tile;
-        unsigned gen0 = 0;  // (this CTA has not arrived yet, so the generation cannot have moved on)
-        if (lane == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen0) : "l"(tile_sync + 1) : "memory");
         float* slice = p.partial + (int64_t)item * tok_tile * (2 * kBM) + (int)rank * kBM + quad * 32 + lane;
         for (int a = 0; a < na; ++a) {
           const int64_t ta = t0 + (int64_t)a * p.N_acc;
@@ -759,49 +757,6 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
 #pragma unroll
             for (int e = 0; e < 16; ++e)
               if (ta + c0 + e < p.T) __stcg(row + e * (2 * kBM), __uint_as_float(v0[e]));
-          }
-        }
-        // count this warp in (4 warps x 2 CTAs x n_split items per tile); the warp that completes the count resets it
-        // for the next launch that is handed this pair and bumps the generation everybody else is watching
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) {
-          const unsigned total = 8u * (unsigned)p.n_split;
-          if (atomicAdd(tile_sync, 1u) == total - 1u) {
-            atomicExch(tile_sync, 0u);
-            __threadfence();
-            atomicAdd(tile_sync + 1, 1u);
-          }
-          const long long t_start = clock64();
-          unsigned gen;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(tile_sync + 1) : "memory");
-            if (clock64() - t_start > 4000000000LL) __trap();
-          } while (gen == gen0);
-        }
-        __syncwarp();
-        // reduction: token rows sp, sp + n_split, ... of the tile belong to this item; its four epilogue warps take
-        // them in turn, a lane holds 4 consecutive features of the CTA's 128
-        const int64_t left = p.T - t0;
-        const int tok_live = left < tok_tile ? (int)left : tok_tile;
-        const int64_t f = feat0 + 4 * lane;
-        if (f < OUT && !(p.debug & 4)) {
-          float bias4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-          if (has_bias) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) bias4[u] = to_f32<ActT>(static_cast<const ActT*>(p.bias)[f + u]);
-          }
-          const float* tile_part = p.partial + (int64_t)tile * p.n_split * tok_tile * (2 * kBM) + (int)rank * kBM + 4 * lane;
-          for (int row = sp + p.n_split * (warp - kEpiWarp0); row < tok_live; row += 4 * p.n_split) {
-            float4 acc = make_float4(bias4[0], bias4[1], bias4[2], bias4[3]);
-            for (int s2 = 0; s2 < p.n_split; ++s2) {
-              const float4 q = __ldcg(reinterpret_cast<const float4*>(tile_part + ((int64_t)s2 * tok_tile + row) * (2 * kBM)));
-              acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
-            }
-            uint2 o;
-            o.x = pack2<ActT>(acc.x, acc.y);
-            o.y = pack2<ActT>(acc.z, acc.w);
-            *reinterpret_cast<uint2*>(static_cast<ActT*>(p.out) + (t0 + row) * OUT + f) = o;
           }
         }
       } else {
@@ -1048,6 +1003,33 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   }
 }
 
+// split contraction, second half: out[t, f] = ActT(bias[f] + sum over splits, in split order, of the fp32 slices);
+// one thread per 4 consecutive features of one token row
+template <typename ActT>
+__global__ void __launch_bounds__(256)
+qlora_tc2_finalize_kernel(const float* __restrict__ partial, const ActT* __restrict__ bias, int64_t T, int64_t OUT,
+                          int tok_tile, int n_fblk, int n_split, ActT* __restrict__ out) {
+  ptx::griddep_wait();  // the slices are written by the GEMM launch in front of this one
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_row = OUT >> 2;
+  if (q >= T * per_row) return;
+  const int64_t t = q / per_row, f = (q - t * per_row) << 2;
+  const int64_t tile = (t / tok_tile) * n_fblk + (f >> 8);
+  const float* src = partial + ((tile * n_split) * tok_tile + (t % tok_tile)) * (2 * kBM) + (f & 255);
+  float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (bias != nullptr) {
+    acc.x = to_f32<ActT>(bias[f]); acc.y = to_f32<ActT>(bias[f + 1]); acc.z = to_f32<ActT>(bias[f + 2]); acc.w = to_f32<ActT>(bias[f + 3]);
+  }
+  for (int s = 0; s < n_split; ++s) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)s * tok_tile * (2 * kBM)));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  uint2 o;
+  o.x = pack2<ActT>(acc.x, acc.y);
+  o.y = pack2<ActT>(acc.z, acc.w);
+  *reinterpret_cast<uint2*>(out + t * OUT + f) = o;
+}
+
 // ---------------------------------------------------------------------------
 // host side: tile shape selection + launch
 // ---------------------------------------------------------------------------
@@ -1098,8 +1080,9 @@ struct Tc2Plan {
 // 2*N_acc cycles per accumulator (M = 256 over the pair, K = 64), decode ~620 ALU-pipe cycles per 128 x 64 weight
 // tile, shared memory 128 B/clk over the activation boxes (TMA write + MMA read) and -- backward only -- the decoded
 // tile (written once, read once per accumulator); per work item ~2500 cycles of fill + ~20 cycles per token of
-// epilogue; a split item instead writes its fp32 partial tile (one 128-byte store per token and warp), meets the other
-// items of its tile (~2000 cycles) and reduces its share of the rows (~12 cycles per token of the tile in all).
+// epilogue; a split item instead writes its fp32 partial tile (one 128-byte store per token and warp: ~50 cycles per
+// token, measured) and a second small launch adds the slices (~5 k cycles of launch + the slices at ~1.5 KB per cycle
+// out of L2), so the split pays for few tokens only (adaLN / modulation layers, text-token projections).
 static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a, int n_pairs, bool allow_split = true,
                         int rp = 0) {
   Tc2Plan best = {};
@@ -1130,7 +1113,7 @@ static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a,
       if (split > 1 && (ws > (64ll << 20) || tiles * split > n_pairs)) { split = 1; k_per = n_main; }
       const double waves = (double)ceil_div64(tiles * split, n_pairs);
       const double tok_live = (double)(tok < T ? tok : T);
-      const double epi = split > 1 ? 12.0 * tok_live + 2000.0 : 20.0 * tok;
+      const double epi = split > 1 ? 50.0 * tok_live + 5000.0 + (double)(split * T * OUT) * 4.0 / 1500.0 : 20.0 * tok;
       const double cost = waves * ((k_per + (r > 0 ? 1 : 0)) * step + 2500.0 + epi);
       if (cost < best_cost * 0.999 || (cost < best_cost * 1.001 && N_acc > best.cfg.N_acc)) {
         best_cost = cost;
@@ -1266,7 +1249,7 @@ static Tc2Choice choose_tc2(const LayerArgs& a, bool backward, int n_pairs) {
 // to avoid is replaying ONE captured graph concurrently with itself on two streams.
 constexpr int kSyncSlots = 4096;
 __device__ unsigned g_tc2_sync[2 * kSyncSlots];
-static unsigned* next_sync_pair(unsigned n = 1) {  // n consecutive pairs (split-K: one per tile, n <= SM pairs)
+static unsigned* next_sync_pair(unsigned n = 1) {  // n consecutive pairs
   static std::atomic<unsigned> next{0};
   static unsigned* base = nullptr;  // (the symbol's address does not change; a failed lookup is retried)
   if (base == nullptr && cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_tc2_sync) != cudaSuccess) {
@@ -1343,11 +1326,6 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
     p.n_split = plan.n_split;
     p.k_per = plan.k_per;
     p.partial = static_cast<float*>(a.ws);
-    p.sync = next_sync_pair((unsigned)p.n_tiles);
-    if (p.sync == nullptr) {
-      set_error("cudaGetSymbolAddress(g_tc2_sync) failed: %s", cudaGetErrorString(cudaGetLastError()));
-      return VFT_ERR_CUDA;
-    }
   }
   p.debug = ev.tc_debug;
 
@@ -1425,6 +1403,19 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   lc.numAttrs = pdl_enabled() ? 2 : 1;
   VFT_CUDA_OK(cudaLaunchKernelEx(&lc, kern, map_act, map_lora, map_out, map_out16, map_p0a, map_p0w, jm, p));
   VFT_CUDA_OK(cudaGetLastError());
+  if (p.n_split > 1) {
+    const int64_t quads = a.T * (OUT / 4);
+    cudaLaunchConfig_t fc = {};
+    fc.gridDim = dim3((unsigned)ceil_div64(quads, 256));
+    fc.blockDim = dim3(256);
+    fc.stream = st;
+    fc.attrs = attr + 1;  // programmatic stream serialization only: its launch latency hides under the GEMM's tail
+    fc.numAttrs = pdl_enabled() ? 1 : 0;
+    VFT_CUDA_OK(cudaLaunchKernelEx(&fc, qlora_tc2_finalize_kernel<ActT>, static_cast<const float*>(p.partial),
+                                   static_cast<const ActT*>(p.bias), a.T, OUT, cfg.n_acc * cfg.N_acc, p.n_fblk, p.n_split,
+                                   static_cast<ActT*>(out)));
+    VFT_CUDA_OK(cudaGetLastError());
+  }
   return VFT_OK;
 }
 
