@@ -277,6 +277,7 @@ def run_gpu_arm(args):
 
     # CUDA graphs: one per input set, so launch overhead is off the device timeline
     graphs, launch_mode = [], "cuda_graph"
+    round_graph = None
     grad_bufs = []
     try:
         side = torch.cuda.Stream()
@@ -294,27 +295,42 @@ def run_gpu_arm(args):
         grad_bufs = [torch.zeros(n_grad, device=dev, dtype=torch.bfloat16) if world > 1 else None for _ in range(n_sets)]
         in_graph = world > 1 and args.exchange == "graph"
         fork = torch.cuda.Stream() if in_graph else None
+        def captured_step(i):
+            cur = torch.cuda.current_stream()
+            if in_graph:
+                fork.wait_stream(cur)
+                with torch.cuda.stream(fork):
+                    dist.all_reduce(grad_bufs[(i - 1) % n_sets], group=comm_group)
+            step(i)
+            if world > 1:  # the flat bucket exists for the NCCL exchange only: a single rank has nothing to pack
+                torch.cat([p.grad.reshape(-1) for p in params], out=grad_bufs[i])
+            if in_graph:
+                cur.wait_stream(fork)
+
         for i in range(n_sets):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                cur = torch.cuda.current_stream()
-                if in_graph:
-                    fork.wait_stream(cur)
-                    with torch.cuda.stream(fork):
-                        dist.all_reduce(grad_bufs[(i - 1) % n_sets], group=comm_group)
-                step(i)
-                if world > 1:  # the flat bucket exists for the NCCL exchange only: a single rank has nothing to pack
-                    torch.cat([p.grad.reshape(-1) for p in params], out=grad_bufs[i])
-                if in_graph:
-                    cur.wait_stream(fork)
+                captured_step(i)
             graphs.append(g)
+        # One graph launch per STEP puts a graph-launch boundary between every backward and the next forward: ~5 us per
+        # 130-us step during which the device idles, and the programmatic dependent launch of the next kernel (its
+        # barrier / TMEM / tensor-map set-up under the previous kernel's tail) is lost.  A training loop captures more
+        # than one layer call per graph; here one graph holds a whole round of the n_sets input sets (same kernels, same
+        # order, same work per step), and a remainder of steps % n_sets steps runs from the single-step graphs.
+        if world == 1 or in_graph:
+            round_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(round_graph):
+                for i in range(n_sets):
+                    captured_step(i)
         torch.cuda.synchronize()
     except Exception as e:  # pragma: no cover - reported, not hidden
         print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
-        graphs, launch_mode = [], "eager"
+        graphs, launch_mode, round_graph = [], "eager", None
         if args.exchange == "graph":
             args.exchange = "overlap"
         torch.cuda.synchronize()
+    if round_graph is not None:
+        launch_mode += f" ({n_sets} steps per graph launch)"
     if world > 1:
         launch_mode += f"+allreduce:{args.exchange}"
 
@@ -354,8 +370,17 @@ def run_gpu_arm(args):
     sampler = ClockSampler(local)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     align = torch.zeros(1, device=dev)
-    for i in range(max(args.warmup, 3)):
-        run_step(i)
+    def run_steps(n):
+        i = 0
+        while i < n:
+            if round_graph is not None and i % n_sets == 0 and i + n_sets <= n:
+                round_graph.replay()  # steps i .. i + n_sets - 1
+                i += n_sets
+            else:
+                run_step(i)
+                i += 1
+
+    run_steps(max(args.warmup, 3))
     if comm is not None:
         torch.cuda.current_stream().wait_stream(comm)
     barrier()
@@ -363,8 +388,7 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(align)  # ranks leave this collective together ON THE DEVICE, right in front of the first event
     e0.record()
-    for i in range(args.steps):
-        run_step(i)
+    run_steps(args.steps)  # exactly args.steps steps
     if comm is not None:
         torch.cuda.current_stream().wait_stream(comm)
     e1.record()
@@ -542,9 +566,9 @@ def run_gpu_arm(args):
             q_ms_set, q_gbs_set, q_k = quant_probe.whole_set_batched(torch.float16)
             extra["nf4_quantize_pack_auraflow_set"] = {
                 "ms": q_ms_set, "GB/s": q_gbs_set, "frac_of_hbm_peak": q_gbs_set / peaks["hbm_gbs"], "tensors": q_k,
-                "elements": 6.80e9, "hbm_floor_ms": 17.4e9 / peaks["hbm_gbs"] / 1e6, "launches": (q_k + 95) // 96,
+                "elements": 6.80e9, "hbm_floor_ms": 17.4e9 / peaks["hbm_gbs"] / 1e6, "launches": 6,
                 "one_launch_per_tensor": {"ms": q_ms_1, "GB/s": q_gbs_1, "frac_of_hbm_peak": q_gbs_1 / peaks["hbm_gbs"]},
-                "note": "fp16 weights device-resident (13.6 GB), vft_nf4_quantize_many: 96 tensors per launch, CUDA events around the call"}
+                "note": "fp16 weights device-resident (13.6 GB), vft_nf4_quantize_many: up to 96 equal-size tensors per launch (6 launches for this set), CUDA events around the call"}
         except Exception as e:  # pragma: no cover - reported, not hidden
             extra["nf4_quantize_pack_auraflow_set"] = {"error": f"{type(e).__name__}: {e}"}
         torch.cuda.empty_cache()
@@ -642,6 +666,7 @@ def run_gpu_arm(args):
         import gc
 
         graphs.clear()
+        round_graph = None
         gc.collect()
         t = threading.Thread(target=dist.destroy_process_group, daemon=True)
         t.start()

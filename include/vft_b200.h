@@ -81,7 +81,8 @@ int vft_debug_side_timeline(unsigned long long* out, int n);
 int vft_nf4_quantize(const void* w, int dtype, int64_t n, int blocksize, uint8_t* packed, float* absmax, void* stream);
 
 /* The same for a batch of tensors of one dtype in as few launches as possible (the tables are HOST arrays of `count`
- * device pointers / element counts; 96 tensors ride one launch).  This is the loop of quantize_state_dict()
+ * device pointers / element counts; up to 96 tensors of EQUAL element count ride one launch -- a model checkpoint
+ * repeats a handful of shapes).  This is the loop of quantize_state_dict()
  * (/root/reference/src/modules/quant/functional.py:342-371) and of tools/quantize_model.py:33-54 over a checkpoint:
  * per-tensor launches leave an HBM-bound kernel waiting on launch latency for the small weights.  Results are
  * bit-identical to `count` calls of vft_nf4_quantize. */

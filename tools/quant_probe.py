@@ -105,5 +105,5 @@ def main():
 if __name__ == "__main__":
     main()
     ms, gbs, k = whole_set_batched(torch.float16)
-    print(f"float16: AuraFlow DiT set through vft_nf4_quantize_many ({k} tensors, 4 launches): {ms:.2f} ms, {gbs:.0f} GB/s "
+    print(f"float16: AuraFlow DiT set through vft_nf4_quantize_many ({k} tensors, one launch per <= 96 tensors of equal size): {ms:.2f} ms, {gbs:.0f} GB/s "
           f"({gbs / 6452.2 * 100:.1f} % of measured HBM copy bandwidth)")

@@ -19,6 +19,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 #include "vft_common.cuh"
 
 namespace vft {
@@ -112,23 +114,26 @@ constexpr int kChunkElems = kWarpElems * kQuantUnroll;  // 1024
 // lane ([cell][lane], 8 bytes each: conflict-free), and the cell index sits at bits [8, 14) of the FFMA result.
 constexpr int kTabBytes = kCells * 32 * 8;  // 16 KB
 
-// One launch quantizes a BATCH of tensors (vft_nf4_quantize_many: a checkpoint is hundreds of weights, and a launch per
-// tensor costs ~2 us of an HBM-bound kernel that needs 4-30 us for one -- the 322-tensor AuraFlow set ran at 57 % of
-// HBM bandwidth against 73 % for its largest tensor).  The chunks (1024 elements) of all tensors form one index space;
-// a warp walks it with the grid stride and steps through the table as it crosses tensor boundaries.  The table rides in
-// the kernel parameters (constant bank: no workspace, capturable), kQuantBatch tensors per launch.
+// One launch quantizes a GROUP of tensors of equal size (vft_nf4_quantize_many: a checkpoint is hundreds of weights in a
+// handful of shapes, and a launch per tensor costs ~2 us of an HBM-bound kernel that needs 4-30 us for one -- the
+// 322-tensor AuraFlow set ran at 57 % of HBM bandwidth against 73 % for its largest tensor).  blockIdx.y selects the
+// tensor, so the pointers are CTA-uniform and the hot loop is the single-tensor loop.  (A walk over one chunk index
+// space across tensors of any size -- table look-up when a boundary is crossed -- cost 16 more registers, a fourth
+// resident CTA per SM and 18 % of the single-tensor speed: the kernel is issue-bound.)  The table rides in the kernel
+// parameters (constant bank: no workspace, capturable), kQuantBatch tensors per launch.
 constexpr int kQuantBatch = 96;
 struct QuantBatch {
   const void* w[kQuantBatch];
   uint32_t* packed[kQuantBatch];
   float* absmax[kQuantBatch];
-  int64_t chunk_end[kQuantBatch];  // exclusive prefix ends in the batch's chunk index space
-  int n;
 };
 
 template <typename T>
 __global__ void __launch_bounds__(kQuantThreads)
-nf4_quantize64_kernel(const __grid_constant__ QuantBatch batch, const __grid_constant__ CellTable table) {
+nf4_quantize64_kernel(const __grid_constant__ QuantBatch batch, int64_t n_chunks, const __grid_constant__ CellTable table) {
+  const T* __restrict__ w = static_cast<const T*>(batch.w[blockIdx.y]);
+  uint32_t* __restrict__ packed_words = batch.packed[blockIdx.y];
+  float* __restrict__ absmax = batch.absmax[blockIdx.y];
   extern __shared__ uint8_t q_smem[];
   const uint32_t raw = static_cast<uint32_t>(__cvta_generic_to_shared(q_smem));
   const uint32_t tab_base = (raw + (uint32_t)kTabBytes - 1u) & ~((uint32_t)kTabBytes - 1u);
@@ -143,33 +148,19 @@ nf4_quantize64_kernel(const __grid_constant__ QuantBatch batch, const __grid_con
   const int64_t warp_global = (int64_t)blockIdx.x * (kQuantThreads / 32) + (threadIdx.x >> 5);
   const int64_t warp_stride = (int64_t)gridDim.x * (kQuantThreads / 32);
 
-  const int64_t n_chunks = batch.chunk_end[batch.n - 1];
-  // tensor of a chunk: the table index only moves forward along a warp's walk
-  int t_cur = 0, t_nxt = 0;
-  auto locate = [&](int64_t chunk, int& t) -> int64_t {  // -> first element of the chunk inside its tensor
-    while (chunk >= batch.chunk_end[t]) ++t;
-    return (chunk - (t > 0 ? batch.chunk_end[t - 1] : 0)) * kChunkElems + lane * 8;
-  };
-
   // register double buffering: the loads of the warp's NEXT chunk are in flight while this one is encoded
   Vec8<T> v[kQuantUnroll], nxt[kQuantUnroll];
-  int64_t base = 0, base_nxt = 0;
   if (warp_global < n_chunks) {
-    base = locate(warp_global, t_cur);
-    t_nxt = t_cur;
-    const T* w = static_cast<const T*>(batch.w[t_cur]);
 #pragma unroll
-    for (int u = 0; u < kQuantUnroll; ++u) v[u].load(w + base + u * kWarpElems);
+    for (int u = 0; u < kQuantUnroll; ++u) v[u].load(w + warp_global * kChunkElems + lane * 8 + u * kWarpElems);
   }
   for (int64_t chunk = warp_global; chunk < n_chunks; chunk += warp_stride) {
+    const int64_t base = chunk * kChunkElems + lane * 8;
     if (chunk + warp_stride < n_chunks) {
-      base_nxt = locate(chunk + warp_stride, t_nxt);
-      const T* w = static_cast<const T*>(batch.w[t_nxt]);
 #pragma unroll
-      for (int u = 0; u < kQuantUnroll; ++u) nxt[u].load(w + base_nxt + u * kWarpElems);
+      for (int u = 0; u < kQuantUnroll; ++u)
+        nxt[u].load(w + (chunk + warp_stride) * kChunkElems + lane * 8 + u * kWarpElems);
     }
-    uint32_t* packed_words = batch.packed[t_cur];
-    float* absmax = batch.absmax[t_cur];
 #pragma unroll
     for (int u = 0; u < kQuantUnroll; ++u) {
       float f[8];
@@ -203,8 +194,6 @@ nf4_quantize64_kernel(const __grid_constant__ QuantBatch batch, const __grid_con
     }
 #pragma unroll
     for (int u = 0; u < kQuantUnroll; ++u) v[u] = nxt[u];
-    t_cur = t_nxt;
-    base = base_nxt;
   }
 }
 
@@ -239,14 +228,16 @@ __global__ void nf4_quantize_generic_kernel(const T* __restrict__ w, int64_t sta
 }
 
 template <typename T>
-static int launch_quant_batch(const QuantBatch& b, cudaStream_t st) {
+static int launch_quant_batch(const QuantBatch& b, int count, int64_t n_chunks, cudaStream_t st) {
   static const CellTable table = make_cell_table();
-  const int64_t n_chunks = b.chunk_end[b.n - 1];
   const int warps_per_block = kQuantThreads / 32;
-  int64_t blocks = ceil_div64(n_chunks, warps_per_block);
-  const int64_t max_blocks = 148 * 6;  // 6 resident CTAs of 256 threads per SM (32 KB of shared memory each)
-  if (blocks > max_blocks) blocks = max_blocks;
-  nf4_quantize64_kernel<T><<<(unsigned)blocks, kQuantThreads, 2 * kTabBytes, st>>>(b, table);
+  // grid.x CTAs walk one tensor with the grid stride; about eight waves of resident CTAs over the whole group
+  const int64_t resident = 148 * 6;  // 6 CTAs of 256 threads per SM by shared memory (32 KB each)
+  int64_t gx = ceil_div64(n_chunks, warps_per_block);
+  int64_t cap = count == 1 ? resident : (8 * resident) / count;
+  if (cap < 8) cap = 8;
+  if (gx > cap) gx = cap;
+  nf4_quantize64_kernel<T><<<dim3((unsigned)gx, (unsigned)count), kQuantThreads, 2 * kTabBytes, st>>>(b, n_chunks, table);
   VFT_CUDA_OK(cudaGetLastError());
   return VFT_OK;
 }
@@ -272,34 +263,36 @@ static int64_t fast_elems(const void* w, int64_t n, int blocksize, const uint8_t
 template <typename T>
 static int quantize_many_typed(int count, const void* const* ws, const int64_t* ns, int blocksize, uint8_t* const* packed,
                                float* const* absmax, cudaStream_t st) {
-  QuantBatch b;
-  b.n = 0;
-  int64_t chunks = 0;
-  auto flush = [&]() -> int {
-    if (b.n == 0) return VFT_OK;
-    const int rc = launch_quant_batch<T>(b, st);
-    b.n = 0;
-    chunks = 0;
-    return rc;
-  };
+  // groups of equal fast-path size, in order of first appearance (model checkpoints repeat a handful of shapes)
+  std::vector<char> done((size_t)count, 0);
   for (int i = 0; i < count; ++i) {
-    if (ns[i] == 0) continue;
-    const int64_t n_main = fast_elems(ws[i], ns[i], blocksize, packed[i]);
-    if (n_main > 0) {
-      chunks += n_main / kChunkElems;
-      b.w[b.n] = ws[i];
-      b.packed[b.n] = reinterpret_cast<uint32_t*>(packed[i]);
-      b.absmax[b.n] = absmax[i];
-      b.chunk_end[b.n] = chunks;
-      if (++b.n == kQuantBatch) {
-        const int rc = flush();
-        if (rc != VFT_OK) return rc;
+    if (done[i]) continue;
+    const int64_t n_main = ns[i] > 0 ? fast_elems(ws[i], ns[i], blocksize, packed[i]) : 0;
+    QuantBatch b;
+    int k = 0;
+    for (int j = i; j < count; ++j) {
+      if (done[j] || ns[j] == 0) { done[j] = 1; continue; }
+      if (fast_elems(ws[j], ns[j], blocksize, packed[j]) != n_main) continue;
+      done[j] = 1;
+      if (n_main > 0) {
+        b.w[k] = ws[j];
+        b.packed[k] = reinterpret_cast<uint32_t*>(packed[j]);
+        b.absmax[k] = absmax[j];
+        if (++k == kQuantBatch) {
+          const int rc = launch_quant_batch<T>(b, k, n_main / kChunkElems, st);
+          if (rc != VFT_OK) return rc;
+          k = 0;
+        }
       }
+      const int rc = quantize_rest(static_cast<const T*>(ws[j]), n_main, ns[j], blocksize, packed[j], absmax[j], st);
+      if (rc != VFT_OK) return rc;
     }
-    const int rc = quantize_rest(static_cast<const T*>(ws[i]), n_main, ns[i], blocksize, packed[i], absmax[i], st);
-    if (rc != VFT_OK) return rc;
+    if (k > 0) {
+      const int rc = launch_quant_batch<T>(b, k, n_main / kChunkElems, st);
+      if (rc != VFT_OK) return rc;
+    }
   }
-  return flush();
+  return VFT_OK;
 }
 
 int launch_quantize_many(int count, const void* const* w, int dtype, const int64_t* n, int blocksize,

@@ -111,8 +111,8 @@ def nf4_quantize(w: torch.Tensor, blocksize: int = 64) -> tuple[torch.Tensor, to
 
 
 def nf4_quantize_many(ws: "list[torch.Tensor]", blocksize: int = 64) -> "list[tuple[torch.Tensor, torch.Tensor]]":
-    """``nf4_quantize`` for a list of CUDA tensors of ONE dtype on one device: up to 96 tensors per launch
-    (``vft_nf4_quantize_many``), bit-identical to the per-tensor calls.  This is what a checkpoint wants: the small
+    """``nf4_quantize`` for a list of CUDA tensors of ONE dtype on one device: up to 96 equal-size tensors per
+    launch (``vft_nf4_quantize_many``), bit-identical to the per-tensor calls.  This is what a checkpoint wants: the small
     weights of a model otherwise spend more time in launch latency than in the kernel."""
     import ctypes
 
