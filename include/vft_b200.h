@@ -14,7 +14,9 @@
  *     activations, workspace) belongs to the caller and is borrowed for the
  *     duration of the call on the given stream.  The only process-wide state is
  *     the triage switches at the end of this header (forced kernel family,
- *     VFT_* environment variables read once at first use);
+ *     VFT_* environment variables read once at first use) and, on the device,
+ *     a pool of 4096 self-resetting {arrivals, generation} counters that the
+ *     launches with an in-kernel side product take in turn;
  *   - re-entrant and callable from any host thread (autograd worker threads call
  *     the backward entry points); the current CUDA device is the caller's;
  *   - every function returns 0 on success or a negative vft_status; the message
@@ -68,8 +70,12 @@ void vft_force_path(int path);
 /* Triage (tests / profiling tools, not thread-safe): re-read the VFT_* environment switches, which are otherwise
  * read once per process; SM-clock timelines of the last launch made with VFT_TC_DEBUG & 16 (rows x 256 / 16 stamps). */
 void vft_reload_env(void);
+int vft_debug_tc_timeline(unsigned long long* out, int n);  /* one-tile kernel (csrc/qlora_tc.cu): 16 stamps */
 int vft_debug_tc2_timeline(unsigned long long* out, int n);
 int vft_debug_side_timeline(unsigned long long* out, int n);
+/* Raw side-product accumulator lanes of CTA pair 0 of the last launch made with VFT_TC_DEBUG & 512 (the TMEM layout
+ * probe of tools/p0_layout_probe.py): out[2 CTAs][128 lanes][32 columns] fp32. */
+int vft_debug_tc2_p0dump(float* out, int n);
 
 /* NF4 quantize/pack.  Replaces bitsandbytes.functional.quantize_4bit(quant_type="nf4")
  * as called at /root/reference/src/modules/quant/functional.py:362-365 and, lazily, by

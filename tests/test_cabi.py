@@ -34,6 +34,16 @@ def test_header_symbols_are_exported(cabi):
     assert sorted(cabi.SYMBOLS) == declared, "ctypes binding and header disagree"
 
 
+def test_every_exported_symbol_is_declared(cabi):
+    """The reverse direction: nothing named vft_* leaves the library without a declaration in the header."""
+    import subprocess
+
+    lib_path = os.path.join(os.path.dirname(cabi.__file__), "libvft_b200.so")
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True, check=True).stdout
+    exported = sorted({ln.split()[-1] for ln in out.splitlines() if ln.split() and ln.split()[-1].startswith("vft_")})
+    assert exported == _declared_symbols()
+
+
 def test_abi_version(cabi):
     assert cabi.lib.vft_abi_version() == cabi.ABI_VERSION == 7
 

@@ -206,3 +206,57 @@ def test_gradient_checkpointing_reenters_the_function():
     assert torch.equal(g_plain[-1], g_ckpt[-1])  # dX: deterministic kernels
     for a, b in zip(g_plain[:-1], g_ckpt[:-1]):  # dA/dB: fp32 atomics -> summation order varies
         assert float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20)) < 5e-3
+
+
+@pytest.mark.gpu
+def test_use_bias_adapter_takes_the_fused_path():
+    """LoRAConfig(use_bias=True): lora_up carries a bias (/root/reference/src/modules/peft/lora.py:52-60).  s * bias rides
+    the fused epilogue's per-feature scalar; y, dx and the gradients of A, B and the bias against the reference's own
+    composition base + lora_up(lora_down(x)) * (alpha / rank) in fp64."""
+    from src.modules.quant import quantize_inplace
+    from vft_b200 import ops
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.linear = nn.Linear(256, 384, bias=True, dtype=torch.bfloat16)
+
+        def forward(self, x):
+            return self.linear(x)
+
+    torch.manual_seed(1)
+    model = M()
+    quantize_inplace(model, "bnb_nf4", include_keys=["linear"])
+    model.cuda()
+    PeftTargetConfig(config=LoRAConfig(rank=8, alpha=4.0, use_bias=True, dtype="bfloat16"), include_keys=["linear"]).replace_to_peft_layer(
+        model, freeze_base=True)
+    layer = model.linear
+    assert layer.lora_up.bias is not None
+    with torch.no_grad():
+        layer.lora_up.weight.normal_(std=0.05)
+        layer.lora_up.bias.normal_(std=0.5)
+    x = torch.randn(3, 50, 256, dtype=torch.bfloat16, device="cuda", requires_grad=True)
+    assert layer._can_fuse(x)
+    y = model(x)
+    assert ops.last_path() == 1  # tcgen05
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    # fp64 truth of the reference's composition on the dequantized weight
+    wd = layer.linear.dequantized_weight().double() if hasattr(layer.linear, "dequantized_weight") else None
+    if wd is None:
+        from vft_b200.nn import dequantize_4bit
+        wd = dequantize_4bit(layer.linear.weight.data, layer.linear.weight.quant_state).double()
+    xd = x.detach().double().requires_grad_(True)
+    A = layer.lora_down.weight.detach().double().requires_grad_(True)
+    B = layer.lora_up.weight.detach().double().requires_grad_(True)
+    b = layer.lora_up.bias.detach().double().requires_grad_(True)
+    s = 4.0 / 8
+    yt = xd @ wd.t() + layer.linear.bias.detach().double() + ((xd @ A.t()) @ B.t() + b) * s
+    yt.backward(dy.double())
+    rel = lambda a_, b_: float((a_.double() - b_).norm() / b_.norm())
+    assert rel(y.detach(), yt.detach()) < 4e-3
+    assert rel(x.grad, xd.grad) < 4e-3
+    assert rel(layer.lora_down.weight.grad, A.grad) < 6e-3
+    assert rel(layer.lora_up.weight.grad, B.grad) < 6e-3
+    assert rel(layer.lora_up.bias.grad, b.grad) < 6e-3
+    assert layer.linear.bias.grad is None and layer.linear.weight.grad is None

@@ -1114,7 +1114,11 @@ static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a,
       const double waves = (double)ceil_div64(tiles * split, n_pairs);
       const double tok_live = (double)(tok < T ? tok : T);
       const double epi = split > 1 ? 50.0 * tok_live + 5000.0 + (double)(split * T * OUT) * 4.0 / 1500.0 : 20.0 * tok;
-      const double cost = waves * ((k_per + (r > 0 ? 1 : 0)) * step + 2500.0 + epi);
+      // (the adapter's single ring step is left out on purpose: the plan -- above all whether and where the contraction
+      //  is split, i.e. the order of the fp32 sums -- must not depend on r, so that a layer whose lora_up is still zero
+      //  returns exactly what the bare base layer returns: /root/reference/tests/test_peft.py:98-101)
+      (void)r;
+      const double cost = waves * (k_per * step + 2500.0 + epi);
       if (cost < best_cost * 0.999 || (cost < best_cost * 1.001 && N_acc > best.cfg.N_acc)) {
         best_cost = cost;
         best.cfg = {n_acc, N_acc, max_stages(tmem_a, n_acc, N_acc, rp), cost};
@@ -1199,9 +1203,7 @@ static Tc2Choice choose_tc2(const LayerArgs& a, bool backward, int n_pairs) {
     const double cyc_per_us = 1900.0;
     const double side_cyc = cyc_per_us * (3.5 + (double)a.T * (double)RED * 2.0 / 3.2e6);
     const double dab_cyc = backward ? cyc_per_us * (4.0 + (double)a.T * (double)(a.N + a.K) * 2.0 / 3.9e6) : 0.0;
-    Tc2Plan base = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs);
-    if (base.n_split > 1 && (!ws_ok || a.ws_bytes < base.ws_bytes))
-      base = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs, /*allow_split=*/false);
+    const Tc2Plan base = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs);  // (whether or not a workspace was passed)
     const double base_cost = base.cfg.cost + side_cyc + dab_cyc;
     // dA/dB job: everything it reads and writes is there, TMA can address the transposed side products (row stride
     // T * 2 bytes), and a second block of r_pad accumulator columns is free
@@ -1232,7 +1234,9 @@ static Tc2Choice choose_tc2(const LayerArgs& a, bool backward, int n_pairs) {
         best_c = k;
       }
     }
-    if (best_cost < 1e300 && (ev.tc2_fuse == 1 || best_cost <= base_cost)) return best_c;
+    // a problem small enough to be split along the contraction keeps its (then tiny) side kernels: with and without
+    // an adapter it must add its fp32 partial sums in the same order (see plan_tc2)
+    if (best_cost < 1e300 && (ev.tc2_fuse == 1 || (best_cost <= base_cost && base.n_split == 1))) return best_c;
     c.rp = 0;
   }
   c.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs);

@@ -85,7 +85,9 @@ class LoRALinear(PeftLayer):
             return False
         if isinstance(self.dropout, nn.Dropout) and self.dropout.training and self.dropout.p > 0:
             return False  # adapter sees dropout(x), base sees x: operands differ
-        if self.lora_up.bias is not None or self.rank > 64:
+        if self.rank > 64:
+            return False
+        if self.lora_up.bias is not None and self.lora_up.bias.dtype != self.lora_up.weight.dtype:
             return False
         act = self.linear._cast_input(x).dtype
         return self.lora_down.weight.dtype == act and self.lora_up.weight.dtype == act
@@ -95,7 +97,11 @@ class LoRALinear(PeftLayer):
             return self.linear(x)
         if self._can_fuse(x):
             scale = self._scale_value()
-            return self.linear.forward_with_lora(x, self.lora_down.weight, self.lora_up.weight, scale)
+            # use_bias (lora.py:52-60 of the reference: a bias on lora_up): (t . B^T + b) * s = s * t . B^T + s * b, so
+            # s * b joins the base bias as the per-feature scalar the fused epilogue adds; its gradient (the column sum
+            # of dy) comes back through the operator's bias input
+            up_bias = self.lora_up.bias * scale if self.lora_up.bias is not None else None
+            return self.linear.forward_with_lora(x, self.lora_down.weight, self.lora_up.weight, scale, up_bias)
         # composition of the reference (lora.py:92-104) for bases/dtypes the fused path does not take
         base = self.linear(x)
         down = self.lora_down(self.dropout(x))

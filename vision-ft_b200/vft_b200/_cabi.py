@@ -30,8 +30,10 @@ SYMBOLS = {
     "vft_last_path": (_i, []),
     "vft_force_path": (None, [_i]),
     "vft_reload_env": (None, []),
+    "vft_debug_tc_timeline": (_i, [_p, _i]),
     "vft_debug_tc2_timeline": (_i, [_p, _i]),
     "vft_debug_side_timeline": (_i, [_p, _i]),
+    "vft_debug_tc2_p0dump": (_i, [_p, _i]),
     "vft_nf4_quantize": (_i, [_p, _i, _i64, _i, _p, _p, _p]),
     "vft_nf4_quantize_many": (_i, [_i, _p, _i, _p, _i, _p, _p, _p]),
     "vft_nf4_dequantize": (_i, [_p, _p, _i64, _i, _p, _i, _p]),

@@ -389,12 +389,17 @@ class Linear4bit(nn.Linear):
                                blocksize, qdtype, tiled)
         return out if out.dtype == inp_dtype else out.to(inp_dtype)
 
-    def forward_with_lora(self, x: torch.Tensor, lora_a: torch.Tensor, lora_b: torch.Tensor, scale: float) -> torch.Tensor:
-        """One fused kernel sequence for base + adapter (used by LoRALinear)."""
+    def forward_with_lora(self, x: torch.Tensor, lora_a: torch.Tensor, lora_b: torch.Tensor, scale: float,
+                          extra_bias: torch.Tensor | None = None) -> torch.Tensor:
+        """One fused kernel sequence for base + adapter (used by LoRALinear).  ``extra_bias`` [out_features] (may
+        require grad) is added to the layer's own bias: one per-feature scalar in the kernel's epilogue."""
         packed, absmax, blocksize, qdtype, tiled = self._operands()
         inp_dtype = x.dtype
         x = self._cast_input(x)
-        out = ops.qlora_linear(x, packed, absmax, self.bias, lora_a, lora_b, scale, self.out_features,
+        bias = self.bias
+        if extra_bias is not None:
+            bias = extra_bias.to(x.dtype) if bias is None else bias.to(x.dtype) + extra_bias.to(x.dtype)
+        out = ops.qlora_linear(x, packed, absmax, bias, lora_a, lora_b, scale, self.out_features,
                                self.in_features, blocksize, qdtype, tiled)
         return out if out.dtype == inp_dtype else out.to(inp_dtype)
 

@@ -297,6 +297,8 @@ class QLoRALinearFunction(torch.autograd.Function):
         T = dy2.shape[0]
         need_dx = ctx.needs_input_grad[0]
         need_ab = r > 0 and (ctx.needs_input_grad[4] or ctx.needs_input_grad[5])
+        # a trainable bias (LoRA use_bias: s * lora_up.bias rides the epilogue's bias): column sum of dy, fp32 accumulation
+        dbias = dy2.sum(0, dtype=torch.float32).to(dy2.dtype) if ctx.needs_input_grad[3] else None
         # allocated in the input's shape: a reshaped view would make AccumulateGrad clone it (25 MB at config #1)
         dx = torch.empty(x_shape, dtype=dy2.dtype, device=dev) if need_dx else None
         dt_save = torch.empty((T, LORA_LD), dtype=dy2.dtype, device=dev) if r else None
@@ -304,7 +306,7 @@ class QLoRALinearFunction(torch.autograd.Function):
         if T == 0:  # empty batch: no launches; the adapter gradients of an empty sum are zeros
             if need_ab:
                 da, db = torch.zeros_like(lora_a), torch.zeros_like(lora_b)
-            return dx, None, None, None, da, db, None, None, None, None, None, None
+            return dx, None, None, dbias, da, db, None, None, None, None, None, None
         if need_dx and need_ab:
             # the whole backward in one C-ABI call (one launch when the persistent tcgen05 kernel takes it)
             da = torch.empty_like(lora_a)
@@ -319,7 +321,7 @@ class QLoRALinearFunction(torch.autograd.Function):
                         _stream(),
                     )
                 )
-            return dx, None, None, None, da, db, None, None, None, None, None, None
+            return dx, None, None, dbias, da, db, None, None, None, None, None, None
         with _on_device(dev):
             if need_dx or need_ab:
                 ws, ws_bytes = _workspace(_cabi.OP_BWD_DX, T, N, K, r, dev) if need_dx else (None, 0)
@@ -341,7 +343,7 @@ class QLoRALinearFunction(torch.autograd.Function):
                         da.data_ptr(), db.data_ptr(), ws.data_ptr(), ws_bytes, _stream(),
                     )
                 )
-        return dx, None, None, None, da, db, None, None, None, None, None, None
+        return dx, None, None, dbias, da, db, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------- torch.library registration
@@ -464,7 +466,8 @@ def _op_backward(ctx, dy, _dt_save, _dbt_save, _dtt_save):
     need_ab = lora_a is not None and (ctx.needs_input_grad[4] or ctx.needs_input_grad[5])
     dx, da, db = _qlora_bwd_op(dy, x, packed, absmax, lora_a, lora_b, t_save, bt_save, tt_save, scale, N, K, blocksize, qdtype,
                                codes_t, absmax_t, need_dx, need_ab)
-    return (dx if need_dx else None, None, None, None, da if need_ab else None, db if need_ab else None,
+    dbias = dy.reshape(-1, N).sum(0, dtype=torch.float32).to(dy.dtype) if ctx.needs_input_grad[3] else None
+    return (dx if need_dx else None, None, None, dbias, da if need_ab else None, db if need_ab else None,
             None, None, None, None, None, None, None)
 
 
