@@ -25,7 +25,7 @@ class Attn(nn.Module):
     def forward(self, x, context=None):
         ctx = x if context is None else context
         q, k, v = self.to_q(x), self.to_k(ctx), self.to_v(ctx)  # the model code stays as it is
-        h = q * torch.sigmoid(torch.cat([k, v], -1))
+        h = q * torch.sigmoid(torch.cat([k, v], -1).mean(1, keepdim=True))  # (stand-in for attention over ctx)
         return self.to_out(h)
 
 

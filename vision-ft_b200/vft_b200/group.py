@@ -60,7 +60,6 @@ class ProjectionGroup:
             raise ValueError(f"members read different input widths: {sorted(k)}")
         self.members = list(members)
         self.names = list(names) if names is not None else [str(i) for i in range(len(members))]
-        self.bases: list[Linear4bit] = bases  # type: ignore[assignment]
         self.in_features = bases[0].in_features
         self.sizes = [b.out_features for b in bases]
         self.out_features = sum(self.sizes)
@@ -69,11 +68,16 @@ class ProjectionGroup:
         self.launches = 0     # group launches served (tests / census)
         self.fallbacks = 0
 
+    @property
+    def bases(self) -> "list[Linear4bit]":
+        return [_base_of(m) for m in self.members]  # type: ignore[misc]
+
     # ------------------------------------------------------------------ stacked operands (derived, rebuilt on change)
     def _operands(self):
-        per = [b._operands() for b in self.bases]
+        bases = self.bases
+        per = [b._operands() for b in bases]
         key = tuple((p[0].data_ptr(), p[0]._version, p[1].data_ptr(), p[1]._version) for p in per) + tuple(
-            (None if b.bias is None else (b.bias.data_ptr(), b.bias._version)) for b in self.bases)
+            (None if b.bias is None else (b.bias.data_ptr(), b.bias._version)) for b in bases)
         if self._stacked is not None and self._stacked[0] == key:
             return self._stacked[1]
         blocksize, qdtype = per[0][2], per[0][3]
@@ -85,9 +89,9 @@ class ProjectionGroup:
         absmax = torch.cat([p[1].reshape(-1) for p in per])
         tiled = ops.nf4_tile_weight(packed, absmax, self.out_features, self.in_features, blocksize)
         bias = None
-        if any(b.bias is not None for b in self.bases):
-            ref = next(b.bias for b in self.bases if b.bias is not None)
-            bias = torch.cat([b.bias.detach() if b.bias is not None else ref.new_zeros(n) for b, n in zip(self.bases, self.sizes)])
+        if any(b.bias is not None for b in bases):
+            ref = next(b.bias for b in bases if b.bias is not None)
+            bias = torch.cat([b.bias.detach() if b.bias is not None else ref.new_zeros(n) for b, n in zip(bases, self.sizes)])
         out = (packed, absmax, blocksize, qdtype, tiled, bias)
         self._stacked = (key, out)
         return out
@@ -194,7 +198,6 @@ class ProjectionGroup:
         memo[id(self)] = new
         new.members = [copy.deepcopy(m, memo) for m in self.members]
         new.names = list(self.names)
-        new.bases = [_base_of(m) for m in new.members]
         new.in_features, new.sizes, new.out_features = self.in_features, list(self.sizes), self.out_features
         new._stacked = None
         new._pending = None
