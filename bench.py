@@ -474,7 +474,9 @@ def run_gpu_arm(args):
     h2d = hx[0].numel() * 2 + hdy[0].numel() * 2
     d2h = hga2[0].numel() * 2 + hgb2[0].numel() * 2
 
-    # ---- roofline: the fused tcgen05 GEMM alone (NF4-only call = exactly one launch), forward and backward
+    # ---- roofline: the two launches of the step, timed alone through the C ABI: forward with the adapter's side
+    # product inside (vft_qlora_fwd, r = 16) and the whole backward in one launch (vft_qlora_bwd: dx, dt, dA, dB); the
+    # NF4-only launches (r = 0) are timed next to them
     roof = None
     if rank == 0:
         w = layer.linear.weight
@@ -487,14 +489,35 @@ def run_gpu_arm(args):
         absmax = qs.absmax_f32()
         tiles = ops.nf4_tile_weight(w.data, absmax, N_FEAT, K_FEAT)  # same derived copy the module path uses
         tc_ptr, ta_ptr = (tiles[0].data_ptr(), tiles[1].data_ptr()) if tiles else (None, None)
+        la, lb = layer.lora_down.weight.detach(), layer.lora_up.weight.detach()
+        sc = float(layer._scale_value())
+        rp = 16 * ((RANK + 15) // 16)
+        tsk = torch.zeros(T, 64, device=dev, dtype=torch.bfloat16)
+        dtsk = torch.zeros(T, 64, device=dev, dtype=torch.bfloat16)
+        btk = torch.empty(rp, N_FEAT, device=dev, dtype=torch.bfloat16)
+        ttk = torch.empty(rp, T, device=dev, dtype=torch.bfloat16)
+        dak, dbk = torch.empty_like(la), torch.empty_like(lb)
+        wsb = _cabi.lib.vft_workspace_bytes(_cabi.OP_BWD, T, N_FEAT, K_FEAT, RANK)
+        wsk = torch.empty(max(wsb, 4), dtype=torch.uint8, device=dev)
 
-        def k_fwd(i):
+        def k_fwd0(i):
             _cabi.check(_cabi.lib.vft_qlora_fwd(xk[i % n_sets].data_ptr(), T, w.data_ptr(), absmax.data_ptr(), N_FEAT, K_FEAT, 64,
                                                 _cabi.BF16, _cabi.BF16, None, None, None, 0, 0.0, yk.data_ptr(), None, None, None, None, 0, tc_ptr, ta_ptr, st))
 
-        def k_bwd(i):
+        def k_bwd0(i):
             _cabi.check(_cabi.lib.vft_qlora_bwd_dx(gk[i % n_sets].data_ptr(), T, w.data_ptr(), absmax.data_ptr(), N_FEAT, K_FEAT, 64,
                                                    _cabi.BF16, _cabi.BF16, None, None, 0, 0.0, dxk.data_ptr(), None, None, None, 0, tc_ptr, ta_ptr, st))
+
+        def k_fwd(i):
+            _cabi.check(_cabi.lib.vft_qlora_fwd(xk[i % n_sets].data_ptr(), T, w.data_ptr(), absmax.data_ptr(), N_FEAT, K_FEAT, 64,
+                                                _cabi.BF16, _cabi.BF16, None, la.data_ptr(), lb.data_ptr(), RANK, sc, yk.data_ptr(),
+                                                tsk.data_ptr(), btk.data_ptr(), ttk.data_ptr(), None, 0, tc_ptr, ta_ptr, st))
+
+        def k_bwd(i):
+            _cabi.check(_cabi.lib.vft_qlora_bwd(gk[i % n_sets].data_ptr(), xk[i % n_sets].data_ptr(), T, w.data_ptr(), absmax.data_ptr(),
+                                                N_FEAT, K_FEAT, 64, _cabi.BF16, _cabi.BF16, la.data_ptr(), lb.data_ptr(), RANK, sc,
+                                                tsk.data_ptr(), ttk.data_ptr(), btk.data_ptr(), dxk.data_ptr(), dak.data_ptr(), dbk.data_ptr(),
+                                                dtsk.data_ptr(), wsk.data_ptr(), wsb, tc_ptr, ta_ptr, st))
 
         def time_kernel(fn, iters=50):
             for i in range(5):
@@ -508,19 +531,24 @@ def run_gpu_arm(args):
             torch.cuda.synchronize()
             return a.elapsed_time(b) / iters
 
+        t_f0, t_b0 = time_kernel(k_fwd0), time_kernel(k_bwd0)
         t_f, t_b = time_kernel(k_fwd), time_kernel(k_bwd)
         assert ops.last_path() == _cabi.PATH_TCGEN05, "roofline kernel is not the tcgen05 path"
         flops_launch = 2 * T * N_FEAT * K_FEAT
-        achieved = 2 * flops_launch / ((t_f + t_b) * 1e-3) / 1e12
+        lora_f, lora_b = 2 * T * RANK * (N_FEAT + K_FEAT), 4 * T * RANK * (N_FEAT + K_FEAT)
+        achieved = (2 * flops_launch + lora_f + lora_b) / ((t_f + t_b) * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": UNIT,
                 "frac": achieved / peaks["bf16_tflops"],
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
-                # kernel (profiles/r01_ncu_pair_kernel_final.txt: 30.5 MB read + 0.3-0.7 MB written; the 25 MB of output
-                # stay in the 126 MB L2 past the end of the launch).  Algorithmic minimum x + y + packed W: 55.9 MB.
-                "traffic": 31.0e6, "traffic_source": "ncu dram bytes per launch (read + write, mean of forward and backward), profiles/r01_ncu_pair_kernel_final.txt",
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of these two
+                # launches (profiles/r02_ncu_tc2_fused.txt: forward 31.1 MB read + 0.9 MB written, backward 58.1 + 3.3 MB --
+                # it also reads x for dA; the 25 MB of output stay in the 126 MB L2 past the end of the launch).
+                # Algorithmic minimum: forward x + y + packed W = 55.9 MB, backward dy + x + dx + packed W = 81 MB.
+                "traffic": 46.7e6, "traffic_source": "ncu dram bytes per launch (read + write, mean of the forward and the backward launch), profiles/r02_ncu_tc2_fused.txt",
                 "peak_source": peaks["source"] + ", burst",
-                "kernel": "qlora_tc2_kernel (persistent CTA-pair tcgen05 GEMM; forward + backward launches)",
-                "fwd_us": t_f * 1e3, "bwd_us": t_b * 1e3, "flops_per_launch": flops_launch}
+                "kernel": "qlora_tc2_kernel as launched in the step: forward <adapter side product inside>, backward <side product + dA/dB job inside> (persistent CTA-pair tcgen05 GEMM)",
+                "fwd_us": t_f * 1e3, "bwd_us": t_b * 1e3, "flops_per_launch": flops_launch + (lora_f + lora_b) / 2,
+                "nf4_only": {"fwd_us": t_f0 * 1e3, "bwd_us": t_b0 * 1e3, "tflops": 2 * flops_launch / ((t_f0 + t_b0) * 1e-3) / 1e12,
+                             "frac": 2 * flops_launch / ((t_f0 + t_b0) * 1e-3) / 1e12 / peaks["bf16_tflops"]}}
 
     # ---- secondary figures of merit (same run, rank 0): quantize/pack GB/s, small-T weight-stream GB/s
     extra = {}
@@ -630,6 +658,18 @@ def run_gpu_arm(args):
                               "note": what + "; forward x2 (checkpointing) + backward, each layer at its own token count"}
         except Exception as e:  # pragma: no cover - reported, not hidden
             extra["auraflow_qlora_step_linear_layers"] = {"error": f"{type(e).__name__}: {e}"}
+        try:  # sibling projections as one launch (vft_b200/group.py), module API, forward + backward
+            import group_probe
+
+            rows = [group_probe.time_case(nm, k, ns, t, r, verbose=False) for nm, k, ns, t, r in (
+                ("sdxl C1280 attn1 to_q/k/v", 1280, [1280] * 3, 2048, 4), ("sdxl C1280 attn1 to_q/k/v", 1280, [1280] * 3, 2048, 16),
+                ("sdxl C640 attn1 to_q/k/v", 640, [640] * 3, 8192, 4), ("sdxl C1280 attn2 to_k/v (2 x 77 text tokens)", 2048, [1280] * 2, 154, 4))]
+            extra["projection_groups"] = {
+                "cases": [{**r_, "speedup": r_["members_us"] / r_["group_us"]} for r_ in rows],
+                "note": "q/k/v (k/v) LoRALinear-over-Linear4bit siblings, forward + backward through the module API in a CUDA graph: "
+                        "one launch per member vs one ProjectionGroup launch per direction; LoRA rank 4 is the reference's shipped rank"}
+        except Exception as e:  # pragma: no cover - reported, not hidden
+            extra["projection_groups"] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         cpu = None

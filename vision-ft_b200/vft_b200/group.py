@@ -33,6 +33,13 @@ from . import ops
 from .nn import Linear4bit
 
 LORA_MAX_RANK = 64  # VFT_LORA_LD: the adapter step carries at most 64 rank columns
+# One launch instead of three pays while a launch's fixed cost (~8 us before its first MMA) matters: measured on B200
+# (tools/group_probe.py, forward + backward through the module API, rank 4 / 16): SDXL C1280 q/k/v at 2048 tokens
+# x1.37 / x0.99, C640 at 8192 tokens x1.33 / x1.13, text-token k/v x1.34 / x1.21; at AuraFlow's sizes (494 GFLOP per
+# q/k/v forward) the members already run near the tensor roofline and the group LOSES 1-8 %: autograd hands the
+# backward three separate dy tensors, and stacking them costs a pass over T x (N1+N2+N3) that the summed dx does not
+# win back.  Groups above this much forward work therefore leave their members alone.
+MAX_GROUP_GFLOP = 80.0
 
 
 def _base_of(m: nn.Module) -> Linear4bit | None:
@@ -67,6 +74,7 @@ class ProjectionGroup:
         self._pending = None  # (x kept alive, outputs, taken flags, grad mode)
         self.launches = 0     # group launches served (tests / census)
         self.fallbacks = 0
+        self.max_gflop = MAX_GROUP_GFLOP
 
     @property
     def bases(self) -> "list[Linear4bit]":
@@ -100,6 +108,9 @@ class ProjectionGroup:
     def _mode(self, x: torch.Tensor) -> str | None:
         """'lora' / 'base' when one launch can serve every member for this input, None when it cannot."""
         if torch.compiler.is_compiling() or not x.is_cuda:
+            return None
+        tokens = x.numel() // max(x.shape[-1], 1)
+        if 2.0 * tokens * self.in_features * self.out_features > self.max_gflop * 1e9:
             return None
         adapters = [_is_adapter(m) for m in self.members]
         if not any(adapters):
@@ -202,6 +213,7 @@ class ProjectionGroup:
         new._stacked = None
         new._pending = None
         new.launches = new.fallbacks = 0
+        new.max_gflop = self.max_gflop
         return new
 
 
