@@ -779,3 +779,21 @@ def test_quantize_many_is_bit_identical_to_per_tensor_calls(ops, dt):
     for i in (0, 4, 6):
         po, ao = nf4_oracle.nf4_quantize(ws[i].cpu())
         assert np.array_equal(many[i][0].cpu().numpy().reshape(-1), po.reshape(-1)) and np.array_equal(many[i][1].cpu().numpy(), ao)
+
+
+def test_misaligned_activations_fall_back_to_the_generic_kernels(ops):
+    """A contiguous view that starts 2 bytes into an allocation cannot be a TMA operand: the call is served by the generic
+    kernels (it used to return VFT_ERR_INVALID) and agrees with the tensor path on the aligned copy."""
+    T, K, N, r = 300, 256, 384, 8
+    w, x, dy, a, b, bv = _make_case(T, K, N, r, seed=77)
+    packed, absmax = ops.nf4_quantize(w.cuda())
+    tiles = ops.nf4_tile_weight(packed, absmax, N, K)
+    xa = x.cuda()
+    xm = torch.empty(T * K + 1, device="cuda", dtype=x.dtype)[1:].view(T, K).copy_(xa)
+    assert xm.data_ptr() % 16 != 0 and xm.is_contiguous()
+    ac, bc = a.cuda(), b.cuda()
+    y_al = ops.qlora_linear(xa, packed, absmax, None, ac, bc, 1.0 / r, N, K, 64, torch.bfloat16, tiles)
+    assert ops.last_path() == TC
+    y_mis = ops.qlora_linear(xm, packed, absmax, None, ac, bc, 1.0 / r, N, K, 64, torch.bfloat16, tiles)
+    assert ops.last_path() == SIMT
+    assert qlora_oracle.rel_l2(y_mis.cpu(), y_al.cpu()) <= 6e-3

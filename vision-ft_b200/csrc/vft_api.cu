@@ -37,10 +37,12 @@ static int check_layer(const LayerArgs& a, const void* act, const void* out, boo
   return VFT_OK;
 }
 
-static bool use_tc(const LayerArgs& a, bool backward, int* status) {
+// `act`, `out`: the activation / output pointers of the call -- TMA needs them 16-byte aligned; a misaligned view falls
+// back to the generic kernels like every other shape the tensor maps cannot describe
+static bool use_tc(const LayerArgs& a, bool backward, const void* act, const void* out, int* status) {
   *status = VFT_OK;
   const int forced = forced_path();
-  const bool ok = tc_supported(a, backward);
+  const bool ok = tc_supported(a, backward) && ((reinterpret_cast<uintptr_t>(act) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
   if (forced == VFT_PATH_TCGEN05 && !ok) {
     set_error("tcgen05 path forced but shape/dtype not supported (T=%lld N=%lld K=%lld blocksize=%d dtype=%d)",
               (long long)a.T, (long long)a.N, (long long)a.K, a.blocksize, a.act_dtype);
@@ -224,7 +226,8 @@ int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* 
   if (rc != VFT_OK) return rc;
   VFT_REQUIRE(r == 0 || t_save != nullptr, "t_save is required when r > 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool gemv = (forced_path() == 0 || forced_path() == VFT_PATH_GEMV) && gemv_supported(a);
+  const bool gemv = (forced_path() == 0 || forced_path() == VFT_PATH_GEMV) && gemv_supported(a) &&
+                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0;
   if (!gemv && forced_path() == VFT_PATH_GEMV) {
     set_error("streaming path forced but shape/dtype not supported (T=%lld N=%lld K=%lld)", (long long)T, (long long)N,
               (long long)K);
@@ -232,7 +235,7 @@ int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* 
   }
   bool tc = false;
   if (!gemv) {
-    tc = use_tc(a, false, &rc);
+    tc = use_tc(a, false, x, y, &rc);
     if (rc != VFT_OK) return rc;
   }
   // t_save = x . A^T: inside the GEMM launch when the persistent tcgen05 kernel takes the call unsplit, else a kernel
@@ -274,7 +277,7 @@ int vft_qlora_bwd_dx(const void* dy, int64_t T, const uint8_t* packed, const flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   bool tc = false;
   if (dx != nullptr) {
-    tc = use_tc(a, true, &rc);
+    tc = use_tc(a, true, dy, dx, &rc);
     if (rc != VFT_OK) return rc;
   }
   // dt_save = s * dy . B: inside the GEMM launch when the persistent tcgen05 kernel takes the call unsplit and the
@@ -318,7 +321,7 @@ int vft_qlora_bwd(const void* dy, const void* x, int64_t T, const uint8_t* packe
     a.job_db = dB;
     int rc = check_layer(a, dy, dx);
     if (rc != VFT_OK) return rc;
-    const bool tc = use_tc(a, true, &rc);
+    const bool tc = use_tc(a, true, dy, dx, &rc);
     if (rc != VFT_OK) return rc;
     if (tc && tc_fuses_side(a, true) && tc2_fuses_dab(a)) {
       set_path(VFT_PATH_TCGEN05);
