@@ -630,6 +630,13 @@ def run_gpu_arm(args):
             res = auraflow_step.measure(B=2, steps=4, warmup=2, attention="stub", world=world, rank=rank, group=aura_group)
             if rank == 0:
                 extra["auraflow_qlora_step_dp"] = res
+            if world == 1:
+                # the same step with torch's SDPA (a library call outside the hot path) in place of the attention stand-in:
+                # the figure a user of the whole model would see per GPU
+                torch.cuda.empty_cache()
+                r2 = auraflow_step.measure(B=2, steps=3, warmup=1, attention="sdpa", world=1, rank=0, group=None)
+                extra["auraflow_qlora_step_sdpa"] = {k: r2[k] for k in ("workload", "launch", "ms_per_step", "steps_per_s", "samples_per_s",
+                                                                        "hot_path_tflops_per_gpu", "hot_path_frac_of_sustained_bf16_peak", "mem_gb") if k in r2}
         except Exception as e:  # pragma: no cover - reported, not hidden
             if rank == 0:
                 extra["auraflow_qlora_step_dp"] = {"error": f"{type(e).__name__}: {e}"}
