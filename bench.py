@@ -641,6 +641,18 @@ def run_gpu_arm(args):
             if rank == 0:
                 extra["auraflow_qlora_step_dp"] = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.empty_cache()
+        if world == 1:
+            # BASELINE configs[2]: the Lumina2 NextDiT-2.6B QLoRA step (batch 1 at 1024^2) as a job, same kind of harness
+            # (tools/lumina2_step.py: 178 NF4 Linears, LoRA r=16, checkpointing, fused AdamW, whole step as one CUDA graph)
+            try:
+                import lumina2_step
+
+                torch.cuda.empty_cache()
+                extra["lumina2_qlora_step"] = {att: {k: v for k, v in lumina2_step.measure(1, 4, 2, att).items() if k not in ("adapter_params", "loss")}
+                                               for att in ("stub", "sdpa")}
+            except Exception as e:  # pragma: no cover - reported, not hidden
+                extra["lumina2_qlora_step"] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
 
     if rank == 0 and world == 1 and not args.no_census:
         # second half of BASELINE's metric: every NF4(+LoRA) Linear of one AuraFlow-6.8B QLoRA training step (per-GPU

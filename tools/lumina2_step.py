@@ -155,16 +155,10 @@ def hot_path_flops(model, B):
     return total
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--attention", default="stub", choices=["stub", "sdpa"])
-    ap.add_argument("--eager", action="store_true", help="no CUDA graph: every launch goes through Python")
-    args = ap.parse_args()
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(dev)
+def measure(batch=1, steps=5, warmup=2, attention="stub", eager=False):
+    """One Lumina2 QLoRA step on the current CUDA device; returns the result dict (bench.py's extra, main())."""
+    args = argparse.Namespace(batch=batch, steps=steps, warmup=warmup, attention=attention, eager=eager)
+    dev = torch.device("cuda", torch.cuda.current_device())
     model = build()
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-4, fused=True, capturable=not args.eager)
@@ -223,14 +217,26 @@ def main():
     except Exception:
         pass
     n_q = sum(1 for m in model.modules() if type(m).__name__ == "BnbLinear4bit")
-    print(json.dumps({
+    return {
         "workload": f"Lumina2 NextDiT-2.6B QLoRA step, Linear skeleton (26 + 2 + 2 blocks, {n_q} NF4 Linears), batch {B} at 1024^2 "
                     f"(4096 image + 256 caption tokens), LoRA r={R} on attention + feed_forward (not the noise refiner), "
                     f"gradient checkpointing, fused AdamW, attention={args.attention}",
         "launch": launch_mode, "ms_per_step": ms, "steps_per_s": 1e3 / ms, "hot_path_tflops": flops / (ms * 1e-3) / 1e12,
         "hot_path_frac_of_sustained_bf16_peak": flops / (ms * 1e-3) / 1e12 / peak, "hot_path_flops_per_step": flops,
         "adapter_params": sum(p.numel() for p in params), "loss": float(loss.item()),
-        "mem_gb": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
+        "mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--attention", default="stub", choices=["stub", "sdpa"])
+    ap.add_argument("--eager", action="store_true", help="no CUDA graph: every launch goes through Python")
+    args = ap.parse_args()
+    torch.cuda.set_device(0)
+    print(json.dumps(measure(args.batch, args.steps, args.warmup, args.attention, args.eager)), flush=True)
 
 
 if __name__ == "__main__":
