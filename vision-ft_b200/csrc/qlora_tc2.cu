@@ -27,6 +27,7 @@
 //   warps 16-19 epilogue, one TMEM lane quadrant each
 //   warps 0-15  decode: four groups of 128 threads, group g owns pipeline steps g, g+4, ...
 #include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 #include <type_traits>
@@ -1133,10 +1134,22 @@ static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a,
 }
 
 static int device_pairs() {
-  int dev = 0, n_sm = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  else cudaGetLastError();
-  return n_sm / 2 > 0 ? n_sm / 2 : 1;
+  // (asked several times per call: one attribute query per device and process)
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 74;
+  }
+  if (dev >= 0 && dev < 64) {
+    const int c = cached[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+  }
+  int n_sm = 148;
+  if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cudaGetLastError();
+  const int pairs = n_sm / 2 > 0 ? n_sm / 2 : 1;
+  if (dev >= 0 && dev < 64) cached[dev].store(pairs, std::memory_order_relaxed);
+  return pairs;
 }
 
 // Padded rank of the side product (forward: t = x . A^T, backward: dt = s * dy . B) that the launch computes itself,
@@ -1169,7 +1182,33 @@ static int pairs_for(const Tc2Plan& plan, int n_pairs) {
 
 // Everything the launch is decided by, in one place (the API asks the same function whether the side kernel can be
 // skipped): tile shape, split, side product, grid.
+static Tc2Choice choose_tc2_uncached(const LayerArgs& a, bool backward, int n_pairs);
+
+// One C-ABI call asks up to three times (does the launch compute the side product itself? dA/dB too? then the launch):
+// the last answer of this thread is kept, keyed on everything the decision reads.
 static Tc2Choice choose_tc2(const LayerArgs& a, bool backward, int n_pairs) {
+  struct Key {
+    int64_t T, N, K, ws_bytes;
+    const void *lora_a, *bt_save, *ws, *job_x, *tt_save, *job_dtt, *job_da, *job_db;
+    int r, backward, n_pairs;
+    unsigned env_gen;
+  };
+  static thread_local Key last_key = {};
+  static thread_local Tc2Choice last_choice = {};
+  static thread_local bool have = false;
+  Key k = {};  // (zero-initialised including padding: compared with memcmp)
+  k.T = a.T; k.N = a.N; k.K = a.K; k.ws_bytes = a.ws_bytes;
+  k.lora_a = a.lora_a; k.bt_save = a.bt_save; k.ws = a.ws; k.job_x = a.job_x; k.tt_save = a.tt_save;
+  k.job_dtt = a.job_dtt; k.job_da = a.job_da; k.job_db = a.job_db;
+  k.r = a.r; k.backward = backward ? 1 : 0; k.n_pairs = n_pairs; k.env_gen = env_generation();
+  if (have && memcmp(&k, &last_key, sizeof(Key)) == 0) return last_choice;
+  last_choice = choose_tc2_uncached(a, backward, n_pairs);
+  last_key = k;
+  have = true;
+  return last_choice;
+}
+
+static Tc2Choice choose_tc2_uncached(const LayerArgs& a, bool backward, int n_pairs) {
   const int64_t OUT = backward ? a.K : a.N;
   const int64_t RED = backward ? a.N : a.K;
   const bool tmem_a = !backward;

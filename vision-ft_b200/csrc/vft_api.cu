@@ -86,7 +86,12 @@ static VftEnv& env_mut() {
   return e;
 }
 const VftEnv& env() { return env_mut(); }
-void reload_env() { env_mut().load(); }
+static std::atomic<unsigned> g_env_generation{0};
+unsigned env_generation() { return g_env_generation.load(std::memory_order_relaxed); }
+void reload_env() {
+  env_mut().load();
+  g_env_generation.fetch_add(1, std::memory_order_relaxed);  // invalidates per-thread memoised launch plans
+}
 static bool side_mma() { return env().side_mma; }
 
 }  // namespace vft

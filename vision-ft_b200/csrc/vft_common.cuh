@@ -126,6 +126,7 @@ struct VftEnv {
 };
 const VftEnv& env();
 void reload_env();
+unsigned env_generation();  // bumped by reload_env()
 inline bool pdl_enabled() { return env().pdl; }
 
 // ---------------------------------------------------------------------------
