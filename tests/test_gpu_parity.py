@@ -659,6 +659,8 @@ def test_lumina2_block_shapes_vs_oracle(ops):
 @pytest.mark.parametrize("T,K,N,r,job", [
     (4096, 3072, 3072, 16, True),    # BASELINE config #1: one launch (side product + dA/dB job inside the GEMM)
     (2176, 1280, 1280, 4, True),     # the reference's shipped rank 4, ragged token count (multiple of 8)
+    (2176, 3072, 8192, 16, True),    # N + K = 88 column tiles > SM pairs: two dA/dB units on some pairs
+    (1096, 8192, 3072, 8, True),     # the same the other way round (K = 8192), rank 8
     (1003, 640, 1280, 8, False),     # T % 8 != 0: t^T cannot be a TMA operand -> two calls inside
     (136, 2048, 640, 16, False),     # few tokens: the contraction is split, side kernels + vft_lora_bwd_dab inside
 ])

@@ -76,7 +76,8 @@ struct AccLayout {
 constexpr int kTmemCols = 512;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kMaxStg = 16;  // output staging tiles
-constexpr int kBarBytes = (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg + 2 * kMaxP0 + 2) * 8 + 16;
+constexpr int kMaxJobUnits = 2;  // dA/dB column tiles one pair can take (each in its own block of r_pad TMEM columns)
+constexpr int kBarBytes = (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg + 2 * kMaxP0 + 1 + kMaxJobUnits) * 8 + 16;
 constexpr int kJobBox = 64 * 128;  // dA/dB job: one [64 tokens x 64 columns] box of x / dy per CTA and ring step
 constexpr int kStgBytes = 32 * kBM * 2;  // one staging tile [32 tokens][128 features] of 16-bit outputs (8 KB)
 constexpr int kEpiBytes = 2 * kStgBytes;  // the minimum: two tiles
@@ -134,7 +135,8 @@ struct Tc2Params {
   void* save_t;       // optional: the side product once more, transposed [r_pad, T] (K-major operand of the dA/dB job)
   // dA/dB job (backward launch with its side product inside): the adapter's weight gradients dA = dt^T . x [r, K] and
   // dB = s * dy^T . t [N, r] are contractions over the TOKENS -- one pass over x and one over dy, a kernel of its own
-  // until now (12.9 us + a launch gap at config #1).  Here pair u < job_units takes 128 columns of x (dA) or dy (dB):
+  // until now (12.9 us + a launch gap at config #1).  Here pair u takes 128 columns of x (dA) or dy (dB) -- unit u, and,
+  // when there are more units than pairs (N + K > 128 * pairs: the 8192-wide MLP layers), unit u + pairs as well:
   // after the side product, the same two threads stream [64 tokens x 64 columns] boxes (MN-major A operand) and
   // [r_pad/2 x 64 tokens] boxes of dt^T / t^T (K-major B operand) through the side product's ring and accumulate
   // M = 128, N = r_pad MMAs in spare TMEM columns; the epilogue warps write the result before the last tile's drain.
@@ -219,8 +221,8 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   auto bar_p0_full = [&](int i) { return bar_base + 8u * (kBarP0 + i); };
   auto bar_p0_empty = [&](int i) { return bar_base + 8u * (kBarP0 + kMaxP0 + i); };
   const uint32_t bar_p0_done = bar_base + 8u * (kBarP0 + 2 * kMaxP0);
-  const uint32_t bar_job_done = bar_base + 8u * (kBarP0 + 2 * kMaxP0 + 1);
-  const uint32_t tmem_slot = bar_base + 8u * (kBarP0 + 2 * kMaxP0 + 2);
+  auto bar_job_done = [&](int j) { return bar_base + 8u * (kBarP0 + 2 * kMaxP0 + 1 + j); };  // unit j of this pair
+  const uint32_t tmem_slot = bar_base + 8u * (kBarP0 + 2 * kMaxP0 + 1 + kMaxJobUnits);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
   auto stage_a = [&](int s) { return smem_base + (uint32_t)(s * p.stage_bytes); };
   auto stage_b = [&](int s, int a) { return smem_base + (uint32_t)(s * p.stage_bytes + kAOff + a * p.b_bytes); };
@@ -231,11 +233,17 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   const int n_p0 = kSide ? n_main : 0;  // side-product steps: one per 64 contraction elements
   const bool p0_m128 = p.p0_rows <= 64;
   // dA/dB job of this pair (kJob): unit, whether it is a dA unit, first column of this CTA's 64, contraction steps
+  // (unit j of this pair is global unit pair + j * n_pairs; units [0, job_units_a) are dA column tiles, the rest dB)
   const bool job_on = kJob && pair < p.job_units;
-  const bool job_is_a = pair < p.job_units_a;
-  const int job_col0 = (job_is_a ? pair : pair - p.job_units_a) * kBM + (int)rank * 64;
+  const int job_mine = job_on ? (p.job_units - pair + n_pairs - 1) / n_pairs : 0;  // 1 or 2 (kMaxJobUnits)
+  auto job_unit_is_a = [&](int j) { return pair + j * n_pairs < p.job_units_a; };
+  auto job_unit_col0 = [&](int j) {
+    const int u = pair + j * n_pairs;
+    return (u < p.job_units_a ? u : u - p.job_units_a) * kBM + (int)rank * 64;
+  };
   const int job_steps = (int)((p.T + 63) / 64);
-  const uint32_t job_col = p0_col - (uint32_t)p.r_pad;  // TMEM columns [job_col, job_col + r_pad / 2)
+  // TMEM columns of unit j: [p0_col - (j + 1) * r_pad, + r_pad / 2)
+  auto job_col = [&](int j) { return p0_col - (uint32_t)((j + 1) * p.r_pad); };
   // grid-wide counter: generation before anybody of this launch can have arrived (read by the one thread that waits)
   const int n_ctas = (int)gridDim.x;
   // accumulators of a tile that hold at least one real token (all roles derive it the same way)
@@ -260,8 +268,10 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       ptx::tma_prefetch_desc(&map_p0w);
     }
     if (kJob) {
-      ptx::tma_prefetch_desc(job_is_a ? &jm.m_a : &jm.m_b);
-      ptx::tma_prefetch_desc(job_is_a ? &jm.v_a : &jm.v_b);
+      ptx::tma_prefetch_desc(&jm.m_a);
+      ptx::tma_prefetch_desc(&jm.v_a);
+      ptx::tma_prefetch_desc(&jm.m_b);
+      ptx::tma_prefetch_desc(&jm.v_b);
     }
     ptx::tma_prefetch_desc(&map_act);
     if (p.r > 0) ptx::tma_prefetch_desc(&map_lora);
@@ -280,7 +290,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         ptx::mbar_init(bar_p0_empty(i), 1);  // multicast tcgen05.commit
       }
       ptx::mbar_init(bar_p0_done, 1);
-      ptx::mbar_init(bar_job_done, 1);
+      for (int j = 0; j < kMaxJobUnits; ++j) ptx::mbar_init(bar_job_done(j), 1);
     }
     for (int a = 0; a < kMaxAcc; ++a) ptx::mbar_init(bar_acc_empty(a), 2 * 4);  // epilogue warps of both CTAs
     for (int b = 0; b < p.n_stg; ++b) {
@@ -406,17 +416,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         ptx::griddep_wait();
         // (the peer CTA's thread has issued nothing so far: the ring is the side product's until its last MMA is done)
         if (rank != 0) ptx::mbar_wait(bar_p0_done, 0);
-        const CUtensorMap* map_m = job_is_a ? &jm.m_a : &jm.m_b;
-        const CUtensorMap* map_v = job_is_a ? &jm.v_a : &jm.v_b;
-        if (job_is_a) {  // dt^T is being written by every CTA of the grid in this very launch
-          const long long t_start = clock64();
-          unsigned gen;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(p.sync + 1) : "memory");
-            if (clock64() - t_start > 4000000000LL) __trap();
-          } while (gen == gen0);
-          asm volatile("fence.proxy.async;" ::: "memory");
-        }
+        bool gen_seen = false;
         int ld_s = n_p0 % p.p0_slots;
         uint32_t ld_par = 1u ^ (uint32_t)((n_p0 / p.p0_slots) & 1);
         mm_s = ld_s;
@@ -424,30 +424,53 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         // M = 128 over the pair: 64 columns per CTA = one MN-major atom [64 tokens x 128 bytes]; N = r_pad; K = tokens
         const uint32_t idesc_job = ptx::make_idesc_f16(std::is_same<ActT, __nv_bfloat16>::value, /*a_mn_major=*/true,
                                                        /*b_mn_major=*/false, kBM, p.r_pad);
+        const int total = job_mine * job_steps;  // the units of this pair, one after the other through the same ring
         int ld = 0, mm = 0;
-        while (ld < job_steps || (rank == 0 && mm < job_steps)) {
-          if (ld < job_steps && ptx::mbar_try_wait(bar_p0_empty(ld_s), ld_par)) {
+        int ld_j = 0, ld_i = 0, mm_j = 0, mm_i = 0;  // (unit, step inside the unit) of the next load / MMA group
+        while (ld < total || (rank == 0 && mm < total)) {
+          if (ld < total && ptx::mbar_try_wait(bar_p0_empty(ld_s), ld_par)) {
+            const bool is_a = job_unit_is_a(ld_j);
+            if (is_a && !gen_seen) {  // dt^T is being written by every CTA of the grid in this very launch
+              const long long t_start = clock64();
+              unsigned gen;
+              do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(p.sync + 1) : "memory");
+                if (clock64() - t_start > 4000000000LL) __trap();
+              } while (gen == gen0);
+              asm volatile("fence.proxy.async;" ::: "memory");
+              gen_seen = true;
+            }
             const uint32_t dst = p0_slot(ld_s);
             if (rank == 0) ptx::mbar_arrive_expect_tx(bar_p0_full(ld_s), (uint32_t)(2 * (kJobBox + p.la_bytes)));
             const uint32_t leader_bar = ptx::mapa(bar_p0_full(ld_s), 0);
-            ptx::tma_load_2d_pair(map_m, dst, leader_bar, job_col0, ld * 64);
-            ptx::tma_load_2d_pair(map_v, dst + (uint32_t)kJobBox, leader_bar, ld * 64, (int)rank * (p.r_pad >> 1));
+            ptx::tma_load_2d_pair(is_a ? &jm.m_a : &jm.m_b, dst, leader_bar, job_unit_col0(ld_j), ld_i * 64);
+            ptx::tma_load_2d_pair(is_a ? &jm.v_a : &jm.v_b, dst + (uint32_t)kJobBox, leader_bar, ld_i * 64,
+                                  (int)rank * (p.r_pad >> 1));
             ++ld;
+            if (++ld_i == job_steps) {
+              ld_i = 0;
+              ++ld_j;
+            }
             if (++ld_s == p.p0_slots) {
               ld_s = 0;
               ld_par ^= 1u;
             }
           }
-          if (rank == 0 && mm < job_steps && ptx::mbar_try_wait(bar_p0_full(mm_s), mm_par)) {
+          if (rank == 0 && mm < total && ptx::mbar_try_wait(bar_p0_full(mm_s), mm_par)) {
             ptx::tc_fence_after();
             const uint64_t ma = ptx::make_smem_desc_sw128(p0_slot(mm_s), 8192, 1024);
             const uint64_t va = ptx::make_smem_desc_sw128(p0_slot(mm_s) + (uint32_t)kJobBox, 16, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)  // 16 tokens: 16 rows of 128 bytes (A), 32 bytes inside a row (B)
-              ptx::umma_ss_pair(tmem_d + job_col, ma + k * (2048u >> 4), va + k * (32u >> 4), idesc_job, (mm | k) != 0 ? 1u : 0u);
+              ptx::umma_ss_pair(tmem_d + job_col(mm_j), ma + k * (2048u >> 4), va + k * (32u >> 4), idesc_job,
+                                (mm_i | k) != 0 ? 1u : 0u);
             ptx::umma_commit_pair(bar_p0_empty(mm_s));
-            if (mm == job_steps - 1) ptx::umma_commit_pair(bar_job_done);  // -> epilogue warps, both CTAs
             ++mm;
+            if (++mm_i == job_steps) {  // unit complete -> epilogue warps, both CTAs
+              ptx::umma_commit_pair(bar_job_done(mm_j));
+              mm_i = 0;
+              ++mm_j;
+            }
             if (++mm_s == p.p0_slots) {
               mm_s = 0;
               mm_par ^= 1u;
@@ -692,28 +715,31 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         }
       }
       if (kJob && job_on && item + n_pairs >= n_items) {
-        // dA/dB job of this pair: its 64 columns x r_pad accumulator (M = 128 layout: lanes 0..63 hold the first half
-        // of the r_pad columns of rows 0..63, lanes 64..127 the second half) -- written while the last tile's MMAs run
-        ptx::mbar_wait(bar_job_done, 0);
-        ptx::tc_fence_after();
-        const int L = quad * 32 + lane;
-        const int64_t col = job_col0 + (L & 63);
-        const int jh = (L >> 6) * (p.r_pad >> 1);
-        const int64_t C = job_is_a ? p.K : p.N;
-        uint32_t v[16];
-        ptx::tmem_ld_32x32b_x16(lane_base + job_col, v);
-        ptx::tmem_ld_wait();
-        if (col < C) {
-          if (job_is_a) {  // dA[j, col]: per j the warp writes 32 consecutive elements
-            ActT* o = static_cast<ActT*>(p.job_da) + col;
+        // dA/dB units of this pair: 64 columns x r_pad accumulators (M = 128 layout: lanes 0..63 hold the first half of
+        // the r_pad columns of rows 0..63, lanes 64..127 the second half) -- written while the last tile's MMAs run
+        for (int j = 0; j < job_mine; ++j) {
+          ptx::mbar_wait(bar_job_done(j), 0);
+          ptx::tc_fence_after();
+          const bool is_a = job_unit_is_a(j);
+          const int L = quad * 32 + lane;
+          const int64_t col = job_unit_col0(j) + (L & 63);
+          const int jh = (L >> 6) * (p.r_pad >> 1);
+          const int64_t C = is_a ? p.K : p.N;
+          uint32_t v[16];
+          ptx::tmem_ld_32x32b_x16(lane_base + job_col(j), v);
+          ptx::tmem_ld_wait();
+          if (col < C) {
+            if (is_a) {  // dA[j, col]: per j the warp writes 32 consecutive elements
+              ActT* o = static_cast<ActT*>(p.job_da) + col;
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (e < (p.r_pad >> 1) && jh + e < p.r) o[(int64_t)(jh + e) * p.K] = from_f32<ActT>(__uint_as_float(v[e]));
-          } else {         // dB[col, j]: this thread's half row
-            ActT* o = static_cast<ActT*>(p.job_db) + col * p.r + jh;
+              for (int e = 0; e < 16; ++e)
+                if (e < (p.r_pad >> 1) && jh + e < p.r) o[(int64_t)(jh + e) * p.K] = from_f32<ActT>(__uint_as_float(v[e]));
+            } else {     // dB[col, j]: this thread's half row
+              ActT* o = static_cast<ActT*>(p.job_db) + col * p.r + jh;
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (e < (p.r_pad >> 1) && jh + e < p.r) o[e] = from_f32<ActT>(p.scale * __uint_as_float(v[e]));
+              for (int e = 0; e < 16; ++e)
+                if (e < (p.r_pad >> 1) && jh + e < p.r) o[e] = from_f32<ActT>(p.scale * __uint_as_float(v[e]));
+            }
           }
         }
       }
@@ -1251,9 +1277,11 @@ static Tc2Choice choose_tc2_uncached(const LayerArgs& a, bool backward, int n_pa
                                           reinterpret_cast<uintptr_t>(a.job_dtt)) & 15u) == 0;
     Tc2Choice best_c = c;
     double best_cost = 1e300;
-    for (int with_job = job_ok ? 1 : 0; with_job >= 0; --with_job) {
+    // candidates: the job with one unit per pair, with two (more column tiles than pairs: N + K > 128 * pairs, the
+    // 8192-wide MLP layers -- each unit has its own block of accumulator columns), and no job at all
+    for (int upp = job_ok ? kMaxJobUnits : 0; upp >= 0; --upp) {
       Tc2Choice k = c;
-      const int cols = c.rp * (1 + with_job);  // accumulator columns set aside
+      const int cols = c.rp * (1 + upp);  // accumulator columns set aside
       k.plan = plan_tc2(a.T, OUT, RED, a.r, tmem_a, n_pairs, /*allow_split=*/false, cols);
       forced(cols, k.plan);
       if (k.plan.cfg.N_acc <= 0) continue;
@@ -1263,11 +1291,12 @@ static Tc2Choice choose_tc2_uncached(const LayerArgs& a, bool backward, int n_pa
       const int64_t units = ceil_div64(a.K, kBM) + ceil_div64(a.N, kBM);
       // the job streams all T tokens through ONE pair per 128 columns at ~900 cycles per 64 tokens: it has to end
       // before the pair's last tile does (C640 at T = 8192: 115 k cycles of job against 21 k of GEMM -- 50 us, measured)
-      const double job_cyc = 900.0 * (double)ceil_div64(a.T, 64);
-      if (with_job && (units > k.pairs || job_cyc > 0.85 * k.plan.cfg.cost)) continue;
+      const double job_cyc = 900.0 * (double)ceil_div64(a.T, 64) * upp;
+      if (upp > 0 && (units > (int64_t)upp * k.pairs || (upp > 1 && units <= k.pairs) || job_cyc > 0.85 * k.plan.cfg.cost))
+        continue;
       k.p0_rows = (int)rows;
-      k.job = with_job != 0;
-      const double cost = 1.08 * k.plan.cfg.cost + (with_job ? 0.0 : dab_cyc);
+      k.job = upp != 0;
+      const double cost = 1.08 * k.plan.cfg.cost + (upp ? 0.0 : dab_cyc);
       if (cost < best_cost) {
         best_cost = cost;
         best_c = k;
