@@ -5,15 +5,21 @@ Workload (BASELINE.json configs[0], the configuration the metric is quoted on): 
 3072x3072 + LoRA r=16, forward + backward (dX, dA, dB) on 4096 tokens per GPU, bf16.  One "step" is one
 forward+backward pass of that layer over one batch of synthetic activations.
 
-  value     whole-job TFLOP/s with inputs resident in HBM, CUDA-event timed, max over ranks
+  value     whole-job TFLOP/s with inputs resident in HBM, CUDA-event timed, max over ranks; a step is TWO launches
+            (forward / backward, the adapter's side products and dA, dB inside them), replayed from CUDA graphs that
+            hold a round of four steps each
   e2e       same metric through the module API with HOST (pinned) inputs: H2D of x, dy every step (uploaded on a copy
             stream one step ahead), D2H of dA, dB every step (consumed by the host one step behind)
-  roofline  the dominant kernel (fused NF4-decode tcgen05 GEMM, forward + backward launches) timed alone
+  roofline  the two launches of the step (fused NF4-decode tcgen05 GEMM with the adapter inside) timed alone through the
+            C ABI; the NF4-only launches beside them
   cpu_baseline  the oracle port (oracle/qlora_oracle.py) on the host cores, bounded sample, rank 0 at N=1 only
 
-  extra     rank 0: NF4 quantize/pack GB/s; few-token (T = 2) weight-stream GB/s, HBM-cold; the layer census of an
-            AuraFlow step (N = 1).  All ranks: `auraflow_qlora_step_dp`, the AuraFlow-6.8B QLoRA step harness
-            (tools/auraflow_step.py: steps/s, samples/s, exposed all-reduce time) -- the second half of BASELINE's metric.
+  extra     rank 0: NF4 quantize/pack GB/s (one tensor, and the whole AuraFlow weight set = BASELINE configs[1]);
+            few-token (T = 2) weight-stream GB/s, HBM-cold; at N = 1 the layer censuses of an AuraFlow / Lumina2 / SDXL
+            step (configs[3], [2], [4]), sibling projections as one launch (projection_groups), the Lumina2 step
+            harness and the AuraFlow step with SDPA.  All ranks: `auraflow_qlora_step_dp`, the AuraFlow-6.8B QLoRA step
+            harness (tools/auraflow_step.py: steps/s, samples/s, exposed all-reduce time) -- the second half of
+            BASELINE's metric.
 
 `--impl reference` times the reference's CPU path for the same layer (the oracle port: bitsandbytes itself is
 not installable here) on the host cores.  Multi-GPU: weak scaling, each rank steps its own 4096 tokens and the

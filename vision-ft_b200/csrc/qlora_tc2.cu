@@ -1110,6 +1110,10 @@ struct Tc2Plan {
 // epilogue; a split item instead writes its fp32 partial tile (one 128-byte store per token and warp: ~50 cycles per
 // token, measured) and a second small launch adds the slices (~5 k cycles of launch + the slices at ~1.5 KB per cycle
 // out of L2), so the split pays for few tokens only (adaLN / modulation layers, text-token projections).
+// cycles per wave that do not scale with the tile: pipeline fill + the part of the accumulator drain the next tile cannot
+// hide.  Fitted on 9216 x 2304 at T = 4352 (forward): 7 waves of 2 x 160 tokens run 143.2 us, 6 waves of 2 x 192 run
+// 135.5 us -- 5-7 k cycles per wave more than the 2500 of fill alone.
+constexpr double kWaveFixed = 7000.0;
 static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a, int n_pairs, bool allow_split = true,
                         int rp = 0) {
   Tc2Plan best = {};
@@ -1145,7 +1149,7 @@ static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a,
       //  is split, i.e. the order of the fp32 sums -- must not depend on r, so that a layer whose lora_up is still zero
       //  returns exactly what the bare base layer returns: /root/reference/tests/test_peft.py:98-101)
       (void)r;
-      const double cost = waves * (k_per * step + 2500.0 + epi);
+      const double cost = waves * (k_per * step + kWaveFixed + epi);
       if (cost < best_cost * 0.999 || (cost < best_cost * 1.001 && N_acc > best.cfg.N_acc)) {
         best_cost = cost;
         best.cfg = {n_acc, N_acc, max_stages(tmem_a, n_acc, N_acc, rp), cost};
