@@ -768,7 +768,8 @@ def test_quantize_many_is_bit_identical_to_per_tensor_calls(ops, dt):
     """vft_nf4_quantize_many: 96 tensors per launch, chunk index space across tensors; ragged / tiny / empty tensors take
     the generic tail.  Codes and absmax must equal the per-tensor entry bit for bit (and through it the oracle)."""
     g = torch.Generator(device="cuda").manual_seed(5)
-    shapes = [(3072, 16), (64, 64), (1, 1), (0,), (1000, 3), (256, 1024), (2048, 640), (33, 64)] + [(128, 8 * (i % 5 + 1)) for i in range(100)]
+    shapes = ([(3072, 16), (64, 64), (1, 1), (0,), (1000, 3), (256, 1024), (2048, 640), (33, 64)]
+              + [(128, 8 * (i % 5 + 1)) for i in range(100)] + [(32, 64)] * 200)  # 200 of one size: more than one launch of 96
     ws = [(torch.randn(*s, generator=g, device="cuda") * 0.02).to(dt) if len(s) > 1 or s[0] else torch.empty(0, device="cuda", dtype=dt)
           for s in shapes]
     ws[5][:64].zero_()  # all-zero blocks
