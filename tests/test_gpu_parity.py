@@ -718,7 +718,8 @@ def test_one_call_backward(ops, vft_env, T, K, N, r, job):
              "dB": s * dy.double().t() @ t_truth, "dt": dt_truth, "tt": t_truth.t(), "t": t_truth}
     rel = lambda a, b: float((a - b).norm() / b.norm())
     for res in results:
-        assert torch.equal(res["tt"], res["t"].t()), "t^T must be the transposed copy of t_save, bit for bit"
+        if L.vft_workspace_bytes(_cabi.OP_BWD_DX, T, N, K, r) == 0:  # (a split backward never reads t^T: not written then)
+            assert torch.equal(res["tt"], res["t"].t()), "t^T must be the transposed copy of t_save, bit for bit"
         for k, lim in (("dx", 4e-3), ("dA", 6e-3), ("dB", 6e-3), ("dt", 4e-3), ("t", 4e-3)):
             assert rel(res[k], truth[k]) <= lim, (k, rel(res[k], truth[k]))
     for k in ("dx", "dA", "dB"):

@@ -250,7 +250,9 @@ int vft_qlora_fwd(const void* x, int64_t T, const uint8_t* packed, const float* 
                                           : side_mma() ? mma_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st)
                                                        : tc_lora_down(x, lora_a, T, K, r, act_dtype, t_save, st);
     if (rc != VFT_OK) return rc;
-    if (a.tt_save != nullptr) {  // t^T for the backward's dA/dB job: the fused launch writes it itself
+    // t^T for the backward's dA/dB job (the fused launch writes it itself).  A backward whose contraction is split keeps
+    // its side kernels and never reads it (choose_tc2: the plan does not depend on r or on the workspace): no launch then
+    if (a.tt_save != nullptr && tc2_workspace_bytes(T, N, K, r, /*backward=*/true) == 0) {
       rc = simt_lora_tt(t_save, T, r, act_dtype, a.tt_save, st);
       if (rc != VFT_OK) return rc;
     }
