@@ -18,8 +18,10 @@ g = torch.randn(T, N, device=dev, dtype=torch.bfloat16)
 y = torch.empty(T, N, device=dev, dtype=torch.bfloat16)
 dx = torch.empty(T, K, device=dev, dtype=torch.bfloat16)
 st = torch.cuda.current_stream().cuda_stream
+wfb, wbb = _cabi.lib.vft_workspace_bytes(_cabi.OP_FWD, T, N, K, 0), _cabi.lib.vft_workspace_bytes(_cabi.OP_BWD_DX, T, N, K, 0)
+wf = torch.empty(max(wfb, 4), dtype=torch.uint8, device=dev); wb = torch.empty(max(wbb, 4), dtype=torch.uint8, device=dev)
 for _ in range(reps):
-    _cabi.check(_cabi.lib.vft_qlora_fwd(x.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, None, 0, 0.0, y.data_ptr(), None, None, None, None, 0, TC, TA, st))
-    _cabi.check(_cabi.lib.vft_qlora_bwd_dx(g.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, 0, 0.0, dx.data_ptr(), None, None, None, 0, TC, TA, st))
+    _cabi.check(_cabi.lib.vft_qlora_fwd(x.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, None, 0, 0.0, y.data_ptr(), None, None, None, wf.data_ptr() if wfb else None, wfb, TC, TA, st))
+    _cabi.check(_cabi.lib.vft_qlora_bwd_dx(g.data_ptr(), T, packed.data_ptr(), absmax.data_ptr(), N, K, 64, 2, 2, None, None, 0, 0.0, dx.data_ptr(), None, None, wb.data_ptr() if wbb else None, wbb, TC, TA, st))
 torch.cuda.synchronize()
 print("ok")
