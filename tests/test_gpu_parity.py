@@ -294,7 +294,7 @@ def test_pair_kernel_forced_tiles(ops, vft_env, nacc, T, K, N, r, bias, tiled):
 # of both pitches (more than 128 staged rows per CTA), above a single accumulator -- on ragged token counts, with the
 # reference's shipped rank 4, rank 16 and a rank that needs 32 padded columns; and forced off, where the side kernel
 # of lora_tc.cu must give the same t_save up to summation order.
-@pytest.mark.parametrize("nacc", ["1x32", "2x48", "1x176", "2x160", "2x176", "1x256", "auto"])
+@pytest.mark.parametrize("nacc", ["1x32", "2x48", "1x176", "2x160", "2x176", "2x192", "1x256", "auto"])  # 2x192: 192 + 176 tokens
 @pytest.mark.parametrize("T,K,N,r,bias", [(700, 256, 640, 16, True), (333, 64, 264, 4, False), (1500, 320, 512, 24, False),
                                            (4096, 192, 768, 16, False)])
 def test_pair_kernel_fused_down_projection(ops, vft_env, nacc, T, K, N, r, bias):

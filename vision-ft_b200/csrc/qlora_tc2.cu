@@ -94,6 +94,7 @@ struct Tc2Params {
   const void* lora_w;  // forward: B [N, r]; backward: A [r, K]
   void* out;           // forward: Y [T, N]; backward: dX [T, K]
   int n_acc, N_acc;    // accumulators per tile, tokens per accumulator (multiple of 16, <= 256)
+  int N_acc1;          // tokens of accumulator 1 (= N_acc, or narrower: the forward's side product then sits behind it)
   int stages;
   int n_stg;        // output staging tiles (2..16): as many as fit, so that the accumulators drain at the epilogue
                     // warps' speed while the TMA stores trickle out under the next tile's main loop
@@ -199,7 +200,9 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   const int S = p.stages;
   const int n_pairs = (int)(gridDim.x >> 1);
   const int pair = (int)(blockIdx.x >> 1);
-  const int tok_tile = p.n_acc * p.N_acc;
+  const int tok_tile = p.N_acc + (p.n_acc == 2 ? p.N_acc1 : 0);
+  auto nacc_of = [&](int a) { return a == 0 ? p.N_acc : p.N_acc1; };   // tokens of accumulator a
+  auto tok_off = [&](int a) { return a == 0 ? 0 : p.N_acc; };          // its first token inside the tile
 
   // shared memory: [S stages: decoded weight tile | n_acc activation boxes][epilogue staging][barriers, TMEM slot]
   // (side product: [p0_slots x (activation rows | rank-r operand box)] between the ring and the staging tiles; its
@@ -229,7 +232,8 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   auto p0_slot = [&](int i) { return p0_base + (uint32_t)(i * p.p0_slot_bytes); };
   // TMEM columns of the side product: the tail of accumulator 0's pitch (two accumulators: N_acc <= pitch - r_pad)
   // or, with one accumulator, the tail of the second pitch
-  const uint32_t p0_col = (uint32_t)((p.n_acc == 2 ? 1 : 2) * kAccCols - p.r_pad);
+  // (two accumulators of equal width: the tail of pitch 0; one accumulator, or a narrower second one: of pitch 1)
+  const uint32_t p0_col = (uint32_t)((p.n_acc == 2 && p.N_acc1 == p.N_acc ? 1 : 2) * kAccCols - p.r_pad);
   const int n_p0 = kSide ? n_main : 0;  // side-product steps: one per 64 contraction elements
   const bool p0_m128 = p.p0_rows <= 64;
   // dA/dB job of this pair (kJob): unit, whether it is a dA unit, first column of this CTA's 64, contraction steps
@@ -249,7 +253,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   // accumulators of a tile that hold at least one real token (all roles derive it the same way)
   auto accs_of = [&](int64_t t0) -> int {
     const int64_t left = p.T - t0;
-    return left >= tok_tile ? p.n_acc : (int)((left + p.N_acc - 1) / p.N_acc);
+    return left >= tok_tile ? p.n_acc : (left > p.N_acc ? 2 : 1);
   };
 
   // work items: item -> (tile, split) -> ring steps [b0, b1) of that tile (step n_main = the adapter step)
@@ -353,7 +357,8 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             if (rank == 0) ptx::mbar_arrive_expect_tx(bar_full(s), (uint32_t)(2 * na * p.b_bytes));
             const uint32_t leader_bar = ptx::mapa(bar_full(s), 0);
             for (int a = 0; a < na; ++a) {
-              const int trow = (int)(t0 + (int64_t)a * p.N_acc) + (int)rank * (p.N_acc >> 1);
+              // (the box always has N_acc / 2 rows; a narrower accumulator 1 ignores the rows past its own half)
+              const int trow = (int)(t0 + tok_off(a)) + (int)rank * (nacc_of(a) >> 1);
               if (b < n_main)
                 ptx::tma_load_2d_pair(&map_act, stage_b(s, a), leader_bar, b * kBK, trow);
               else
@@ -489,6 +494,8 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
     if (rank == 0) {
       const uint32_t idesc = ptx::make_idesc_f16(std::is_same<ActT, __nv_bfloat16>::value,
                                                  /*a_mn_major=*/kBackward, /*b_mn_major=*/false, 2 * kBM, p.N_acc);
+      const uint32_t idesc1 = ptx::make_idesc_f16(std::is_same<ActT, __nv_bfloat16>::value,
+                                                  /*a_mn_major=*/kBackward, /*b_mn_major=*/false, 2 * kBM, p.N_acc1);
       // advance 16 contraction elements: 32 B inside a K-major swizzle row, 16 rows (2048 B) MN-major
       constexpr uint32_t kAStep = kBackward ? (2048u >> 4) : (32u >> 4);
       constexpr uint32_t kBStep = 32u >> 4;
@@ -518,8 +525,9 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
           // forward: A = TMEM stage s, 8 columns (16 packed 16-bit values per lane) per MMA
           const uint32_t a_tmem = tmem_d + (uint32_t)(kTmemACol0 + 32 * s);
           auto mma = [&](uint32_t d, int k, uint64_t b_desc, uint32_t accumulate) {
-            if (kTmemA) ptx::umma_ts_pair(d, a_tmem + (uint32_t)(8 * k), b_desc + k * kBStep, idesc, accumulate);
-            else ptx::umma_ss_pair(d, a_desc + k * kAStep, b_desc + k * kBStep, idesc, accumulate);
+            const uint32_t id = d == tmem_d ? idesc : idesc1;
+            if (kTmemA) ptx::umma_ts_pair(d, a_tmem + (uint32_t)(8 * k), b_desc + k * kBStep, id, accumulate);
+            else ptx::umma_ss_pair(d, a_desc + k * kAStep, b_desc + k * kBStep, id, accumulate);
           };
           if (ptx::elect_one()) {
             if (do_mma) {
@@ -586,15 +594,16 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         const int na = accs_of(t0);
         const int64_t feat0 = (int64_t)(tile % p.n_fblk) * (2 * kBM) + (int64_t)rank * kBM;
         for (int a = 0; a < na; ++a) {
-          const int64_t ta = t0 + (int64_t)a * p.N_acc;
-          for (int c0 = 0; c0 < p.N_acc && ta + c0 < p.T; c0 += 32, ++chunk) {
+          const int64_t ta = t0 + tok_off(a);
+          const int na_cols = nacc_of(a);
+          for (int c0 = 0; c0 < na_cols && ta + c0 < p.T; c0 += 32, ++chunk) {
             const uint32_t b = sb;
             ptx::mbar_wait(bar_stg_full(b), sphase);
             if (feat0 < OUT && !(p.debug & 4)) {
               // the staged tile is two halves [32 tokens][64 features] (128-byte rows, SWIZZLE_128B); a chunk cut
               // short by N_acc (a multiple of 16) leaves through the 16-token boxes
               const uint32_t src = stg + b * (uint32_t)kStgBytes;
-              const CUtensorMap* m = (c0 + 32 <= p.N_acc) ? &map_out : &map_out16;
+              const CUtensorMap* m = (c0 + 32 <= na_cols) ? &map_out : &map_out16;
               ptx::tma_store_2d(m, src, (int)feat0, (int)(ta + c0));
               if (feat0 + 64 < OUT) ptx::tma_store_2d(m, src + 4096u, (int)feat0 + 64, (int)(ta + c0));
             }
@@ -765,22 +774,23 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         // 256 features per row (a warp's 32 lanes = 32 consecutive features: 128-byte stores)
         float* slice = p.partial + (int64_t)item * tok_tile * (2 * kBM) + (int)rank * kBM + quad * 32 + lane;
         for (int a = 0; a < na; ++a) {
-          const int64_t ta = t0 + (int64_t)a * p.N_acc;
+          const int64_t ta = t0 + tok_off(a);
+          const int na_cols = nacc_of(a);
 #pragma unroll 1
-          for (int c0 = 0; c0 < p.N_acc; c0 += 16) {  // (N_acc is a multiple of 16)
+          for (int c0 = 0; c0 < na_cols; c0 += 16) {  // (a multiple of 16)
             const bool live = ta + c0 < p.T;  // warp-uniform; dead chunks still release the accumulator below
             uint32_t v0[16];  // lane = feature, registers = 16 consecutive token columns
             if (live) {
               ptx::tmem_ld_32x32b_x16(lane_base + (uint32_t)(a * kAccCols + c0), v0);
               ptx::tmem_ld_wait();
             }
-            if (c0 + 16 >= p.N_acc) {  // accumulator a is in registers / not needed: the issuer may overwrite it
+            if (c0 + 16 >= na_cols) {  // accumulator a is in registers / not needed: the issuer may overwrite it
               ptx::tc_fence_before();
               __syncwarp();
               if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar_acc_empty(a), 0));
             }
             if (!live || (p.debug & 4)) continue;
-            float* row = slice + (int64_t)(a * p.N_acc + c0) * (2 * kBM);
+            float* row = slice + (int64_t)(tok_off(a) + c0) * (2 * kBM);
 #pragma unroll
             for (int e = 0; e < 16; ++e)
               if (ta + c0 + e < p.T) __stcg(row + e * (2 * kBM), __uint_as_float(v0[e]));
@@ -796,9 +806,10 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
         // drain from 7.1 k to 3.4 k cycles on the epilogue warp's clock and left the launch where it was (58.0 us with,
         // 58.2 us without): every CTA of the grid drains at the same moment, and 13 MB of output leave in one burst.
         for (int a = 0; a < na; ++a) {
-          const int64_t ta = t0 + (int64_t)a * p.N_acc;
+          const int64_t ta = t0 + tok_off(a);
+          const int na_cols = nacc_of(a);
 #pragma unroll 1
-          for (int c0 = 0; c0 < p.N_acc; c0 += 32) {
+          for (int c0 = 0; c0 < na_cols; c0 += 32) {
             const bool live = ta + c0 < p.T;  // warp-uniform; dead chunks still release the accumulator below
             // 16x256b: mma-style fragments -- r[4q], r[4q+1] = (lane t/4, tokens 8q + 2(t%4), +1); r[4q+2], r[4q+3] = lane + 8
             uint32_t v0[16], v1[16];  // lanes 0..15 / 16..31 of the quadrant, 32 token columns
@@ -807,7 +818,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
               ptx::tmem_ld_16x256b_x4(lane_base + (16u << 16) + (uint32_t)(a * kAccCols + c0), v1);
               ptx::tmem_ld_wait();
             }
-            if (c0 + 32 >= p.N_acc) {  // accumulator a is in registers / not needed: the issuer may overwrite it
+            if (c0 + 32 >= na_cols) {  // accumulator a is in registers / not needed: the issuer may overwrite it
               ptx::tc_fence_before();
               __syncwarp();
               if (lane == 0) ptx::mbar_arrive_cluster(acc_empty_leader + 8u * (uint32_t)a);
@@ -1076,6 +1087,8 @@ qlora_tc2_finalize_kernel(const float* __restrict__ partial, const ActT* __restr
 struct Tc2Config {
   int n_acc, N_acc, stages;
   double cost;
+  int N_acc1 = 0;  // tokens of accumulator 1 when it is narrower than accumulator 0 (0: the same)
+  int tok() const { return n_acc == 2 ? N_acc + (N_acc1 > 0 ? N_acc1 : N_acc) : N_acc; }
 };
 
 // Cycle model per pipeline step (one CTA): tensor pipe 2*N_acc cycles per accumulator (M = 256 over the pair,
@@ -1133,13 +1146,11 @@ static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a,
   double best_cost = 1e300;
   const int n_main = (int)ceil_div64(RED, kBK);
   const int64_t n_f = ceil_div64(OUT, 2 * kBM);
-  for (int n_acc = 1; n_acc <= kMaxAcc; ++n_acc) {
-    for (int N_acc = 32; N_acc <= 256; N_acc += 16) {
-      if (!config_ok(tmem_a, n_acc, N_acc, rp)) continue;
+  auto consider = [&](int n_acc, int N_acc, int N_acc1) {  // N_acc1 = 0: both accumulators N_acc wide
       const int b_bytes = (N_acc / 2) * 128;
-      const int64_t tok = (int64_t)n_acc * N_acc;
+      const int64_t tok = n_acc == 2 ? N_acc + (N_acc1 > 0 ? N_acc1 : N_acc) : N_acc;
       const int64_t tiles = n_f * ceil_div64(T, tok);
-      const double mma = 2.0 * N_acc * n_acc;
+      const double mma = 2.0 * (double)tok;
       const double smem = ((tmem_a ? 0.0 : kATileBytes * (1.0 + n_acc)) + 2.0 * n_acc * b_bytes) / 128.0;
       double step = mma > smem ? mma : smem;
       if (step < 620.0) step = 620.0;
@@ -1163,15 +1174,23 @@ static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a,
       //  returns exactly what the bare base layer returns: /root/reference/tests/test_peft.py:98-101)
       (void)r;
       const double cost = waves * (k_per * step + kWaveFixed + epi);
-      if (cost < best_cost * 0.999 || (cost < best_cost * 1.001 && N_acc > best.cfg.N_acc)) {
+      if (cost < best_cost * 0.999 || (cost < best_cost * 1.001 && tok > best.cfg.tok())) {
         best_cost = cost;
-        best.cfg = {n_acc, N_acc, max_stages(tmem_a, n_acc, N_acc, rp), cost};
+        best.cfg = {n_acc, N_acc, max_stages(tmem_a, n_acc, N_acc, rp), cost, N_acc1};
         best.n_tiles = (int)tiles;
         best.n_split = split;
         best.k_per = k_per;
         best.ws_bytes = split > 1 ? ws : 0;
       }
-    }
+  };
+  for (int n_acc = 1; n_acc <= kMaxAcc; ++n_acc)
+    for (int N_acc = 32; N_acc <= 256; N_acc += 16)
+      if (config_ok(tmem_a, n_acc, N_acc, rp)) consider(n_acc, N_acc, 0);
+  // forward with its side product inside: accumulator 0 keeps the full pitch, accumulator 1 gives up the rp columns
+  // (2 x 176 tokens per tile is 300 tiles = 5 waves at T = 8720, 3072 features; 192 + 176 is 288 = 4 waves)
+  if (tmem_a && rp > 0 && !allow_split) {
+    const int pitch = AccLayout<true>::pitch;
+    if (max_stages(tmem_a, 2, pitch, rp) >= kGroups) consider(2, pitch, pitch - rp);
   }
   return best;
 }
@@ -1264,9 +1283,14 @@ static Tc2Choice choose_tc2_uncached(const LayerArgs& a, bool backward, int n_pa
     if (ev.tc2_force_na <= 0) return false;
     int na = ev.tc2_force_na, nn = ev.tc2_force_nn;
     if (tmem_a && na == 2 && nn > AccLayout<true>::pitch) nn = AccLayout<true>::pitch;
-    if (!config_ok(tmem_a, na, nn, rp)) return false;
-    plan.cfg = {na, nn, max_stages(tmem_a, na, nn, rp), plan.cfg.cost};
-    plan.n_tiles = (int)(ceil_div64(OUT, 2 * kBM) * ceil_div64(a.T, (int64_t)na * nn));
+    int nn1 = 0;
+    if (tmem_a && rp > 0 && na == 2 && nn == AccLayout<true>::pitch && max_stages(tmem_a, na, nn, rp) >= kGroups) {
+      nn1 = nn - rp;  // "2x192" with a side product inside: accumulator 1 gives up the columns
+    } else if (!config_ok(tmem_a, na, nn, rp)) {
+      return false;
+    }
+    plan.cfg = {na, nn, max_stages(tmem_a, na, nn, rp), plan.cfg.cost, nn1};
+    plan.n_tiles = (int)(ceil_div64(OUT, 2 * kBM) * ceil_div64(a.T, (int64_t)plan.cfg.tok()));
     plan.n_split = 1;
     plan.k_per = (int)ceil_div64(RED, kBK);
     plan.ws_bytes = 0;
@@ -1374,6 +1398,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   p.out = out;
   p.n_acc = cfg.n_acc;
   p.N_acc = cfg.N_acc;
+  p.N_acc1 = cfg.N_acc1 > 0 ? cfg.N_acc1 : cfg.N_acc;
   p.stages = cfg.stages;
   p.side = rp > 0 ? 1 : 0;
   p.r_pad = rp > 0 ? rp : 16;
@@ -1407,7 +1432,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   p.b_bytes = (cfg.N_acc / 2) * 128;
   p.stage_bytes = (kTmemA ? 0 : kATileBytes) + cfg.n_acc * p.b_bytes;
   p.n_fblk = (int)ceil_div64(OUT, 2 * kBM);
-  p.n_tiles = p.n_fblk * (int)ceil_div64(a.T, (int64_t)cfg.n_acc * cfg.N_acc);
+  p.n_tiles = p.n_fblk * (int)ceil_div64(a.T, (int64_t)cfg.tok());
   p.n_split = 1;
   p.k_per = (int)ceil_div64(RED, kBK);
   p.partial = nullptr;
@@ -1501,7 +1526,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
     fc.attrs = attr + 1;  // programmatic stream serialization only: its launch latency hides under the GEMM's tail
     fc.numAttrs = pdl_enabled() ? 1 : 0;
     VFT_CUDA_OK(cudaLaunchKernelEx(&fc, qlora_tc2_finalize_kernel<ActT>, static_cast<const float*>(p.partial),
-                                   static_cast<const ActT*>(p.bias), a.T, OUT, cfg.n_acc * cfg.N_acc, p.n_fblk, p.n_split,
+                                   static_cast<const ActT*>(p.bias), a.T, OUT, cfg.tok(), p.n_fblk, p.n_split,
                                    static_cast<ActT*>(out)));
     VFT_CUDA_OK(cudaGetLastError());
   }
