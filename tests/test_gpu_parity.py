@@ -294,7 +294,7 @@ def test_pair_kernel_forced_tiles(ops, vft_env, nacc, T, K, N, r, bias, tiled):
 # of both pitches (more than 128 staged rows per CTA), above a single accumulator -- on ragged token counts, with the
 # reference's shipped rank 4, rank 16 and a rank that needs 32 padded columns; and forced off, where the side kernel
 # of lora_tc.cu must give the same t_save up to summation order.
-@pytest.mark.parametrize("nacc", ["1x32", "2x48", "1x176", "2x160", "2x176", "2x192", "1x256", "auto"])  # 2x192: 192 + 176 tokens
+@pytest.mark.parametrize("nacc", ["1x32", "1x32pp", "2x48", "1x176", "1x160pp", "2x160", "2x176", "2x192", "1x256", "auto"])  # 2x192: 192 + 176 tokens
 @pytest.mark.parametrize("T,K,N,r,bias", [(700, 256, 640, 16, True), (333, 64, 264, 4, False), (1500, 320, 512, 24, False),
                                            (4096, 192, 768, 16, False)])
 def test_pair_kernel_fused_down_projection(ops, vft_env, nacc, T, K, N, r, bias):
@@ -306,7 +306,9 @@ def test_pair_kernel_fused_down_projection(ops, vft_env, nacc, T, K, N, r, bias)
     packed, absmax = torch.from_numpy(p).cuda(), torch.from_numpy(am).cuda()
     t_saves = []
     for fuse in ("1", "0"):
-        vft_env(VFT_TC2="1", VFT_TC2_FUSE=fuse, VFT_TC2_NACC=None if nacc == "auto" else nacc)
+        pp = nacc.endswith("pp")  # "1x32pp": one accumulator per tile, alternating pitches (ping-pong)
+        vft_env(VFT_TC2="1", VFT_TC2_FUSE=fuse, VFT_TC2_NACC=None if nacc == "auto" else nacc.replace("pp", ""),
+                VFT_TC2_PINGPONG="1" if pp else None)
         out, used = _run_cuda(ops, packed, absmax, x, dy, a, b, bv, 1.0, N, K, torch.bfloat16, TC, tiled=True)
         assert used == TC
         _check(out, ref, truth, ("y", "dx", "da", "db"), f"fused{fuse}-{nacc}-T{T}K{K}N{N}r{r}")
@@ -332,10 +334,12 @@ def test_pair_kernel_fused_down_projection(ops, vft_env, nacc, T, K, N, r, bias)
     assert qlora_oracle.max_abs(t_saves[0][:, :rp], t_saves[1][:, :rp]) <= 2 * BF16_ULP * float(t_truth.abs().max())
 
 
+@pytest.mark.parametrize("pingpong", [None, "1"])
 @pytest.mark.parametrize("stages", ["4", "5", "8"])
-def test_pair_kernel_many_tiles_per_pair(ops, vft_env, stages):
-    """More tiles than SM pairs with a tiny tile (1x32): every pair walks several tiles, ring phases wrap many times."""
-    vft_env(VFT_TC2="1", VFT_TC2_NACC="1x32", VFT_TC2_STAGES=stages)
+def test_pair_kernel_many_tiles_per_pair(ops, vft_env, stages, pingpong):
+    """More tiles than SM pairs with a tiny tile (1x32): every pair walks several tiles, ring phases wrap many times;
+    with VFT_TC2_PINGPONG=1 consecutive tiles of a pair alternate between the two accumulator pitches."""
+    vft_env(VFT_TC2="1", VFT_TC2_NACC="1x32", VFT_TC2_STAGES=stages, VFT_TC2_PINGPONG=pingpong)
     N, K, T = 1024, 320, 2500
     g = torch.Generator(device="cuda").manual_seed(5)
     w = (torch.randn(N, K, generator=g, device="cuda") * 0.02).to(torch.bfloat16)

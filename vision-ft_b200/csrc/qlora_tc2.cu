@@ -77,7 +77,7 @@ constexpr int kTmemCols = 512;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kMaxStg = 16;  // output staging tiles
 constexpr int kMaxJobUnits = 2;  // dA/dB column tiles one pair can take (each in its own block of r_pad TMEM columns)
-constexpr int kBarBytes = (2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg + 2 * kMaxP0 + 1 + kMaxJobUnits) * 8 + 16;
+constexpr int kBarBytes = (2 * kMaxStages + 2 * kMaxAcc + 2 * kMaxStg + 2 * kMaxP0 + 1 + kMaxJobUnits) * 8 + 16;
 constexpr int kJobBox = 64 * 128;  // dA/dB job: one [64 tokens x 64 columns] box of x / dy per CTA and ring step
 constexpr int kStgBytes = 32 * kBM * 2;  // one staging tile [32 tokens][128 features] of 16-bit outputs (8 KB)
 constexpr int kEpiBytes = 2 * kStgBytes;  // the minimum: two tiles
@@ -94,6 +94,8 @@ struct Tc2Params {
   const void* lora_w;  // forward: B [N, r]; backward: A [r, K]
   void* out;           // forward: Y [T, N]; backward: dX [T, K]
   int n_acc, N_acc;    // accumulators per tile, tokens per accumulator (multiple of 16, <= 256)
+  int pingpong;        // one accumulator per tile (n_acc == 1), tile i of a pair in accumulator i & 1: the drain of a tile
+                       // runs under the next tile's contraction (short contractions, several tiles per pair)
   int N_acc1;          // tokens of accumulator 1 (= N_acc, or narrower: the forward's side product then sits behind it)
   int stages;
   int n_stg;        // output staging tiles (2..16): as many as fit, so that the accumulators drain at the epilogue
@@ -213,14 +215,15 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
   const uint32_t bar_base = smem_base + (uint32_t)(S * p.stage_bytes + p0_bytes + epi_bytes);
   auto bar_full = [&](int s) { return bar_base + 8u * s; };
   auto bar_empty = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
-  const uint32_t bar_acc_full = bar_base + 8u * (2 * kMaxStages);
-  auto bar_acc_empty = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 1 + a); };
+  // accumulators: full[i] (ping-pong: accumulator i; otherwise full[0] for the whole tile) / empty[a]
+  auto bar_acc_full = [&](int i) { return bar_base + 8u * (2 * kMaxStages + i); };
+  auto bar_acc_empty = [&](int a) { return bar_base + 8u * (2 * kMaxStages + kMaxAcc + a); };
   // output staging tiles: full[b] (the four epilogue warps have written tile b) / empty[b] (its TMA store has read it)
-  auto bar_stg_full = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc + b); };
-  auto bar_stg_empty = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 1 + kMaxAcc + kMaxStg + b); };
+  auto bar_stg_full = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 2 * kMaxAcc + b); };
+  auto bar_stg_empty = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 2 * kMaxAcc + kMaxStg + b); };
   // side product: full / empty per ring slot (same protocol as the main ring: bytes of both CTAs are counted on the
   // leader's barrier, a multicast commit frees the slot in both) and "done" (multicast commit behind its last MMA)
-  constexpr int kBarP0 = 2 * kMaxStages + 1 + kMaxAcc + 2 * kMaxStg;
+  constexpr int kBarP0 = 2 * kMaxStages + 2 * kMaxAcc + 2 * kMaxStg;
   auto bar_p0_full = [&](int i) { return bar_base + 8u * (kBarP0 + i); };
   auto bar_p0_empty = [&](int i) { return bar_base + 8u * (kBarP0 + kMaxP0 + i); };
   const uint32_t bar_p0_done = bar_base + 8u * (kBarP0 + 2 * kMaxP0);
@@ -287,7 +290,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       ptx::mbar_init(bar_full(s), 1 + 2 * 4);  // leader's producer (expect_tx) + the decode warps of both CTAs
       ptx::mbar_init(bar_empty(s), 1);         // multicast tcgen05.commit
     }
-    ptx::mbar_init(bar_acc_full, 1);
+    for (int a = 0; a < kMaxAcc; ++a) ptx::mbar_init(bar_acc_full(a), 1);
     if (kSide) {
       for (int i = 0; i < p.p0_slots; ++i) {
         ptx::mbar_init(bar_p0_full(i), 1);   // the leader's producer (expect_tx for both CTAs)
@@ -502,16 +505,20 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
       const int k_lora = (p.r + 15) / 16;
       const bool do_mma = !(p.debug & 2);
       int g = 0, s = 0;
-      uint32_t full_par = 0, acc_par = 1;
-      for (int item = pair; item < n_items; item += n_pairs) {
+      uint32_t full_par = 0, acc_par = 1, it_local = 0;
+      for (int item = pair; item < n_items; item += n_pairs, ++it_local) {
         const int tile = item_tile(item);
         const int64_t t0 = (int64_t)(tile / p.n_fblk) * tok_tile;
         const int na = accs_of(t0);
         const int b0 = item_b0(item), b1 = item_b1(item);
+        // ping-pong: this item's accumulator, and the parity of ITS "drained" barrier (it is used by every other item)
+        const int ab = p.pingpong ? (int)(it_local & 1u) : 0;
+        const uint32_t d_base = tmem_d + (uint32_t)(ab * kAccCols);
         for (int b = b0; b < b1; ++b, ++g) {
           ptx::mbar_wait(bar_full(s), full_par);
-          if (b == b0) {  // the epilogue must have drained the accumulators of the previous work item
-            for (int a = 0; a < na; ++a) ptx::mbar_wait(bar_acc_empty(a), acc_par);
+          if (b == b0) {  // the epilogue must have drained the accumulators this work item writes
+            if (p.pingpong) ptx::mbar_wait(bar_acc_empty(ab), ((it_local >> 1) & 1u) ^ 1u);
+            else for (int a = 0; a < na; ++a) ptx::mbar_wait(bar_acc_empty(a), acc_par);
           }
           ptx::tc_fence_after();
           tl_mark(p, 0, g);
@@ -525,7 +532,7 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
           // forward: A = TMEM stage s, 8 columns (16 packed 16-bit values per lane) per MMA
           const uint32_t a_tmem = tmem_d + (uint32_t)(kTmemACol0 + 32 * s);
           auto mma = [&](uint32_t d, int k, uint64_t b_desc, uint32_t accumulate) {
-            const uint32_t id = d == tmem_d ? idesc : idesc1;
+            const uint32_t id = d == d_base ? idesc : idesc1;
             if (kTmemA) ptx::umma_ts_pair(d, a_tmem + (uint32_t)(8 * k), b_desc + k * kBStep, id, accumulate);
             else ptx::umma_ss_pair(d, a_desc + k * kAStep, b_desc + k * kBStep, id, accumulate);
           };
@@ -533,20 +540,20 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             if (do_mma) {
               if (b < n_main) {
 #pragma unroll
-                for (int k = 0; k < kBK / 16; ++k) mma(tmem_d, k, b_desc0, k > 0 ? 1u : acc0);
+                for (int k = 0; k < kBK / 16; ++k) mma(d_base, k, b_desc0, k > 0 ? 1u : acc0);
                 if (na > 1) {
 #pragma unroll
-                  for (int k = 0; k < kBK / 16; ++k) mma(tmem_d + kAccCols, k, b_desc1, k > 0 ? 1u : acc0);
+                  for (int k = 0; k < kBK / 16; ++k) mma(d_base + kAccCols, k, b_desc1, k > 0 ? 1u : acc0);
                 }
               } else {  // adapter step: ceil(r / 16) MMAs per accumulator
-                for (int k = 0; k < k_lora; ++k) mma(tmem_d, k, b_desc0, k > 0 ? 1u : acc0);
+                for (int k = 0; k < k_lora; ++k) mma(d_base, k, b_desc0, k > 0 ? 1u : acc0);
                 if (na > 1) {
-                  for (int k = 0; k < k_lora; ++k) mma(tmem_d + kAccCols, k, b_desc1, k > 0 ? 1u : acc0);
+                  for (int k = 0; k < k_lora; ++k) mma(d_base + kAccCols, k, b_desc1, k > 0 ? 1u : acc0);
                 }
               }
             }
             ptx::umma_commit_pair(bar_empty(s));  // the stage is reusable in both CTAs once these MMAs have read it
-            if (b == b1 - 1) ptx::umma_commit_pair(bar_acc_full);  // item complete -> epilogue warps, both CTAs
+            if (b == b1 - 1) ptx::umma_commit_pair(bar_acc_full(ab));  // item complete -> epilogue warps, both CTAs
           }
           __syncwarp();
           tl_mark(p, 1, g);
@@ -766,7 +773,8 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             bt[(int64_t)j * p.N] = from_f32<ActT>(j < p.r ? p.scale * to_f32<ActT>(brow[j]) : 0.0f);
         }
       }
-      ptx::mbar_wait(bar_acc_full, it & 1u);
+      const int ab = p.pingpong ? (int)(it & 1u) : 0;  // ping-pong: this item's accumulator
+      ptx::mbar_wait(bar_acc_full(ab), p.pingpong ? ((it >> 1) & 1u) : (it & 1u));
       ptx::tc_fence_after();
       if (et == 0) tl_mark(p, 4, 4 * (int)it + 2);
       if (p.n_split > 1) {
@@ -814,14 +822,14 @@ qlora_tc2_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_const
             // 16x256b: mma-style fragments -- r[4q], r[4q+1] = (lane t/4, tokens 8q + 2(t%4), +1); r[4q+2], r[4q+3] = lane + 8
             uint32_t v0[16], v1[16];  // lanes 0..15 / 16..31 of the quadrant, 32 token columns
             if (live) {
-              ptx::tmem_ld_16x256b_x4(lane_base + (uint32_t)(a * kAccCols + c0), v0);
-              ptx::tmem_ld_16x256b_x4(lane_base + (16u << 16) + (uint32_t)(a * kAccCols + c0), v1);
+              ptx::tmem_ld_16x256b_x4(lane_base + (uint32_t)((ab + a) * kAccCols + c0), v0);
+              ptx::tmem_ld_16x256b_x4(lane_base + (16u << 16) + (uint32_t)((ab + a) * kAccCols + c0), v1);
               ptx::tmem_ld_wait();
             }
             if (c0 + 32 >= na_cols) {  // accumulator a is in registers / not needed: the issuer may overwrite it
               ptx::tc_fence_before();
               __syncwarp();
-              if (lane == 0) ptx::mbar_arrive_cluster(acc_empty_leader + 8u * (uint32_t)a);
+              if (lane == 0) ptx::mbar_arrive_cluster(acc_empty_leader + 8u * (uint32_t)(ab + a));
             }
             if (!live) continue;
             const uint32_t buf = epi_smem + sb * (uint32_t)kStgBytes;
@@ -1088,6 +1096,7 @@ struct Tc2Config {
   int n_acc, N_acc, stages;
   double cost;
   int N_acc1 = 0;  // tokens of accumulator 1 when it is narrower than accumulator 0 (0: the same)
+  int pingpong = 0;  // n_acc == 1: consecutive tiles of a pair alternate between the two accumulator pitches
   int tok() const { return n_acc == 2 ? N_acc + (N_acc1 > 0 ? N_acc1 : N_acc) : N_acc; }
 };
 
@@ -1146,7 +1155,7 @@ static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a,
   double best_cost = 1e300;
   const int n_main = (int)ceil_div64(RED, kBK);
   const int64_t n_f = ceil_div64(OUT, 2 * kBM);
-  auto consider = [&](int n_acc, int N_acc, int N_acc1) {  // N_acc1 = 0: both accumulators N_acc wide
+  auto consider = [&](int n_acc, int N_acc, int N_acc1, int pp = 0) {  // N_acc1 = 0: both accumulators N_acc wide
       const int b_bytes = (N_acc / 2) * 128;
       const int64_t tok = n_acc == 2 ? N_acc + (N_acc1 > 0 ? N_acc1 : N_acc) : N_acc;
       const int64_t tiles = n_f * ceil_div64(T, tok);
@@ -1173,10 +1182,16 @@ static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a,
       //  is split, i.e. the order of the fp32 sums -- must not depend on r, so that a layer whose lora_up is still zero
       //  returns exactly what the bare base layer returns: /root/reference/tests/test_peft.py:98-101)
       (void)r;
-      const double cost = waves * (k_per * step + kWaveFixed + epi);
+      double cost = waves * (k_per * step + kWaveFixed + epi);
+      if (pp) {
+        // ping-pong: a tile's drain and the next tile's fill run under the contraction; what is left per tile is the
+        // commit / barrier round trip, and one fill + one drain per launch.  Needs several tiles per pair and no split.
+        if (split > 1 || waves < 2.0) return;
+        cost = waves * (k_per * step + 1500.0) + kWaveFixed + epi;
+      }
       if (cost < best_cost * 0.999 || (cost < best_cost * 1.001 && tok > best.cfg.tok())) {
         best_cost = cost;
-        best.cfg = {n_acc, N_acc, max_stages(tmem_a, n_acc, N_acc, rp), cost, N_acc1};
+        best.cfg = {n_acc, N_acc, max_stages(tmem_a, n_acc, N_acc, rp), cost, N_acc1, pp};
         best.n_tiles = (int)tiles;
         best.n_split = split;
         best.k_per = k_per;
@@ -1186,6 +1201,14 @@ static Tc2Plan plan_tc2(int64_t T, int64_t OUT, int64_t RED, int r, bool tmem_a,
   for (int n_acc = 1; n_acc <= kMaxAcc; ++n_acc)
     for (int N_acc = 32; N_acc <= 256; N_acc += 16)
       if (config_ok(tmem_a, n_acc, N_acc, rp)) consider(n_acc, N_acc, 0);
+  // one accumulator per tile, alternating between the two pitches (same column budget per pitch as two accumulators).
+  // OFF unless VFT_TC2_PINGPONG=1: measured on the short-K SDXL layers it was meant for, the planner's choices with
+  // it ran SLOWER than two accumulators sharing every decoded tile (10240 x 1280 at T = 2048 forward 66.7 vs 54.8 us,
+  // 5120 x 640 at T = 8192 75.3 vs 63.9 us, 640 x 2560 backward 41.2 vs 32.8 us): halving the tokens per decoded tile
+  // costs more decode than the hidden drain wins back.  Kept as a tested schedule (tests force it), not as a default.
+  if (env().tc2_pingpong == 1)
+    for (int N_acc = 32; N_acc <= 256; N_acc += 16)
+      if (config_ok(tmem_a, 2, N_acc, rp)) consider(1, N_acc, 0, 1);
   // forward with its side product inside: accumulator 0 keeps the full pitch, accumulator 1 gives up the rp columns
   // (2 x 176 tokens per tile is 300 tiles = 5 waves at T = 8720, 3072 features; 192 + 176 is 288 = 4 waves)
   if (tmem_a && rp > 0 && !allow_split) {
@@ -1290,6 +1313,7 @@ static Tc2Choice choose_tc2_uncached(const LayerArgs& a, bool backward, int n_pa
       return false;
     }
     plan.cfg = {na, nn, max_stages(tmem_a, na, nn, rp), plan.cfg.cost, nn1};
+    plan.cfg.pingpong = (na == 1 && ev.tc2_pingpong == 1 && config_ok(tmem_a, 2, nn, rp)) ? 1 : 0;  // triage: force it
     plan.n_tiles = (int)(ceil_div64(OUT, 2 * kBM) * ceil_div64(a.T, (int64_t)plan.cfg.tok()));
     plan.n_split = 1;
     plan.k_per = (int)ceil_div64(RED, kBK);
@@ -1399,6 +1423,7 @@ static int launch_tc2(const LayerArgs& a, const void* act, void* out, void* lora
   p.n_acc = cfg.n_acc;
   p.N_acc = cfg.N_acc;
   p.N_acc1 = cfg.N_acc1 > 0 ? cfg.N_acc1 : cfg.N_acc;
+  p.pingpong = cfg.n_acc == 1 ? cfg.pingpong : 0;
   p.stages = cfg.stages;
   p.side = rp > 0 ? 1 : 0;
   p.r_pad = rp > 0 ? rp : 16;

@@ -78,6 +78,7 @@ void VftEnv::load() {
   }
   tc2_nosplit = is("VFT_TC2_NOSPLIT", '1');
   tc2_fuse = num("VFT_TC2_FUSE", -1);
+  tc2_pingpong = num("VFT_TC2_PINGPONG", -1);
   tc2_job = num("VFT_TC2_JOB", -1);
   tc2_p0kb = num("VFT_TC2_P0KB", 0);
 }

@@ -119,6 +119,7 @@ struct VftEnv {
   int tc2_force_na = 0, tc2_force_nn = 0;                   // VFT_TC2_NACC="<n_acc>x<N_acc>"
   bool tc2_nosplit = false;                                 // VFT_TC2_NOSPLIT=1
   int tc2_p0kb = 0;   // VFT_TC2_P0KB: shared memory (KB) of the side product's ring (default 40)
+  int tc2_pingpong = -1;  // VFT_TC2_PINGPONG=1: let the planner alternate accumulators between the tiles of a pair (off by default: measured slower)
   int tc2_job = -1;   // VFT_TC2_JOB=0: adapter weight gradients by vft_lora_bwd_dab's kernel, not inside the backward launch
   int tc2_fuse = -1;  // VFT_TC2_FUSE=1: adapter down-projection fused into the forward launch whenever the shape
                       // allows it (never splits the contraction); otherwise a side kernel (see fuse_rank())
