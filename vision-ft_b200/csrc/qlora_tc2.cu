@@ -18,6 +18,12 @@
 //     -> global) while the decode warps and the MMA issuer are already on tile i+1; the issuer only waits for
 //     "accumulator a drained" before its first MMA into a.
 //
+//   * (round 2) The adapter rides the same launch: the rank-r side product (x . A^T / s * dy . B) is computed by every CTA
+//     for its share of the token rows next to the first tile's main loop (kSide), the adapter's weight gradients as a
+//     column-tile job behind it in the backward (kJob) -- two launches per layer step.  The forward also knows an
+//     asymmetric tile (192 + 176 tokens) so that the side product's columns do not cost a wave; few-token problems
+//     split the contraction into per-item fp32 slices that a dependent launch adds in split order.
+//
 // Warp roles (768 threads per CTA, both CTAs of a pair run all roles except the MMA issuer):
 //   warp 20     TMA producer: for every stage, n_acc boxes [N_acc/2 tokens x 64] of the activations
 //               (SWIZZLE_128B); completion bytes of BOTH CTAs are counted on the leader's barrier
