@@ -622,6 +622,45 @@ def run_gpu_arm(args):
         except Exception as e:  # pragma: no cover - reported, not hidden
             extra["few_token_weight_stream"] = {"error": f"{type(e).__name__}: {e}"}
 
+    # (the censuses run BEFORE the step harnesses: ten seconds of whole-model steps leave the GPU heat-soaked and under its
+    #  power cap, and the per-layer timings that follow then read 3-10 % slower than the same library measured by
+    #  tools/census.py alone -- profiles/README.md)
+    if rank == 0 and world == 1 and not args.no_census:
+        # second half of BASELINE's metric: every NF4(+LoRA) Linear of one AuraFlow-6.8B QLoRA training step (per-GPU
+        # batch 2 at 1024^2, LoRA r=16 on attention + MLP projections, gradient checkpointing = forward twice), each at
+        # its own token count, timed through the C ABI (tools/census.py).  Attention, norms and the optimizer are not
+        # part of the hot path and are not included: this bounds steps/s from above.
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import census
+
+            ms, avg_tf, _ = census.model_step(census.auraflow(2), dev)
+            extra["auraflow_qlora_step_linear_layers"] = {
+                "ms_per_step": ms, "steps_per_s_upper_bound": 1e3 / ms, "avg_tflops": avg_tf,
+                "frac_of_measured_bf16_peak": avg_tf / peaks["bf16_tflops"], "per_gpu_batch": 2,
+                "note": "322 quantized Linears, forward x2 (checkpointing) + backward; data-parallel ranks step independently"}
+            # BASELINE configs[2] and [4]: the same census for Lumina2 NextDiT-2.6B (batch 1, 1024^2) and the SDXL UNet
+            # transformer Linears (batch 2, 1024^2: small K, 77-token cross-attention projections)
+            for key, layers, what in (("lumina2_qlora_step_linear_layers", census.lumina2(1), "178 quantized Linears of NextDiT-2.6B, batch 1"),
+                                      ("sdxl_qlora_step_linear_layers", census.sdxl(2), "SDXL UNet attention/FF Linears (C = 640, 1280), batch 2")):
+                ms, avg_tf, _ = census.model_step(layers, dev)
+                extra[key] = {"ms_per_step": ms, "avg_tflops": avg_tf, "frac_of_measured_bf16_peak": avg_tf / peaks["bf16_tflops"],
+                              "note": what + "; forward x2 (checkpointing) + backward, each layer at its own token count"}
+        except Exception as e:  # pragma: no cover - reported, not hidden
+            extra["auraflow_qlora_step_linear_layers"] = {"error": f"{type(e).__name__}: {e}"}
+        try:  # SURVEY 8f-2: sibling projections as one launch (vft_b200/group.py), module API, forward + backward
+            import group_probe
+
+            rows = [group_probe.time_case(nm, k, ns, t, r, verbose=False) for nm, k, ns, t, r in (
+                ("sdxl C1280 attn1 to_q/k/v", 1280, [1280] * 3, 2048, 4), ("sdxl C1280 attn1 to_q/k/v", 1280, [1280] * 3, 2048, 16),
+                ("sdxl C640 attn1 to_q/k/v", 640, [640] * 3, 8192, 4), ("sdxl C1280 attn2 to_k/v (2 x 77 text tokens)", 2048, [1280] * 2, 154, 4))]
+            extra["projection_groups"] = {
+                "cases": [{**r_, "speedup": r_["members_us"] / r_["group_us"]} for r_ in rows],
+                "note": "q/k/v (k/v) LoRALinear-over-Linear4bit siblings, forward + backward through the module API in a CUDA graph: "
+                        "one launch per member vs one ProjectionGroup launch per direction; LoRA rank 4 is the reference's shipped rank"}
+        except Exception as e:  # pragma: no cover - reported, not hidden
+            extra["projection_groups"] = {"error": f"{type(e).__name__}: {e}"}
+
     if not args.no_aura_step:
         # second half of BASELINE's metric, measured as a job: the AuraFlow-6.8B QLoRA step over the Linear skeleton of
         # the MMDiT (tools/auraflow_step.py: module API, 322 NF4 Linears, LoRA r=16, checkpointing, fused AdamW,
@@ -659,42 +698,6 @@ def run_gpu_arm(args):
             except Exception as e:  # pragma: no cover - reported, not hidden
                 extra["lumina2_qlora_step"] = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.empty_cache()
-
-    if rank == 0 and world == 1 and not args.no_census:
-        # second half of BASELINE's metric: every NF4(+LoRA) Linear of one AuraFlow-6.8B QLoRA training step (per-GPU
-        # batch 2 at 1024^2, LoRA r=16 on attention + MLP projections, gradient checkpointing = forward twice), each at
-        # its own token count, timed through the C ABI (tools/census.py).  Attention, norms and the optimizer are not
-        # part of the hot path and are not included: this bounds steps/s from above.
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import census
-
-            ms, avg_tf, _ = census.model_step(census.auraflow(2), dev)
-            extra["auraflow_qlora_step_linear_layers"] = {
-                "ms_per_step": ms, "steps_per_s_upper_bound": 1e3 / ms, "avg_tflops": avg_tf,
-                "frac_of_measured_bf16_peak": avg_tf / peaks["bf16_tflops"], "per_gpu_batch": 2,
-                "note": "322 quantized Linears, forward x2 (checkpointing) + backward; data-parallel ranks step independently"}
-            # BASELINE configs[2] and [4]: the same census for Lumina2 NextDiT-2.6B (batch 1, 1024^2) and the SDXL UNet
-            # transformer Linears (batch 2, 1024^2: small K, 77-token cross-attention projections)
-            for key, layers, what in (("lumina2_qlora_step_linear_layers", census.lumina2(1), "178 quantized Linears of NextDiT-2.6B, batch 1"),
-                                      ("sdxl_qlora_step_linear_layers", census.sdxl(2), "SDXL UNet attention/FF Linears (C = 640, 1280), batch 2")):
-                ms, avg_tf, _ = census.model_step(layers, dev)
-                extra[key] = {"ms_per_step": ms, "avg_tflops": avg_tf, "frac_of_measured_bf16_peak": avg_tf / peaks["bf16_tflops"],
-                              "note": what + "; forward x2 (checkpointing) + backward, each layer at its own token count"}
-        except Exception as e:  # pragma: no cover - reported, not hidden
-            extra["auraflow_qlora_step_linear_layers"] = {"error": f"{type(e).__name__}: {e}"}
-        try:  # SURVEY 8f-2: sibling projections as one launch (vft_b200/group.py), module API, forward + backward
-            import group_probe
-
-            rows = [group_probe.time_case(nm, k, ns, t, r, verbose=False) for nm, k, ns, t, r in (
-                ("sdxl C1280 attn1 to_q/k/v", 1280, [1280] * 3, 2048, 4), ("sdxl C1280 attn1 to_q/k/v", 1280, [1280] * 3, 2048, 16),
-                ("sdxl C640 attn1 to_q/k/v", 640, [640] * 3, 8192, 4), ("sdxl C1280 attn2 to_k/v (2 x 77 text tokens)", 2048, [1280] * 2, 154, 4))]
-            extra["projection_groups"] = {
-                "cases": [{**r_, "speedup": r_["members_us"] / r_["group_us"]} for r_ in rows],
-                "note": "q/k/v (k/v) LoRALinear-over-Linear4bit siblings, forward + backward through the module API in a CUDA graph: "
-                        "one launch per member vs one ProjectionGroup launch per direction; LoRA rank 4 is the reference's shipped rank"}
-        except Exception as e:  # pragma: no cover - reported, not hidden
-            extra["projection_groups"] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         cpu = None
